@@ -1,0 +1,1009 @@
+// locohd_capi.cu — implementation of the C ABI declared in include/locohd_b200.h.
+// Host-side orchestration only: validation (LoCoHD::build, locohd.rs:289-389), device memory, stream
+// ordering and the launch sequence K0 -> K1 -> scan -> K1' -> K2.  No CPU fallback exists: every entry point
+// needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "locohd_kernels.cuh"
+
+using namespace locohd;
+
+namespace {
+std::mutex g_err_mutex;
+std::string g_global_err;
+}
+
+struct locohd_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    bool has_params = false;
+    KParams kp{};
+    int n_categories = 0;
+    // device-side parameter storage
+    double* d_cat_w = nullptr;
+    double* d_cat_sw = nullptr;
+    WfDev* d_wfs = nullptr;
+    uint64_t* d_tag_pairs = nullptr;
+    double* d_sqrt_tbl = nullptr;
+    double* d_rsqrt_tbl = nullptr;
+    int* d_err = nullptr;
+    ScanResult* d_scan = nullptr;
+    // per-kernel-group event timing
+    bool prof_on = false;
+    struct ProfRec { int group; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+};
+
+namespace {
+// Brackets the launches issued in its scope with a pair of events when profiling is enabled.
+struct ProfScope {
+    locohd_ctx* ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int group;
+    ProfScope(locohd_ctx* c, int g) : ctx(c), group(g) {
+        if (!ctx->prof_on) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->prof.push_back({group, a, b});
+    }
+};
+}
+
+struct locohd_structs {
+    locohd_ctx* ctx = nullptr;
+    uint64_t n_structs = 0, n_prims = 0;
+    uint64_t* d_prim_off = nullptr;
+    double* d_xyz = nullptr;
+    uint8_t* d_cat = nullptr;
+    uint32_t* d_tag = nullptr;
+    StructMeta* d_meta = nullptr;
+    float4* d_pf = nullptr;
+    PrimRec* d_pd = nullptr;
+    uint32_t* d_sorted_pos = nullptr;
+    uint32_t* d_cell_start = nullptr;
+    bool cells_valid = false;
+    double cell_threshold = 0.0;
+    StructsView view() const {
+        StructsView v;
+        v.n_structs = n_structs; v.prim_off = d_prim_off; v.xyz = d_xyz; v.cat = d_cat; v.tag = d_tag;
+        v.meta = d_meta; v.pf = d_pf; v.pd = d_pd; v.sorted_pos = d_sorted_pos; v.cell_start = d_cell_start;
+        return v;
+    }
+};
+
+struct locohd_envset {
+    locohd_ctx* ctx = nullptr;
+    uint64_t n_env = 0, total = 0;
+    unsigned max_count = 0;
+    uint64_t* d_off = nullptr;
+    uint32_t* d_count = nullptr;
+    double* d_dist = nullptr;
+    uint8_t* d_cat = nullptr;
+    uint32_t* d_idx = nullptr;
+    EnvView view() const {
+        EnvView v;
+        v.n_env = n_env; v.off = d_off; v.dist = d_dist; v.cat = d_cat; v.idx = d_idx;
+        return v;
+    }
+};
+
+namespace {
+
+int fail(locohd_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else {
+        std::lock_guard<std::mutex> g(g_err_mutex);
+        g_global_err = buf;
+    }
+    return code;
+}
+
+#define CU(ctx, expr)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(ctx, LOCOHD_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e__), __FILE__, \
+                        __LINE__, cudaGetErrorString(e__));                                                   \
+    } while (0)
+
+#define TRY_ST(expr)             \
+    do {                         \
+        int st__ = (expr);       \
+        if (st__) return st__;   \
+    } while (0)
+
+const char* status_text(int code) {
+    switch (code) {
+        case LOCOHD_ERR_LEN_MISMATCH: return "Lists seq and dists must have equal lengths!";
+        case LOCOHD_ERR_FIRST_NOT_ZERO: return "The dists list must start with a distance of 0!";
+        case LOCOHD_ERR_UNKNOWN_CATEGORY: return "Category not found!";
+        case LOCOHD_ERR_ZERO_NORM: return "Zero norm error for a PMF";
+        case LOCOHD_ERR_NEGATIVE_POINT: return "Invalid input value: all weight function inputs must be non-negative!";
+        case LOCOHD_ERR_NAN: return "NaN or non-finite value in the input";
+        case LOCOHD_ERR_EMPTY_ENV: return "Empty environment (non-positive or NaN threshold distance?)";
+        case LOCOHD_ERR_INDEX: return "Anchor or environment index out of range";
+        case LOCOHD_ERR_DMX_SHAPE: return "Expected matrices with the same length";
+        case LOCOHD_ERR_CUDA: return "internal device error";
+        default: return "error";
+    }
+}
+
+// Device allocations are stream-ordered on the context stream.
+template <class T>
+int dev_alloc(locohd_ctx* ctx, T** out, uint64_t n) {
+    *out = nullptr;
+    if (n == 0) n = 1;
+    void* p = nullptr;
+    CU(ctx, cudaMallocAsync(&p, n * sizeof(T), ctx->stream));
+    *out = static_cast<T*>(p);
+    return 0;
+}
+template <class T>
+void dev_free(locohd_ctx* ctx, T*& p) {
+    if (p) cudaFreeAsync((void*)p, ctx->stream);
+    p = nullptr;
+}
+
+bool is_device_ptr(const locohd_ctx* ctx, const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return (at.type == cudaMemoryTypeDevice && at.device == ctx->device) || at.type == cudaMemoryTypeManaged;
+}
+
+// Input array that may be host or device memory: `ptr` is always device-accessible afterwards.
+template <class T>
+struct InBuf {
+    locohd_ctx* ctx = nullptr;
+    const T* ptr = nullptr;
+    T* owned = nullptr;
+    ~InBuf() { if (owned) cudaFreeAsync(owned, ctx->stream); }
+    int load(locohd_ctx* c, const T* src, uint64_t n) {
+        ctx = c;
+        if (!src || n == 0) { ptr = nullptr; return 0; }
+        if (is_device_ptr(c, src)) { ptr = src; return 0; }
+        TRY_ST(dev_alloc(c, &owned, n));
+        CU(c, cudaMemcpyAsync(owned, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+        ptr = owned;
+        return 0;
+    }
+};
+
+// Output array that may be host or device memory.
+template <class T>
+struct OutBuf {
+    locohd_ctx* ctx = nullptr;
+    T* ptr = nullptr;
+    T* owned = nullptr;
+    T* user = nullptr;
+    uint64_t n = 0;
+    ~OutBuf() { if (owned) cudaFreeAsync(owned, ctx->stream); }
+    int prepare(locohd_ctx* c, T* dst, uint64_t count) {
+        ctx = c; user = dst; n = count;
+        if (!dst) { ptr = nullptr; return 0; }
+        if (is_device_ptr(c, dst)) { ptr = dst; return 0; }
+        TRY_ST(dev_alloc(c, &owned, count));
+        ptr = owned;
+        return 0;
+    }
+    int commit() {  // enqueue the device -> host copy when the destination is host memory
+        if (owned && n) CU(ctx, cudaMemcpyAsync(user, owned, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+        return 0;
+    }
+};
+
+int sync_and_check(locohd_ctx* ctx) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    int code = 0;
+    CU(ctx, cudaMemcpy(&code, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (code) {
+        CU(ctx, cudaMemset(ctx->d_err, 0, sizeof(int)));
+        return fail(ctx, code, "%s", status_text(code));
+    }
+    return 0;
+}
+
+int need_params(locohd_ctx* ctx) {
+    if (!ctx) return fail(nullptr, LOCOHD_ERR_BAD_PARAM, "null context");
+    if (!ctx->has_params) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "locohd_ctx_set_params has not been called");
+    return 0;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int small_int_exponent(double v) {
+    if (v >= 0.0 && v <= 64.0 && std::floor(v) == v) return (int)v;
+    return -1;
+}
+
+// WeightFunction::build validation (weight_function.rs:22-93)
+int make_wf(locohd_ctx* ctx, const locohd_weight_function& in, WfDev* out) {
+    WfDev w{};
+    w.kind = in.kind;
+    w.n = in.n_params;
+    w.int_a = w.int_b = -1;
+    w.inv_range = w.inv_norm = 0.0;
+    if (in.n_params < 0 || in.n_params > LOCOHD_MAX_WF_PARAMS)
+        return fail(ctx, LOCOHD_ERR_BAD_PARAM, "weight function with %d parameters (max %d)", in.n_params,
+                    LOCOHD_MAX_WF_PARAMS);
+    for (int i = 0; i < in.n_params; ++i) w.p[i] = in.params[i];
+    const double* p = in.params;
+    switch (in.kind) {
+        case LOCOHD_WF_HYPER_EXP: {
+            if (in.n_params % 2 != 0)
+                return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"hyper_exp\" there must be an even number of parameters!");
+            double norm = 0.0;
+            for (int i = 0; i < in.n_params; ++i)
+                if (!(p[i] > 0.0))
+                    return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"hyper_exp\" all parameters must be positive!");
+            for (int i = 0; i < in.n_params / 2; ++i) norm += p[i];
+            w.inv_norm = 1.0 / norm;
+            break;
+        }
+        case LOCOHD_WF_DAGUM:
+            if (in.n_params != 3)
+                return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"dagum\" there must be exactly 3 parameters!");
+            if (p[0] < 0.0 || p[1] < 0.0 || p[2] < 0.0)
+                return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"dagum\" all parameters must be positive!");
+            break;
+        case LOCOHD_WF_UNIFORM:
+            if (in.n_params != 2)
+                return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"uniform\" there must be exactly 2 parameters!");
+            if (p[0] < 0.0) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"uniform\" the first parameter must be non-negative!");
+            if (p[1] <= 0.0) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"uniform\" the second parameter must be positive!");
+            if (!(p[0] < p[1])) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"uniform\" the first parameter must be smaller than the second!");
+            w.inv_range = 1.0 / (p[1] - p[0]);
+            break;
+        case LOCOHD_WF_KUMARASWAMY:
+            if (in.n_params != 4)
+                return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"kumaraswamy\" there must be exactly 4 parameters!");
+            if (p[0] < 0.0) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"kumaraswamy\" the first parameter must be non-negative!");
+            if (p[1] <= 0.0 || p[2] <= 0.0 || p[3] <= 0.0)
+                return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"kumaraswamy\" after the first parameter all parameters must be positive!");
+            if (!(p[0] < p[1])) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"kumaraswamy\" the first parameter must be smaller than the second!");
+            w.inv_range = 1.0 / (p[1] - p[0]);
+            w.int_a = small_int_exponent(p[2]);
+            w.int_b = small_int_exponent(p[3]);
+            break;
+        default:
+            return fail(ctx, LOCOHD_ERR_BAD_PARAM, "No function implemented with kind %d!", in.kind);
+    }
+    *out = w;
+    return 0;
+}
+
+int ensure_cells(locohd_structs* s, double threshold) {
+    locohd_ctx* ctx = s->ctx;
+    if (s->cells_valid && s->cell_threshold == threshold) return 0;
+    { ProfScope ps(ctx, LOCOHD_PROF_CELLS); ctx->launches += launch_build_cells(s->view(), threshold, ctx->stream); }
+    CU(ctx, cudaGetLastError());
+    s->cells_valid = true;
+    s->cell_threshold = threshold;
+    return 0;
+}
+
+int read_scan(locohd_ctx* ctx, ScanResult* host) {
+    CU(ctx, cudaMemcpyAsync(host, ctx->d_scan, sizeof(ScanResult), cudaMemcpyDeviceToHost, ctx->stream));
+    return sync_and_check(ctx);
+}
+
+void destroy_envset(locohd_envset* e) {
+    if (!e) return;
+    locohd_ctx* ctx = e->ctx;
+    DeviceGuard g(ctx->device);
+    dev_free(ctx, e->d_off); dev_free(ctx, e->d_count); dev_free(ctx, e->d_dist); dev_free(ctx, e->d_cat);
+    dev_free(ctx, e->d_idx);
+    delete e;
+}
+
+int alloc_envset_storage(locohd_ctx* ctx, locohd_envset* e, bool keep_indices) {
+    TRY_ST(dev_alloc(ctx, &e->d_dist, e->total));
+    TRY_ST(dev_alloc(ctx, &e->d_cat, e->total));
+    if (keep_indices) TRY_ST(dev_alloc(ctx, &e->d_idx, e->total));
+    return 0;
+}
+
+EnvOut env_out(const locohd_envset* e) {
+    EnvOut o;
+    o.n_env = e->n_env; o.off = e->d_off; o.count = e->d_count; o.dist = e->d_dist; o.cat = e->d_cat; o.idx = e->d_idx;
+    return o;
+}
+
+int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const uint32_t* d_anchor_struct,
+                 const uint32_t* d_anchor_prim, double threshold, int keep_indices, locohd_envset** out) {
+    if (!(threshold > 0.0))  // NaN included: nothing passes `d2 < r*r`, the reference then panics on dists[0]
+        return fail(ctx, LOCOHD_ERR_EMPTY_ENV, "threshold_distance must be positive (got %g): every environment would be empty", threshold);
+    TRY_ST(ensure_cells(s, threshold));
+    locohd_envset* e = new locohd_envset();
+    e->ctx = ctx;
+    e->n_env = n_anchors;
+    auto bail = [&](int st) { destroy_envset(e); return st; };
+    int st;
+    if ((st = dev_alloc(ctx, &e->d_count, n_anchors))) return bail(st);
+    if ((st = dev_alloc(ctx, &e->d_off, n_anchors + 1))) return bail(st);
+    uint64_t* d_block_sums = nullptr;
+    if ((st = dev_alloc(ctx, &d_block_sums, scan_scratch_entries(n_anchors)))) return bail(st);
+    const StructsView sv = s->view();
+    { ProfScope ps(ctx, LOCOHD_PROF_COUNT);
+      ctx->launches += launch_env_count(sv, ctx->kp, n_anchors, d_anchor_struct, d_anchor_prim, threshold, e->d_count,
+                                        ctx->stream); }
+    { ProfScope ps(ctx, LOCOHD_PROF_SCAN);
+      ctx->launches += launch_scan_counts(e->d_count, n_anchors, e->d_off, d_block_sums, ctx->d_scan, ctx->stream); }
+    ScanResult sr{};
+    st = read_scan(ctx, &sr);
+    dev_free(ctx, d_block_sums);
+    if (st) return bail(st);
+    e->total = sr.total;
+    e->max_count = sr.max_count;
+    if ((st = alloc_envset_storage(ctx, e, keep_indices != 0))) return bail(st);
+    { ProfScope ps(ctx, LOCOHD_PROF_FILL);
+      ctx->launches += launch_env_fill(sv, ctx->kp, d_anchor_struct, d_anchor_prim, threshold, env_out(e), sr, ctx->stream); }
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
+    *out = e;
+    return 0;
+}
+
+int run_score(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_pairs,
+              const uint32_t* d_pairs, const locohd_job* d_jobs, const uint64_t* d_job_off, uint64_t n_jobs,
+              uint64_t uniform_n, const uint32_t* d_wf_idx, double* d_out) {
+    ScoreArgs sa{};
+    sa.a = a->view(); sa.b = b->view();
+    sa.n_pairs = n_pairs; sa.pairs = d_pairs; sa.jobs = d_jobs; sa.job_pair_off = d_job_off; sa.n_jobs = n_jobs;
+    sa.uniform_n = uniform_n; sa.wf_idx = d_wf_idx; sa.out = d_out; sa.stage_cap = 0;
+    int n;
+    { ProfScope ps(ctx, LOCOHD_PROF_SCORE); n = launch_score(sa, ctx->kp, a->max_count, b->max_count, ctx->stream); }
+    if (n < 0) return fail(ctx, LOCOHD_ERR_UNSUPPORTED, "shared memory budget exceeded for %d categories", ctx->kp.C);
+    ctx->launches += n;
+    CU(ctx, cudaGetLastError());
+    return 0;
+}
+
+int check_wf_indices(locohd_ctx* ctx, const uint32_t* wf_idx, uint64_t n) {
+    // host-side check only possible for host arrays; device arrays are trusted to be in range
+    if (!wf_idx || is_device_ptr(ctx, wf_idx)) return 0;
+    for (uint64_t i = 0; i < n; ++i)
+        if (wf_idx[i] >= (uint32_t)ctx->kp.n_wf)
+            return fail(ctx, LOCOHD_ERR_BAD_PARAM, "weight function index %u out of range (%d functions)", wf_idx[i], ctx->kp.n_wf);
+    return 0;
+}
+
+}  // namespace
+
+#define API_BEGIN(ctx_expr)                                                                       \
+    locohd_ctx* ctx__ = (ctx_expr);                                                               \
+    if (!ctx__) return fail(nullptr, LOCOHD_ERR_BAD_PARAM, "null context");                      \
+    DeviceGuard guard__(ctx__->device);                                                           \
+    try {
+#define API_END()                                                                                 \
+    } catch (const std::bad_alloc&) {                                                             \
+        return fail(ctx__, LOCOHD_ERR_CUDA, "host out of memory");                               \
+    } catch (const std::exception& ex) {                                                          \
+        return fail(ctx__, LOCOHD_ERR_CUDA, "exception: %s", ex.what());                         \
+    }
+
+extern "C" {
+
+int locohd_abi_version(void) { return LOCOHD_ABI_VERSION; }
+
+int locohd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* locohd_last_error(const locohd_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> g(g_err_mutex);
+    static thread_local std::string copy;
+    copy = g_global_err;
+    return copy.c_str();
+}
+
+int locohd_ctx_create(int device, locohd_ctx** out) {
+    if (!out) return fail(nullptr, LOCOHD_ERR_BAD_PARAM, "null output pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, LOCOHD_ERR_NO_DEVICE,
+                    "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(nullptr, LOCOHD_ERR_NO_DEVICE, "device %d out of range (%d devices)", device, n);
+    DeviceGuard g(device);
+    locohd_ctx* ctx = new locohd_ctx();
+    ctx->device = device;
+    auto bail = [&](cudaError_t ce) {
+        fail(nullptr, LOCOHD_ERR_CUDA, "context creation failed: %s", cudaGetErrorString(ce));
+        delete ctx;
+        return (int)LOCOHD_ERR_CUDA;
+    };
+    cudaError_t ce;
+    if ((ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if ((ce = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) return bail(ce);
+    if ((ce = cudaMemset(ctx->d_err, 0, sizeof(int))) != cudaSuccess) return bail(ce);
+    if ((ce = cudaMalloc(&ctx->d_scan, sizeof(ScanResult))) != cudaSuccess) return bail(ce);
+    if ((ce = cudaMalloc(&ctx->d_sqrt_tbl, kSqrtTableSize * sizeof(double))) != cudaSuccess) return bail(ce);
+    if ((ce = cudaMalloc(&ctx->d_rsqrt_tbl, kSqrtTableSize * sizeof(double))) != cudaSuccess) return bail(ce);
+    std::vector<double> t(kSqrtTableSize), r(kSqrtTableSize);
+    for (int k = 0; k < kSqrtTableSize; ++k) {
+        t[k] = std::sqrt((double)k);
+        r[k] = k ? 1.0 / std::sqrt((double)k) : 0.0;
+    }
+    if ((ce = cudaMemcpy(ctx->d_sqrt_tbl, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce);
+    if ((ce = cudaMemcpy(ctx->d_rsqrt_tbl, r.data(), r.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(ce);
+    *out = ctx;
+    return 0;
+}
+
+void locohd_ctx_destroy(locohd_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_cat_w); cudaFree(ctx->d_cat_sw); cudaFree(ctx->d_wfs); cudaFree(ctx->d_tag_pairs);
+    cudaFree(ctx->d_sqrt_tbl); cudaFree(ctx->d_rsqrt_tbl); cudaFree(ctx->d_err); cudaFree(ctx->d_scan);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void* locohd_ctx_stream(locohd_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+uint64_t locohd_ctx_launch_count(const locohd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int locohd_ctx_synchronize(locohd_ctx* ctx) {
+    API_BEGIN(ctx)
+    return sync_and_check(ctx);
+    API_END()
+}
+
+int locohd_ctx_profile_enable(locohd_ctx* ctx, int on) {
+    API_BEGIN(ctx)
+    ctx->prof_on = on != 0;
+    return 0;
+    API_END()
+}
+
+int locohd_ctx_profile_read(locohd_ctx* ctx, double* ms, uint64_t* launches) {
+    API_BEGIN(ctx)
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& r : ctx->prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.group >= 0 && r.group < LOCOHD_PROF_GROUPS) {
+            if (ms) ms[r.group] += t;
+            if (launches) launches[r.group] += 1;
+        }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+    return 0;
+    API_END()
+}
+
+int locohd_measure_fp64_tflops(locohd_ctx* ctx, double* out_tflops) {
+    API_BEGIN(ctx)
+    if (!out_tflops) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null output");
+    cudaDeviceProp prop;
+    CU(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    double* scratch = nullptr;
+    TRY_ST(dev_alloc(ctx, &scratch, 1));
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+    cudaEvent_t a, b;
+    CU(ctx, cudaEventCreate(&a)); CU(ctx, cudaEventCreate(&b));
+    launch_fp64_peak(scratch, blocks, 1 << 12, ctx->stream);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CU(ctx, cudaEventRecord(a, ctx->stream));
+        launch_fp64_peak(scratch, blocks, iters, ctx->stream);
+        CU(ctx, cudaEventRecord(b, ctx->stream));
+        CU(ctx, cudaEventSynchronize(b));
+        float msf = 0.f;
+        CU(ctx, cudaEventElapsedTime(&msf, a, b));
+        const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+        if (msf > 0.f) best = std::max(best, flops / (msf * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    dev_free(ctx, scratch);
+    *out_tflops = best;
+    return 0;
+    API_END()
+}
+
+int locohd_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return LOCOHD_ERR_BAD_PARAM;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; return fail(nullptr, LOCOHD_ERR_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+void locohd_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int locohd_ctx_set_params(locohd_ctx* ctx, const locohd_params* params) {
+    API_BEGIN(ctx)
+    if (!params) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null params");
+    const int C = params->n_categories;
+    // LoCoHD::build (locohd.rs:305-346)
+    if (C <= 0) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "The number of possible categories (primitive types) cannot be zero!");
+    if (C > LOCOHD_MAX_CATEGORIES)
+        return fail(ctx, LOCOHD_ERR_UNSUPPORTED, "at most %d categories are supported (got %d)", LOCOHD_MAX_CATEGORIES, C);
+    std::vector<double> w(C, 1.0), sw(C, 1.0);
+    bool unit = true;
+    if (params->category_weights) {
+        int bad = 0;
+        for (int i = 0; i < C; ++i) {
+            w[i] = params->category_weights[i];
+            if (!(w[i] > 0.0)) ++bad;
+            if (w[i] != 1.0) unit = false;
+            sw[i] = std::sqrt(w[i]);
+        }
+        if (bad)
+            return fail(ctx, LOCOHD_ERR_BAD_PARAM, "LoCoHD parameter 'category_weights' must only contain positive values! Instead, it contains %d non-positive values!", bad);
+    }
+    // StatisticalDistance::build (statistical_distances.rs:97-121)
+    if (params->sd_kind < LOCOHD_SD_HELLINGER || params->sd_kind > LOCOHD_SD_RENYI)
+        return fail(ctx, LOCOHD_ERR_BAD_PARAM, "Invalid statistical distance kind %d!", params->sd_kind);
+    if (params->n_weight_functions < 1) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "at least one weight function is required");
+    std::vector<WfDev> wfs(params->n_weight_functions);
+    for (int i = 0; i < params->n_weight_functions; ++i) TRY_ST(make_wf(ctx, params->weight_functions[i], &wfs[i]));
+    if (params->tpr_kind != LOCOHD_TPR_WITHOUT_LIST && params->tpr_kind != LOCOHD_TPR_WITH_LIST)
+        return fail(ctx, LOCOHD_ERR_BAD_PARAM, "Invalid tag pairing rule kind %d!", params->tpr_kind);
+    std::vector<uint64_t> pairs;
+    if (params->tpr_kind == LOCOHD_TPR_WITH_LIST && params->n_tag_pairs) {
+        pairs.assign(params->tag_pairs, params->tag_pairs + params->n_tag_pairs);
+        std::sort(pairs.begin(), pairs.end());
+        pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+    }
+
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_cat_w); cudaFree(ctx->d_cat_sw); cudaFree(ctx->d_wfs); cudaFree(ctx->d_tag_pairs);
+    ctx->d_cat_w = ctx->d_cat_sw = nullptr; ctx->d_wfs = nullptr; ctx->d_tag_pairs = nullptr;
+    ctx->has_params = false;
+    CU(ctx, cudaMalloc(&ctx->d_cat_w, C * sizeof(double)));
+    CU(ctx, cudaMalloc(&ctx->d_cat_sw, C * sizeof(double)));
+    CU(ctx, cudaMalloc(&ctx->d_wfs, wfs.size() * sizeof(WfDev)));
+    CU(ctx, cudaMemcpy(ctx->d_cat_w, w.data(), C * sizeof(double), cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(ctx->d_cat_sw, sw.data(), C * sizeof(double), cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(ctx->d_wfs, wfs.data(), wfs.size() * sizeof(WfDev), cudaMemcpyHostToDevice));
+    if (!pairs.empty()) {
+        CU(ctx, cudaMalloc(&ctx->d_tag_pairs, pairs.size() * sizeof(uint64_t)));
+        CU(ctx, cudaMemcpy(ctx->d_tag_pairs, pairs.data(), pairs.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    KParams k{};
+    k.C = C;
+    k.sd_kind = params->sd_kind;
+    k.sd_p0 = params->sd_params[0];
+    k.sd_p1 = params->sd_params[1];
+    k.hell2 = (params->sd_kind == LOCOHD_SD_HELLINGER && params->sd_params[0] == 2.0) ? 1 : 0;
+    k.unit_w = unit ? 1 : 0;
+    k.tpr_kind = params->tpr_kind;
+    k.tpr_accept_same = params->tpr_accept_same ? 1 : 0;
+    k.tpr_accepted_pairs = params->tpr_accepted_pairs ? 1 : 0;
+    k.tpr_ordered = params->tpr_ordered ? 1 : 0;
+    k.n_tag_pairs = pairs.size();
+    k.tag_pairs = ctx->d_tag_pairs;
+    k.cat_w = ctx->d_cat_w;
+    k.cat_sw = ctx->d_cat_sw;
+    k.wfs = ctx->d_wfs;
+    k.n_wf = (int)wfs.size();
+    k.sqrt_tbl = ctx->d_sqrt_tbl;
+    k.rsqrt_tbl = ctx->d_rsqrt_tbl;
+    k.err = ctx->d_err;
+    ctx->kp = k;
+    ctx->n_categories = C;
+    ctx->has_params = true;
+    return 0;
+    API_END()
+}
+
+// ---------------------------------------------------------------------------------------------- structures
+int locohd_structs_create(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* prim_offsets, const double* xyz,
+                          const uint16_t* category, const uint32_t* tag, locohd_structs** out) {
+    API_BEGIN(ctx)
+    TRY_ST(need_params(ctx));
+    if (!out || !prim_offsets) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
+    *out = nullptr;
+    if (n_structs == 0) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "at least one structure is required");
+    // prim_offsets must be readable on the host to size the allocations
+    std::vector<uint64_t> offs(n_structs + 1);
+    if (is_device_ptr(ctx, prim_offsets)) {
+        CU(ctx, cudaMemcpy(offs.data(), prim_offsets, offs.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    } else {
+        std::memcpy(offs.data(), prim_offsets, offs.size() * sizeof(uint64_t));
+    }
+    if (offs[0] != 0) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "prim_offsets[0] must be 0");
+    for (uint64_t s = 0; s < n_structs; ++s) {
+        if (offs[s + 1] < offs[s]) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "prim_offsets must be non-decreasing");
+        if (offs[s + 1] - offs[s] > 0xFFFFFFFFull) return fail(ctx, LOCOHD_ERR_UNSUPPORTED, "structure %llu has more than 2^32 primitives", (unsigned long long)s);
+    }
+    const uint64_t n = offs[n_structs];
+    if (n && (!xyz || !category || !tag)) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null primitive arrays");
+    locohd_structs* s = new locohd_structs();
+    s->ctx = ctx; s->n_structs = n_structs; s->n_prims = n;
+    auto bail = [&](int st) { locohd_structs_destroy(s); return st; };
+    int st;
+    if ((st = dev_alloc(ctx, &s->d_prim_off, n_structs + 1)) || (st = dev_alloc(ctx, &s->d_xyz, 3 * n)) ||
+        (st = dev_alloc(ctx, &s->d_cat, n)) || (st = dev_alloc(ctx, &s->d_tag, n)) ||
+        (st = dev_alloc(ctx, &s->d_meta, n_structs)) || (st = dev_alloc(ctx, &s->d_pf, n)) ||
+        (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_sorted_pos, n)) ||
+        (st = dev_alloc(ctx, &s->d_cell_start, n_structs * (uint64_t)kCellStride)))
+        return bail(st);
+    cudaError_t ce = cudaMemcpyAsync(s->d_prim_off, offs.data(), offs.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(s->d_xyz, xyz, 3 * n * sizeof(double), cudaMemcpyDefault, ctx->stream);
+    if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(s->d_tag, tag, n * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream);
+    if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "upload failed: %s", cudaGetErrorString(ce)));
+    {
+        InBuf<uint16_t> cat16;
+        if ((st = cat16.load(ctx, category, n))) return bail(st);
+        ctx->launches += launch_convert_categories(cat16.ptr, s->d_cat, n, ctx->kp.C, ctx->stream);
+    }
+    ctx->launches += launch_validate_xyz(s->d_xyz, 3 * n, ctx->d_err, ctx->stream);
+    // offs (host vector) is consumed by an async copy: wait before it goes out of scope
+    if ((st = sync_and_check(ctx))) return bail(st);
+    *out = s;
+    return 0;
+    API_END()
+}
+
+void locohd_structs_destroy(locohd_structs* s) {
+    if (!s) return;
+    locohd_ctx* ctx = s->ctx;
+    DeviceGuard g(ctx->device);
+    dev_free(ctx, s->d_prim_off); dev_free(ctx, s->d_xyz); dev_free(ctx, s->d_cat); dev_free(ctx, s->d_tag);
+    dev_free(ctx, s->d_meta); dev_free(ctx, s->d_pf); dev_free(ctx, s->d_pd); dev_free(ctx, s->d_sorted_pos);
+    dev_free(ctx, s->d_cell_start);
+    delete s;
+}
+
+void locohd_structs_drop_cells(locohd_structs* s) { if (s) s->cells_valid = false; }
+
+int locohd_structs_update_xyz(locohd_structs* s, const double* xyz) {
+    if (!s) return fail(nullptr, LOCOHD_ERR_BAD_PARAM, "null structures");
+    API_BEGIN(s->ctx)
+    locohd_ctx* ctx = s->ctx;
+    if (s->n_prims && !xyz) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null xyz");
+    s->cells_valid = false;
+    if (s->n_prims) {
+        CU(ctx, cudaMemcpyAsync(s->d_xyz, xyz, 3 * s->n_prims * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        ctx->launches += launch_validate_xyz(s->d_xyz, 3 * s->n_prims, ctx->d_err, ctx->stream);
+    }
+    return sync_and_check(ctx);
+    API_END()
+}
+
+// -------------------------------------------------------------------------------------------- environments
+int locohd_envset_build(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const uint32_t* anchor_struct,
+                        const uint32_t* anchor_prim, double threshold, int keep_indices, locohd_envset** out) {
+    API_BEGIN(ctx)
+    TRY_ST(need_params(ctx));
+    if (!s || !out || (n_anchors && !anchor_prim)) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
+    if (s->ctx != ctx) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "structures belong to another context");
+    *out = nullptr;
+    InBuf<uint32_t> as, ap;
+    TRY_ST(as.load(ctx, anchor_struct, n_anchors));
+    TRY_ST(ap.load(ctx, anchor_prim, n_anchors));
+    TRY_ST(build_envset(ctx, s, n_anchors, as.ptr, ap.ptr, threshold, keep_indices, out));
+    // the anchor arrays may be temporaries that are released (stream-ordered) when this scope ends
+    return 0;
+    API_END()
+}
+
+static int rows_envset(locohd_ctx* ctx, uint64_t n_rows, uint64_t row_len, const double* dmx, const double* xyz,
+                       const uint16_t* category, locohd_envset** out) {
+    TRY_ST(need_params(ctx));
+    if (!out || (!dmx && !xyz) || (row_len && !category)) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
+    *out = nullptr;
+    if (row_len > 0xFFFFFFFFull) return fail(ctx, LOCOHD_ERR_UNSUPPORTED, "rows longer than 2^32");
+    InBuf<double> in;
+    if (dmx) TRY_ST(in.load(ctx, dmx, n_rows * row_len));
+    else TRY_ST(in.load(ctx, xyz, 3 * row_len));
+    InBuf<uint16_t> cat16;
+    TRY_ST(cat16.load(ctx, category, row_len));
+    uint8_t* d_cat8 = nullptr;
+    TRY_ST(dev_alloc(ctx, &d_cat8, row_len));
+    ctx->launches += launch_convert_categories(cat16.ptr, d_cat8, row_len, ctx->kp.C, ctx->stream);
+    if (xyz) ctx->launches += launch_validate_xyz(in.ptr, 3 * row_len, ctx->d_err, ctx->stream);
+    locohd_envset* e = new locohd_envset();
+    e->ctx = ctx; e->n_env = n_rows; e->total = n_rows * row_len; e->max_count = (unsigned)row_len;
+    auto bail = [&](int st) { dev_free(ctx, d_cat8); destroy_envset(e); return st; };
+    int st;
+    if ((st = dev_alloc(ctx, &e->d_count, n_rows)) || (st = dev_alloc(ctx, &e->d_off, n_rows + 1)) ||
+        (st = alloc_envset_storage(ctx, e, true)))
+        return bail(st);
+    ctx->launches += launch_fill_u64_iota_rows(e->d_off, e->d_count, n_rows, row_len, ctx->stream);
+    ctx->launches += launch_rows_fill(dmx ? in.ptr : nullptr, d_cat8, n_rows, row_len, xyz ? in.ptr : nullptr, ctx->kp,
+                                      env_out(e), ctx->stream);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
+    if ((st = sync_and_check(ctx))) return bail(st);
+    dev_free(ctx, d_cat8);
+    *out = e;
+    return 0;
+}
+
+int locohd_envset_from_rows(locohd_ctx* ctx, uint64_t n_rows, uint64_t row_len, const double* dmx,
+                            const uint16_t* category, locohd_envset** out) {
+    API_BEGIN(ctx)
+    if (!dmx && n_rows * row_len) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null distance matrix");
+    return rows_envset(ctx, n_rows, row_len, dmx, nullptr, category, out);
+    API_END()
+}
+
+int locohd_envset_from_coords(locohd_ctx* ctx, uint64_t n_points, const double* xyz, const uint16_t* category,
+                              locohd_envset** out) {
+    API_BEGIN(ctx)
+    if (!xyz && n_points) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null coordinates");
+    return rows_envset(ctx, n_points, n_points, nullptr, xyz, category, out);
+    API_END()
+}
+
+void locohd_envset_destroy(locohd_envset* e) { destroy_envset(e); }
+uint64_t locohd_envset_size(const locohd_envset* e) { return e ? e->n_env : 0; }
+uint64_t locohd_envset_total_members(const locohd_envset* e) { return e ? e->total : 0; }
+
+int locohd_envset_dump(locohd_ctx* ctx, const locohd_envset* e, uint64_t* offsets, double* distances,
+                       uint16_t* categories, uint32_t* prim_indices) {
+    API_BEGIN(ctx)
+    if (!e) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null envset");
+    TRY_ST(sync_and_check(ctx));
+    if (offsets) CU(ctx, cudaMemcpy(offsets, e->d_off, (e->n_env + 1) * sizeof(uint64_t), cudaMemcpyDefault));
+    if (distances && e->total) CU(ctx, cudaMemcpy(distances, e->d_dist, e->total * sizeof(double), cudaMemcpyDefault));
+    if (categories && e->total) {
+        std::vector<uint8_t> c8(e->total);
+        CU(ctx, cudaMemcpy(c8.data(), e->d_cat, e->total, cudaMemcpyDeviceToHost));
+        std::vector<uint16_t> c16(e->total);
+        for (uint64_t i = 0; i < e->total; ++i) c16[i] = c8[i] == kUnknownCat8 ? (uint16_t)LOCOHD_UNKNOWN_CATEGORY : c8[i];
+        CU(ctx, cudaMemcpy(categories, c16.data(), e->total * sizeof(uint16_t), cudaMemcpyDefault));
+    }
+    if (prim_indices && e->total) {
+        if (!e->d_idx) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "envset was built without keep_indices");
+        CU(ctx, cudaMemcpy(prim_indices, e->d_idx, e->total * sizeof(uint32_t), cudaMemcpyDefault));
+    }
+    return 0;
+    API_END()
+}
+
+// ------------------------------------------------------------------------------------------------ scoring
+int locohd_score_pairs(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_pairs,
+                       const uint32_t* pairs, const uint32_t* wf_idx, double* out_scores) {
+    API_BEGIN(ctx)
+    TRY_ST(need_params(ctx));
+    if (!a || !b || (n_pairs && (!pairs || !out_scores))) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
+    TRY_ST(check_wf_indices(ctx, wf_idx, n_pairs));
+    InBuf<uint32_t> pr, wf;
+    TRY_ST(pr.load(ctx, pairs, 2 * n_pairs));
+    TRY_ST(wf.load(ctx, wf_idx, n_pairs));
+    OutBuf<double> out;
+    TRY_ST(out.prepare(ctx, out_scores, n_pairs));
+    TRY_ST(run_score(ctx, a, b, n_pairs, pr.ptr, nullptr, nullptr, 0, 0, wf.ptr, out.ptr));
+    TRY_ST(out.commit());
+    return sync_and_check(ctx);
+    API_END()
+}
+
+int locohd_score_jobs(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_jobs,
+                      const locohd_job* jobs, const uint32_t* wf_idx, double* out_scores, double* out_job_means) {
+    API_BEGIN(ctx)
+    TRY_ST(need_params(ctx));
+    if (!a || !b || (n_jobs && !jobs)) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
+    // the job table is read on the host to lay out the output
+    std::vector<locohd_job> hj(n_jobs);
+    if (n_jobs) {
+        if (is_device_ptr(ctx, jobs)) CU(ctx, cudaMemcpy(hj.data(), jobs, n_jobs * sizeof(locohd_job), cudaMemcpyDeviceToHost));
+        else std::memcpy(hj.data(), jobs, n_jobs * sizeof(locohd_job));
+    }
+    std::vector<uint64_t> joff(n_jobs + 1, 0);
+    bool uniform = n_jobs > 0;
+    for (uint64_t j = 0; j < n_jobs; ++j) {
+        if (hj[j].a_first + hj[j].n > a->n_env || hj[j].b_first + hj[j].n > b->n_env)
+            return fail(ctx, LOCOHD_ERR_INDEX, "job %llu addresses environments beyond the env-set", (unsigned long long)j);
+        joff[j + 1] = joff[j] + hj[j].n;
+        if (hj[j].n != hj[0].n) uniform = false;
+    }
+    const uint64_t n_pairs = joff[n_jobs];
+    if (n_pairs && !out_scores && !out_job_means) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "no output requested");
+    TRY_ST(check_wf_indices(ctx, wf_idx, n_pairs));
+    InBuf<locohd_job> dj;
+    InBuf<uint64_t> djoff;
+    InBuf<uint32_t> wf;
+    TRY_ST(dj.load(ctx, hj.data(), n_jobs));
+    TRY_ST(djoff.load(ctx, joff.data(), n_jobs + 1));
+    TRY_ST(wf.load(ctx, wf_idx, n_pairs));
+    OutBuf<double> out, means;
+    double* d_scores_tmp = nullptr;
+    TRY_ST(out.prepare(ctx, out_scores, n_pairs));
+    double* d_scores = out.ptr;
+    if (!d_scores) { TRY_ST(dev_alloc(ctx, &d_scores_tmp, n_pairs)); d_scores = d_scores_tmp; }
+    TRY_ST(means.prepare(ctx, out_job_means, n_jobs));
+    int st = run_score(ctx, a, b, n_pairs, nullptr, dj.ptr, djoff.ptr, n_jobs, (uniform && hj[0].n) ? hj[0].n : 0,
+                       wf.ptr, d_scores);
+    if (!st && means.ptr) {
+        ctx->launches += launch_job_means(d_scores, djoff.ptr, n_jobs, means.ptr, ctx->stream);
+    }
+    if (!st) st = out.commit();
+    if (!st) st = means.commit();
+    const int st2 = sync_and_check(ctx);  // also keeps hj/joff alive until the copies are done
+    dev_free(ctx, d_scores_tmp);
+    return st ? st : st2;
+    API_END()
+}
+
+int locohd_score_anchor_lists(locohd_ctx* ctx, const uint16_t* seq_a, uint64_t len_a, const double* dists_a,
+                              uint64_t dlen_a, const uint16_t* seq_b, uint64_t len_b, const double* dists_b,
+                              uint64_t dlen_b, uint32_t wf_idx, double* out_score) {
+    API_BEGIN(ctx)
+    TRY_ST(need_params(ctx));
+    if (!out_score) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null output");
+    if (len_a != dlen_a || len_b != dlen_b) return fail(ctx, LOCOHD_ERR_LEN_MISMATCH, "%s", status_text(LOCOHD_ERR_LEN_MISMATCH));
+    if (len_a == 0 || len_b == 0) return fail(ctx, LOCOHD_ERR_EMPTY_ENV, "from_anchors needs non-empty lists (the reference panics on dists[0])");
+    if (wf_idx >= (uint32_t)ctx->kp.n_wf) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "weight function index out of range");
+    InBuf<uint16_t> sa16, sb16;
+    InBuf<double> da, db;
+    TRY_ST(sa16.load(ctx, seq_a, len_a)); TRY_ST(sb16.load(ctx, seq_b, len_b));
+    TRY_ST(da.load(ctx, dists_a, len_a)); TRY_ST(db.load(ctx, dists_b, len_b));
+    uint8_t *sa8 = nullptr, *sb8 = nullptr;
+    TRY_ST(dev_alloc(ctx, &sa8, len_a)); TRY_ST(dev_alloc(ctx, &sb8, len_b));
+    ctx->launches += launch_convert_categories(sa16.ptr, sa8, len_a, ctx->kp.C, ctx->stream);
+    ctx->launches += launch_convert_categories(sb16.ptr, sb8, len_b, ctx->kp.C, ctx->stream);
+    OutBuf<double> out;
+    int st = out.prepare(ctx, out_score, 1);
+    if (!st) {
+        ctx->launches += launch_anchor_lists(ctx->kp, sa8, len_a, da.ptr, sb8, len_b, db.ptr, wf_idx, out.ptr, ctx->stream);
+        st = out.commit();
+    }
+    const int st2 = sync_and_check(ctx);
+    dev_free(ctx, sa8); dev_free(ctx, sb8);
+    return st ? st : st2;
+    API_END()
+}
+
+int locohd_from_primitives(locohd_ctx* ctx, uint64_t n_a, const double* xyz_a, const uint16_t* cat_a,
+                           const uint32_t* tag_a, uint64_t n_b, const double* xyz_b, const uint16_t* cat_b,
+                           const uint32_t* tag_b, uint64_t n_pairs, const uint32_t* anchors,
+                           const uint32_t* wf_idx, double threshold, double* out_scores) {
+    API_BEGIN(ctx)
+    TRY_ST(need_params(ctx));
+    if (n_pairs && (!anchors || !out_scores)) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
+    if ((n_a && (!xyz_a || !cat_a || !tag_a)) || (n_b && (!xyz_b || !cat_b || !tag_b)))
+        return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null primitive arrays");
+    if (n_pairs == 0) return 0;
+    if (!(threshold > 0.0))
+        return fail(ctx, LOCOHD_ERR_EMPTY_ENV, "threshold_distance must be positive (got %g): every environment would be empty", threshold);
+    TRY_ST(check_wf_indices(ctx, wf_idx, n_pairs));
+    const uint64_t n = n_a + n_b;
+    // one structure set holding A then B
+    locohd_structs* s = new locohd_structs();
+    s->ctx = ctx; s->n_structs = 2; s->n_prims = n;
+    locohd_envset* env = nullptr;
+    uint32_t *d_as = nullptr, *d_ap = nullptr;
+    auto cleanup = [&](int st) {
+        dev_free(ctx, d_as); dev_free(ctx, d_ap);
+        if (env) destroy_envset(env);
+        locohd_structs_destroy(s);
+        return st;
+    };
+    int st;
+    if ((st = dev_alloc(ctx, &s->d_prim_off, 3)) || (st = dev_alloc(ctx, &s->d_xyz, 3 * n)) ||
+        (st = dev_alloc(ctx, &s->d_cat, n)) || (st = dev_alloc(ctx, &s->d_tag, n)) ||
+        (st = dev_alloc(ctx, &s->d_meta, 2)) || (st = dev_alloc(ctx, &s->d_pf, n)) ||
+        (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_sorted_pos, n)) ||
+        (st = dev_alloc(ctx, &s->d_cell_start, 2 * (uint64_t)kCellStride)))
+        return cleanup(st);
+    const uint64_t offs[3] = {0, n_a, n};
+    cudaError_t ce = cudaMemcpyAsync(s->d_prim_off, offs, sizeof offs, cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess && n_a) ce = cudaMemcpyAsync(s->d_xyz, xyz_a, 3 * n_a * sizeof(double), cudaMemcpyDefault, ctx->stream);
+    if (ce == cudaSuccess && n_b) ce = cudaMemcpyAsync(s->d_xyz + 3 * n_a, xyz_b, 3 * n_b * sizeof(double), cudaMemcpyDefault, ctx->stream);
+    if (ce == cudaSuccess && n_a) ce = cudaMemcpyAsync(s->d_tag, tag_a, n_a * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream);
+    if (ce == cudaSuccess && n_b) ce = cudaMemcpyAsync(s->d_tag + n_a, tag_b, n_b * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream);
+    if (ce != cudaSuccess) return cleanup(fail(ctx, LOCOHD_ERR_CUDA, "upload failed: %s", cudaGetErrorString(ce)));
+    {
+        InBuf<uint16_t> ca, cb;
+        if ((st = ca.load(ctx, cat_a, n_a)) || (st = cb.load(ctx, cat_b, n_b))) return cleanup(st);
+        ctx->launches += launch_convert_categories(ca.ptr, s->d_cat, n_a, ctx->kp.C, ctx->stream);
+        ctx->launches += launch_convert_categories(cb.ptr, s->d_cat + n_a, n_b, ctx->kp.C, ctx->stream);
+    }
+    ctx->launches += launch_validate_xyz(s->d_xyz, 3 * n, ctx->d_err, ctx->stream);
+    // anchors: environments [0, P) belong to A, [P, 2P) to B
+    std::vector<uint32_t> h_as(2 * n_pairs), h_ap(2 * n_pairs);
+    {
+        std::vector<uint32_t> h_anchor;
+        const uint32_t* an = anchors;
+        if (is_device_ptr(ctx, anchors)) {
+            h_anchor.resize(2 * n_pairs);
+            CU(ctx, cudaMemcpy(h_anchor.data(), anchors, 2 * n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            an = h_anchor.data();
+        }
+        for (uint64_t i = 0; i < n_pairs; ++i) {
+            h_as[i] = 0; h_ap[i] = an[2 * i];
+            h_as[n_pairs + i] = 1; h_ap[n_pairs + i] = an[2 * i + 1];
+        }
+    }
+    if ((st = dev_alloc(ctx, &d_as, 2 * n_pairs)) || (st = dev_alloc(ctx, &d_ap, 2 * n_pairs))) return cleanup(st);
+    ce = cudaMemcpyAsync(d_as, h_as.data(), 2 * n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_ap, h_ap.data(), 2 * n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (ce != cudaSuccess) return cleanup(fail(ctx, LOCOHD_ERR_CUDA, "upload failed: %s", cudaGetErrorString(ce)));
+    if ((st = build_envset(ctx, s, 2 * n_pairs, d_as, d_ap, threshold, 0, &env))) return cleanup(st);
+    const locohd_job job{0, n_pairs, n_pairs};
+    InBuf<locohd_job> dj;
+    InBuf<uint32_t> wf;
+    OutBuf<double> out;
+    if ((st = dj.load(ctx, &job, 1)) || (st = wf.load(ctx, wf_idx, n_pairs)) || (st = out.prepare(ctx, out_scores, n_pairs)))
+        return cleanup(st);
+    st = run_score(ctx, env, env, n_pairs, nullptr, dj.ptr, nullptr, 1, n_pairs, wf.ptr, out.ptr);
+    if (!st) st = out.commit();
+    const int st2 = sync_and_check(ctx);
+    return cleanup(st ? st : st2);
+    API_END()
+}
+
+// ----------------------------------------------------------------------------------------------- leaf math
+int locohd_wf_integral_points(locohd_ctx* ctx, const locohd_weight_function* wf, uint64_t n, const double* x,
+                              double* out) {
+    API_BEGIN(ctx)
+    if (!wf || (n && (!x || !out))) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
+    WfDev w;
+    TRY_ST(make_wf(ctx, *wf, &w));
+    WfDev* d_w = nullptr;
+    TRY_ST(dev_alloc(ctx, &d_w, 1));
+    CU(ctx, cudaMemcpyAsync(d_w, &w, sizeof w, cudaMemcpyHostToDevice, ctx->stream));
+    InBuf<double> in;
+    OutBuf<double> o;
+    int st = in.load(ctx, x, n);
+    if (!st) st = o.prepare(ctx, out, n);
+    if (!st) {
+        ctx->launches += launch_wf_points(d_w, n, in.ptr, o.ptr, ctx->d_err, ctx->stream);
+        st = o.commit();
+    }
+    const int st2 = sync_and_check(ctx);
+    dev_free(ctx, d_w);
+    return st ? st : st2;
+    API_END()
+}
+
+int locohd_sd_run(locohd_ctx* ctx, int32_t sd_kind, const double* sd_params, int32_t n_categories, uint64_t n,
+                  const double* p1, const double* p2, double* out) {
+    API_BEGIN(ctx)
+    if (sd_kind < LOCOHD_SD_HELLINGER || sd_kind > LOCOHD_SD_RENYI) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "Invalid statistical distance kind %d!", sd_kind);
+    if (n_categories <= 0 || (n && (!p1 || !p2 || !out))) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "bad argument");
+    const double q0 = sd_params ? sd_params[0] : 0.0, q1 = sd_params ? sd_params[1] : 0.0;
+    InBuf<double> a, b;
+    OutBuf<double> o;
+    TRY_ST(a.load(ctx, p1, n * n_categories));
+    TRY_ST(b.load(ctx, p2, n * n_categories));
+    TRY_ST(o.prepare(ctx, out, n));
+    ctx->launches += launch_sd_run(sd_kind, q0, q1, n_categories, n, a.ptr, b.ptr, o.ptr, ctx->stream);
+    TRY_ST(o.commit());
+    return sync_and_check(ctx);
+    API_END()
+}
+
+}  // extern "C"
