@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py — LoCoHD anchor-pairs/second on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5] [--impl reference]
+
+A *step* is one pass of the hot path over one batch of synthetic structure pairs (SURVEY.md §8(d) generator):
+cell lists (K0) -> environments (K1, scan, K1') -> scoring (K2).  Default workload = BASELINE.json configs[1]:
+all_atom-shaped protein pairs (10 000 primitives each), kumaraswamy [3, 10, 2, 5], 10 A threshold, hetero
+contacts only, every primitive an anchor; `--pairs` structure pairs per GPU per step (weak scaling).
+
+    value  whole-job throughput with the structures already resident in HBM (CUDA events on the library stream)
+    e2e    same metric through the C-ABI call sequence with HOST (pinned) buffers: H2D of the structures and
+           anchors and D2H of the scores inside the timed region (wall clock between synchronisations)
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, all host threads; the Rust crate
+cannot be built in this image) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+from loco_hd_b200 import synth  # noqa: E402
+
+F_WF = {"uniform": 11, "kumaraswamy": 19, "dagum": 9}  # flops of one integral_range
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+class Workload:
+    """clouds: structures of this rank; groups: (structure, anchor primitive indices) -> one environment each,
+    laid out group after group; jobs: (group_a, group_b) scored with identity pairing."""
+
+    def __init__(self, name, desc, n_categories, wf, clouds, groups, jobs, scaling="weak"):
+        self.name, self.desc, self.C, self.wf, self.scaling = name, desc, n_categories, wf, scaling
+        self.rule = {"accept_same": False}
+        self.threshold = 10.0
+        self.clouds = clouds
+        self.offsets = np.cumsum([0] + [c.n for c in clouds]).astype(np.uint64)
+        self.xyz = np.concatenate([c.xyz for c in clouds])
+        self.cat = np.concatenate([c.cat for c in clouds]).astype(np.uint16)
+        self.tag = np.concatenate([c.tag for c in clouds]).astype(np.uint32)
+        self.anchor_struct = np.concatenate([np.full(len(p), s, np.uint32) for s, p in groups])
+        self.anchor_prim = np.concatenate([np.asarray(p, np.uint32) for _, p in groups])
+        goff = np.cumsum([0] + [len(p) for _, p in groups])
+        self.jobs = np.array([(goff[a], goff[b], goff[a + 1] - goff[a]) for a, b in jobs],
+                             dtype=[("a_first", "<u8"), ("b_first", "<u8"), ("n", "<u8")])
+        self.n_pairs = int(self.jobs["n"].sum())
+        self.groups, self.job_groups = groups, jobs
+
+    @property
+    def h2d_bytes(self):
+        return (self.xyz.nbytes + self.cat.nbytes + self.tag.nbytes + self.offsets.nbytes + self.anchor_struct.nbytes
+                + self.anchor_prim.nbytes + self.jobs.nbytes)
+
+    def job_arrays(self, j):
+        """(A cloud, B cloud, anchors [n, 2]) of job j, for the CPU restatement."""
+        ga, gb = self.job_groups[j]
+        (sa, pa), (sb, pb) = self.groups[ga], self.groups[gb]
+        return self.clouds[sa], self.clouds[sb], np.stack([pa, pb], axis=1).astype(np.uint32)
+
+
+def make_workload(name, rank, world, args):
+    if name == "cfg2":
+        B = args.pairs
+        clouds, groups, jobs = [], [], []
+        for i in range(B):
+            a, b = synth.config2_pair(rank * B + i)
+            clouds += [a, b]
+            groups += [(2 * i, np.arange(a.n)), (2 * i + 1, np.arange(b.n))]
+            jobs.append((2 * i, 2 * i + 1))
+        return Workload("cfg2", f"BASELINE configs[1]: {B} all_atom-shaped structure pairs per GPU (10000 primitives each, "
+                        "C=7), kumaraswamy [3,10,2,5], threshold 10, accept_same=False, every primitive an anchor",
+                        7, ("kumaraswamy", (3.0, 10.0, 2.0, 5.0)), clouds, groups, jobs)
+    if name == "cfg3":
+        M = args.models
+        ref = synth.config3_reference()
+        clouds = [ref] + [synth.config3_model(ref, rank * M + m) for m in range(M)]
+        cent = ref.centroid_anchors()
+        groups = [(s, cent) for s in range(M + 1)]
+        return Workload("cfg3", f"BASELINE configs[2]: 1 reference vs {M} models per GPU (300 residues, 2700 primitives, "
+                        "all_atom_with_centroid, C=8), uniform [3,10], Cent anchors", 8, ("uniform", (3.0, 10.0)), clouds,
+                        groups, [(0, m + 1) for m in range(M)])
+    if name == "cfg4":
+        F = args.frames
+        f0 = synth.config4_frame0()
+        clouds = [f0] + [synth.config4_frame(f0, 1 + rank * F + t) for t in range(F)]
+        cent = f0.centroid_anchors()
+        groups = [(s, cent) for s in range(F + 1)]
+        return Workload("cfg4", f"BASELINE configs[3]: {F} trajectory frames per GPU (5000 primitives, "
+                        "coarse_grained_with_centroid, C=8) vs frame 0, uniform [3,10], 1250 Cent anchors per frame", 8,
+                        ("uniform", (3.0, 10.0)), clouds, groups, [(0, t + 1) for t in range(F)])
+    if name == "cfg5":
+        S = args.ensemble
+        base = synth.config5_base()
+        clouds = [synth.config5_member(base, i) for i in range(S)]
+        groups = [(s, np.arange(base.n)) for s in range(S)]
+        all_jobs = [(i, j) for i in range(S) for j in range(i + 1, S)]
+        return Workload("cfg5", f"BASELINE configs[4]: all-vs-all ensemble of {S} structures (5000 primitives, all_atom, "
+                        f"C=7), uniform [3,10], every primitive an anchor; {len(all_jobs)} structure pairs dealt "
+                        f"round-robin over {world} GPU(s)", 7, ("uniform", (3.0, 10.0)), clouds, groups,
+                        all_jobs[rank::world], scaling="strong")
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ---------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(device)], stdout=subprocess.PIPE, text=True,
+                                         stderr=subprocess.DEVNULL)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def oracle_params(oracle, wl):
+    return oracle.Params(wl.C, [(wl.wf[0], list(wl.wf[1]))], tag_rule=wl.rule)
+
+
+def oracle_run_jobs(oracle, op, wl, job_ids, n_threads=0):
+    """The CPU restatement on a set of jobs; returns (anchor pairs, seconds, walk steps, env members)."""
+    pairs, steps, members = 0, 0, 0
+    t0 = time.perf_counter()
+    for j in job_ids:
+        a, b, anchors = wl.job_arrays(j)
+        r = oracle.from_primitives(op, a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, wl.threshold,
+                                   n_threads=n_threads, debug=True)
+        pairs += len(anchors)
+        steps += int(r["steps"].sum())
+        members += int(r["env_sizes"].sum())
+    return pairs, time.perf_counter() - t0, steps, members
+
+
+def sample_jobs(wl, target_pairs):
+    ids, tot = [], 0
+    for j in range(len(wl.jobs)):
+        ids.append(j)
+        tot += int(wl.jobs["n"][j])
+        if tot >= target_pairs:
+            break
+    return ids
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's algorithm on the host cores (oracle/, C++/OpenMP restatement)."""
+    if rank != 0:
+        return
+    import oracle
+
+    oracle.build()
+    wl = make_workload(args.workload, 0, world, args)
+    op = oracle_params(oracle, wl)
+    ids = sample_jobs(wl, args.ref_pairs)
+    cores = oracle.max_threads()
+    for _ in range(args.warmup):
+        oracle_run_jobs(oracle, op, wl, ids[:1])
+    t, pairs = 0.0, 0
+    for _ in range(args.steps):
+        p, dt, _, _ = oracle_run_jobs(oracle, op, wl, ids)
+        t += dt
+        pairs += p
+    value = pairs / t
+    sample = f"{len(ids)} structure pair(s) = {pairs // max(args.steps, 1)} anchor pairs per step of workload {wl.name}"
+    print(json.dumps({
+        "impl": "reference", "metric": "anchor_pairs_per_second", "value": value, "unit": "anchor-pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(args.steps, 1),
+        "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl.desc, "host": "CPU only"},
+        "cpu_baseline": {"value": value, "unit": "anchor-pairs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "C++/OpenMP restatement of the reference algorithm (kd-tree query, stable sort, "
+                                 "sequential merge walk, pow-based Hellinger); the Rust crate cannot be built here"},
+        "e2e": {"value": value, "unit": "anchor-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from loco_hd_b200 import _capi
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    wl = make_workload(args.workload, rank, world, args)
+    ctx = _capi.Context(local_rank)
+    ctx.set_params(wl.C, [wl.wf], tag_rule=wl.rule)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    n_env = len(wl.anchor_prim)
+
+    # ---- resident inputs: structures in HBM (locohd_structs), anchors and outputs as device arrays
+    structs = ctx.structs_create(wl.offsets, wl.xyz, wl.cat, wl.tag)
+    d_as = torch.from_numpy(wl.anchor_struct.view(np.int32)).cuda()
+    d_ap = torch.from_numpy(wl.anchor_prim.view(np.int32)).cuda()
+    d_out = torch.empty(wl.n_pairs, dtype=torch.float64, device="cuda")
+
+    def step_resident():
+        structs.drop_cells()  # the reference rebuilds its kd-trees on every call (locohd.rs:504-510): so do we
+        env = ctx.envset_build(structs, d_ap.data_ptr(), wl.threshold, anchor_struct=d_as.data_ptr(), n_anchors=n_env)
+        ctx.score_jobs(env, env, wl.jobs, out=d_out.data_ptr())
+        env.close()
+
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.synchronize()
+    ctx.profile_read()
+    barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    ctx.profile_enable(True)
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launch_count - launches0
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    clock_info = clocks.stop()
+    total_pairs = sum_over_ranks(float(wl.n_pairs))
+    value = total_pairs * args.steps / (ms_total * 1e-3)
+
+    # ---- algorithmic work from the environment sizes of one extra, untimed build
+    env = ctx.envset_build(structs, d_ap.data_ptr(), wl.threshold, anchor_struct=d_as.data_ptr(), n_anchors=n_env)
+    off = np.empty(n_env + 1, np.uint64)
+    ctx._check(ctx.lib.locohd_envset_dump(ctx.h, env.h, _capi._p(off), None, None, None))
+    check_scores = d_out.cpu().numpy()
+    env.close()
+    sizes = np.diff(off).astype(np.int64)
+    m_a = np.concatenate([sizes[j["a_first"]:j["a_first"] + j["n"]] for j in wl.jobs])
+    m_b = np.concatenate([sizes[j["b_first"]:j["b_first"] + j["n"]] for j in wl.jobs])
+    events = m_a + m_b - 1                                   # E (cross-list exact ties: none in this workload)
+    f_walk = float((events * (10 * wl.C + 4 + F_WF[wl.wf[0]])).sum())
+    f_gather = float(10 * sizes.sum())                       # every environment is gathered once per step
+    alg_bytes = 16.0 * wl.n_pairs + 29.0 * float(wl.offsets[-1])
+
+    # ---- e2e: host (pinned) buffers through the same C-ABI calls, copies inside the timed region
+    h_off = wl.offsets
+    h_xyz = ctx.pinned_array(wl.xyz.shape, np.float64); h_xyz[...] = wl.xyz
+    h_cat = ctx.pinned_array(wl.cat.shape, np.uint16); h_cat[...] = wl.cat
+    h_tag = ctx.pinned_array(wl.tag.shape, np.uint32); h_tag[...] = wl.tag
+    h_as = ctx.pinned_array(wl.anchor_struct.shape, np.uint32); h_as[...] = wl.anchor_struct
+    h_ap = ctx.pinned_array(wl.anchor_prim.shape, np.uint32); h_ap[...] = wl.anchor_prim
+    h_out = ctx.pinned_array((wl.n_pairs,), np.float64)
+
+    def step_e2e():
+        st = ctx.structs_create(h_off, h_xyz, h_cat, h_tag)
+        env = ctx.envset_build(st, h_ap, wl.threshold, anchor_struct=h_as)
+        ctx.score_jobs(env, env, wl.jobs, out=h_out)
+        env.close()
+        st.close()
+
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        step_e2e()
+    ctx.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    ctx.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = total_pairs * e2e_steps / t_e2e
+    e2e_ok = bool(np.array_equal(h_out, check_scores))
+
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rooflines (rank 0's kernels; all ranks run identical shapes)
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except OSError:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    fp64_peak = ctx.measure_fp64_tflops()
+    kernels = {g: {"ms_per_step": ms / args.steps, "share": ms / max(sum(v[0] for v in prof.values()), 1e-9)}
+               for g, (ms, n) in prof.items() if n}
+    dominant = max(kernels, key=lambda g: kernels[g]["ms_per_step"])
+    dom_flops = {"score": f_walk, "fill": f_gather, "count": f_gather}.get(dominant, 0.0)
+    dom_ms = kernels[dominant]["ms_per_step"]
+    achieved = dom_flops / (dom_ms * 1e-3) / 1e12
+    step_ms = ms_total / args.steps
+    roofline = {
+        "kernel": {"score": "score_kernel (K2)", "fill": "env_fill_kernel (K1')", "count": "env_count_kernel (K1)"}.get(dominant, dominant),
+        "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+        "peak_source": "FP64 FMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 entry)",
+        "traffic": None, "alg_flops_per_launch": dom_flops, "launch_ms": dom_ms,
+    }
+    roofline_hbm = {"bound": "hbm", "achieved": alg_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                    "alg_bytes_per_step": alg_bytes, "scope": "whole step"}
+    roofline_step = {"bound": "fp64", "achieved": (f_walk + f_gather) / (step_ms * 1e-3) / 1e12, "peak": fp64_peak,
+                     "unit": "TFLOP/s", "frac": (f_walk + f_gather) / (step_ms * 1e-3) / 1e12 / fp64_peak,
+                     "scope": "whole step (ALG_FLOPS of SURVEY.md 8(d))"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on a bounded sample of the same workload
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        oracle.build()
+        op = oracle_params(oracle, wl)
+        ids = sample_jobs(wl, args.ref_pairs)
+        oracle_run_jobs(oracle, op, wl, ids[:1])
+        p, dt, steps, members = oracle_run_jobs(oracle, op, wl, ids)
+        ids1 = sample_jobs(wl, max(1, args.ref_pairs // 16))
+        p1, dt1, _, _ = oracle_run_jobs(oracle, op, wl, ids1, n_threads=1)
+        # the sample doubles as a parity spot check of this very run
+        a, b, anchors = wl.job_arrays(0)
+        ref = oracle.from_primitives(op, a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, wl.threshold)
+        n0 = int(wl.jobs["n"][0])
+        cpu = {"value": p / dt, "unit": "anchor-pairs/s", "cores": oracle.max_threads(), "kind": "port",
+               "sample": f"first {len(ids)} structure pair(s) of the step = {p} anchor pairs, {dt:.2f} s",
+               "single_thread_value": p1 / dt1,
+               "walk_steps_per_pair": steps / p, "env_members_per_pair": members / p,
+               "max_abs_score_diff_vs_gpu_job0": float(np.abs(ref - check_scores[:n0]).max()),
+               "note": "C++/OpenMP restatement of the reference algorithm (Rust toolchain unavailable)"}
+
+    line = {
+        "metric": "anchor_pairs_per_second", "value": value, "unit": "anchor-pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl.desc, "anchor_pairs_per_gpu_per_step": wl.n_pairs,
+                   "environments_per_gpu_per_step": n_env,
+                   "l2": f"inputs larger than L2 each step: {wl.h2d_bytes / 1e6:.0f} MB of structures/anchors + "
+                         f"{9 * float(sizes.sum()) / 1e6:.0f} MB environment store streamed per step"},
+        "e2e": {"value": e2e_value, "unit": "anchor-pairs/s", "h2d_bytes_per_step": int(wl.h2d_bytes),
+                "d2h_bytes_per_step": int(8 * wl.n_pairs), "steps": e2e_steps,
+                "scores_identical_to_resident_run": e2e_ok},
+        "gpu_launches": int(launches),
+        "clocks": clock_info,
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_step": roofline_step,
+        "kernels": kernels,
+        "env_size_mean": float(sizes.mean()), "env_size_max": int(sizes.max()),
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--pairs", type=int, default=256, help="cfg2: structure pairs per GPU per step")
+    ap.add_argument("--models", type=int, default=500, help="cfg3: models per GPU per step")
+    ap.add_argument("--frames", type=int, default=1024, help="cfg4: frames per GPU per step")
+    ap.add_argument("--ensemble", type=int, default=96, help="cfg5: ensemble size (all-vs-all, jobs dealt over GPUs)")
+    ap.add_argument("--ref-pairs", type=int, default=160000, help="anchor pairs per CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", str(Path(__file__).resolve())] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

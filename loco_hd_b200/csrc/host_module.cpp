@@ -588,10 +588,10 @@ struct LoCoHD {
         std::optional<std::vector<std::string>> keys;
         if (with_keys) keys = std::move(key_list);
         const auto wf = resolve_keys(keys, n_pairs);
+        if (n_pairs == 0) return {};
         std::lock_guard<std::mutex> g(mu);
         ensure_ctx();  // interns the rule's tags first so that their ids are stable
         const Flat a = flatten(prim_a, "prim_a"), b = flatten(prim_b, "prim_b");
-        if (n_pairs == 0) return {};
         for (size_t k = 0; k < n_pairs; ++k)  // prim_seq[anchor_idx] panics upstream (locohd.rs:521)
             if (anchors[2 * k] >= a.cat.size() || anchors[2 * k + 1] >= b.cat.size())
                 throw py::value_error("Anchor index out of range: pair " + std::to_string(k) + " = (" + std::to_string(anchors[2 * k]) +

@@ -571,8 +571,8 @@ int oracle_from_primitives(const oracle_params* p, uint64_t na, const double* xy
     int first_err = OK;
     const int C = pk.model.C;
 #ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
-#pragma omp parallel for schedule(dynamic, 16)
+    const int nt = n_threads > 0 ? n_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
 #endif
     for (int64_t i = 0; i < int64_t(n_pairs); ++i) {  // locohd.rs:545-554
         std::vector<double> da, db;
@@ -613,8 +613,8 @@ int oracle_from_dmxs(const oracle_params* p, const uint16_t* seq_a, uint64_t len
     ParamPack pk = unpack(p);
     int first_err = OK;
 #ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
-#pragma omp parallel for schedule(dynamic, 4)
+    const int nt = n_threads > 0 ? n_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nt)
 #endif
     for (int64_t i = 0; i < int64_t(rows_a); ++i) {  // locohd.rs:434-443
         std::vector<double> ra(dmx_a + i * cols_a, dmx_a + (i + 1) * cols_a);
