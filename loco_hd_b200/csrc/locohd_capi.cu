@@ -38,7 +38,7 @@ struct locohd_ctx {
     double* d_sqrt_tbl = nullptr;
     double* d_rsqrt_tbl = nullptr;
     int* d_err = nullptr;
-    ScanResult* d_scan = nullptr;
+    FillStats* d_fill = nullptr;
     // per-kernel-group event timing
     bool prof_on = false;
     struct ProfRec { int group; cudaEvent_t a, b; };
@@ -90,14 +90,16 @@ struct locohd_envset {
     locohd_ctx* ctx = nullptr;
     uint64_t n_env = 0, total = 0;
     unsigned max_count = 0;
+    bool key_is_w = false;
     uint64_t* d_off = nullptr;
     uint32_t* d_count = nullptr;
-    double* d_dist = nullptr;
+    double* d_key = nullptr;
     uint8_t* d_cat = nullptr;
+    double* d_dist = nullptr;   // plain distances, kept only for locohd_envset_dump when the keys hold W
     uint32_t* d_idx = nullptr;
     EnvView view() const {
         EnvView v;
-        v.n_env = n_env; v.off = d_off; v.dist = d_dist; v.cat = d_cat; v.idx = d_idx;
+        v.n_env = n_env; v.off = d_off; v.count = d_count; v.key = d_key; v.cat = d_cat; v.key_is_w = key_is_w ? 1 : 0;
         return v;
     }
 };
@@ -292,6 +294,19 @@ int make_wf(locohd_ctx* ctx, const locohd_weight_function& in, WfDev* out) {
         default:
             return fail(ctx, LOCOHD_ERR_BAD_PARAM, "No function implemented with kind %d!", in.kind);
     }
+    {   // CDF(+inf) with the reference's formulas (cdfs.rs:5-63)
+        const double inf = std::numeric_limits<double>::infinity();
+        switch (in.kind) {
+            case LOCOHD_WF_DAGUM: w.w_inf = std::pow(1.0 + std::pow(inf / p[1], -p[0]), -p[2]); break;
+            case LOCOHD_WF_HYPER_EXP: {
+                double sum = 0.0, norm = 0.0;
+                for (int i = 0; i < in.n_params / 2; ++i) { sum += p[i] * std::exp(-p[in.n_params / 2 + i] * inf); norm += p[i]; }
+                w.w_inf = 1.0 - sum / norm;
+                break;
+            }
+            default: w.w_inf = 1.0;
+        }
+    }
     *out = w;
     return 0;
 }
@@ -306,8 +321,8 @@ int ensure_cells(locohd_structs* s, double threshold) {
     return 0;
 }
 
-int read_scan(locohd_ctx* ctx, ScanResult* host) {
-    CU(ctx, cudaMemcpyAsync(host, ctx->d_scan, sizeof(ScanResult), cudaMemcpyDeviceToHost, ctx->stream));
+int read_fill_stats(locohd_ctx* ctx, FillStats* host) {
+    CU(ctx, cudaMemcpyAsync(host, ctx->d_fill, sizeof(FillStats), cudaMemcpyDeviceToHost, ctx->stream));
     return sync_and_check(ctx);
 }
 
@@ -315,24 +330,35 @@ void destroy_envset(locohd_envset* e) {
     if (!e) return;
     locohd_ctx* ctx = e->ctx;
     DeviceGuard g(ctx->device);
-    dev_free(ctx, e->d_off); dev_free(ctx, e->d_count); dev_free(ctx, e->d_dist); dev_free(ctx, e->d_cat);
-    dev_free(ctx, e->d_idx);
+    dev_free(ctx, e->d_off); dev_free(ctx, e->d_count); dev_free(ctx, e->d_key); dev_free(ctx, e->d_cat);
+    dev_free(ctx, e->d_dist); dev_free(ctx, e->d_idx);
     delete e;
 }
 
-int alloc_envset_storage(locohd_ctx* ctx, locohd_envset* e, bool keep_indices) {
-    TRY_ST(dev_alloc(ctx, &e->d_dist, e->total));
-    TRY_ST(dev_alloc(ctx, &e->d_cat, e->total));
-    if (keep_indices) TRY_ST(dev_alloc(ctx, &e->d_idx, e->total));
+void free_envset_storage(locohd_ctx* ctx, locohd_envset* e) {
+    dev_free(ctx, e->d_key); dev_free(ctx, e->d_cat); dev_free(ctx, e->d_dist); dev_free(ctx, e->d_idx);
+}
+
+int alloc_envset_storage(locohd_ctx* ctx, locohd_envset* e, uint64_t capacity, bool debug) {
+    TRY_ST(dev_alloc(ctx, &e->d_key, capacity));
+    TRY_ST(dev_alloc(ctx, &e->d_cat, capacity));
+    if (debug) {
+        TRY_ST(dev_alloc(ctx, &e->d_idx, capacity));
+        if (e->key_is_w) TRY_ST(dev_alloc(ctx, &e->d_dist, capacity));
+    }
     return 0;
 }
 
-EnvOut env_out(const locohd_envset* e) {
+EnvOut env_out(locohd_ctx* ctx, const locohd_envset* e, uint64_t capacity) {
     EnvOut o;
-    o.n_env = e->n_env; o.off = e->d_off; o.count = e->d_count; o.dist = e->d_dist; o.cat = e->d_cat; o.idx = e->d_idx;
+    o.n_env = e->n_env; o.off = e->d_off; o.count = e->d_count; o.key = e->d_key; o.cat = e->d_cat;
+    o.dist = e->d_dist; o.idx = e->d_idx; o.capacity = capacity; o.stats = ctx->d_fill; o.key_is_w = e->key_is_w ? 1 : 0;
     return o;
 }
 
+// kd-tree build + env_from_idx for a list of anchors (locohd.rs:504-542): cell lists, a sampled size probe to
+// choose the shared-memory class and the store capacity, then one gather+sort+store launch whose store is
+// allocated by a device cursor; the rare overflow is repeated with the exact capacity.
 int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const uint32_t* d_anchor_struct,
                  const uint32_t* d_anchor_prim, double threshold, int keep_indices, locohd_envset** out) {
     if (!(threshold > 0.0))  // NaN included: nothing passes `d2 < r*r`, the reference then panics on dists[0]
@@ -341,31 +367,66 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
     locohd_envset* e = new locohd_envset();
     e->ctx = ctx;
     e->n_env = n_anchors;
+    e->key_is_w = ctx->kp.n_wf == 1;  // a single weight function: the store holds W(distance) directly
     auto bail = [&](int st) { destroy_envset(e); return st; };
     int st;
     if ((st = dev_alloc(ctx, &e->d_count, n_anchors))) return bail(st);
-    if ((st = dev_alloc(ctx, &e->d_off, n_anchors + 1))) return bail(st);
-    uint64_t* d_block_sums = nullptr;
-    if ((st = dev_alloc(ctx, &d_block_sums, scan_scratch_entries(n_anchors)))) return bail(st);
+    if ((st = dev_alloc(ctx, &e->d_off, n_anchors))) return bail(st);
     const StructsView sv = s->view();
-    { ProfScope ps(ctx, LOCOHD_PROF_COUNT);
-      ctx->launches += launch_env_count(sv, ctx->kp, n_anchors, d_anchor_struct, d_anchor_prim, threshold, e->d_count,
-                                        ctx->stream); }
-    { ProfScope ps(ctx, LOCOHD_PROF_SCAN);
-      ctx->launches += launch_scan_counts(e->d_count, n_anchors, e->d_off, d_block_sums, ctx->d_scan, ctx->stream); }
-    ScanResult sr{};
-    st = read_scan(ctx, &sr);
-    dev_free(ctx, d_block_sums);
-    if (st) return bail(st);
-    e->total = sr.total;
-    e->max_count = sr.max_count;
-    if ((st = alloc_envset_storage(ctx, e, keep_indices != 0))) return bail(st);
-    { ProfScope ps(ctx, LOCOHD_PROF_FILL);
-      ctx->launches += launch_env_fill(sv, ctx->kp, d_anchor_struct, d_anchor_prim, threshold, env_out(e), sr, ctx->stream); }
-    cudaError_t ce = cudaGetLastError();
-    if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
-    *out = e;
-    return 0;
+    if (n_anchors == 0) { *out = e; return 0; }
+
+    // ---- size probe on a strided sample
+    const uint64_t want = std::max<uint64_t>(2048, n_anchors / 64);
+    const uint64_t stride = std::max<uint64_t>(1, n_anchors / want);
+    const uint64_t n_sample = (n_anchors + stride - 1) / stride;
+    std::vector<uint32_t> sample(n_sample);
+    {
+        uint32_t* d_sample = nullptr;
+        if ((st = dev_alloc(ctx, &d_sample, n_sample))) return bail(st);
+        { ProfScope ps(ctx, LOCOHD_PROF_COUNT);
+          ctx->launches += launch_env_count_sample(sv, ctx->kp, n_sample, stride, d_anchor_struct, d_anchor_prim,
+                                                   threshold, d_sample, ctx->stream); }
+        cudaError_t ce = cudaMemcpyAsync(sample.data(), d_sample, n_sample * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        st = ce == cudaSuccess ? sync_and_check(ctx) : fail(ctx, LOCOHD_ERR_CUDA, "copy failed: %s", cudaGetErrorString(ce));
+        dev_free(ctx, d_sample);
+        if (st) return bail(st);
+    }
+    uint64_t sum = 0;
+    uint32_t smax = 0;
+    for (uint32_t c : sample) { sum += c; smax = std::max(smax, c); }
+    const double mean = (double)sum / (double)n_sample;
+    uint64_t capacity = (uint64_t)(mean * 1.10 * (double)n_anchors) + 64ull * smax + 4096;
+    if (n_sample == n_anchors) capacity = sum;  // the probe saw everything
+    int cap_class = 2048;
+    for (int c : {256, 512, 1024, 2048}) if ((double)smax * 1.2 <= (double)c) { cap_class = c; break; }
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((st = alloc_envset_storage(ctx, e, capacity, keep_indices != 0))) return bail(st);
+        { ProfScope ps(ctx, LOCOHD_PROF_FILL);
+          ctx->launches += launch_env_fill(sv, ctx->kp, d_anchor_struct, d_anchor_prim, threshold,
+                                           env_out(ctx, e, capacity), cap_class, ctx->stream); }
+        FillStats fs{};
+        if ((st = read_fill_stats(ctx, &fs))) return bail(st);
+        e->total = fs.cursor;
+        e->max_count = fs.max_count;
+        if (!fs.overflow) {
+            if (fs.n_big) {
+                ProfScope ps(ctx, LOCOHD_PROF_FILL);
+                ctx->launches += launch_env_fill_big(sv, ctx->kp, d_anchor_struct, d_anchor_prim, threshold,
+                                                     env_out(ctx, e, capacity), cap_class, ctx->stream);
+            }
+            cudaError_t ce = cudaGetLastError();
+            if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
+            *out = e;
+            return 0;
+        }
+        // the estimate was too small: the cursor now holds the exact total
+        free_envset_storage(ctx, e);
+        capacity = fs.cursor;
+        if (fs.max_count > (unsigned)cap_class && cap_class < 2048)
+            for (int c : {512, 1024, 2048}) if (c > cap_class && (fs.max_count <= (unsigned)c || c == 2048)) { cap_class = c; break; }
+    }
+    return bail(fail(ctx, LOCOHD_ERR_CUDA, "environment store allocation failed twice"));
 }
 
 int run_score(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_pairs,
@@ -376,7 +437,15 @@ int run_score(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, u
     sa.n_pairs = n_pairs; sa.pairs = d_pairs; sa.jobs = d_jobs; sa.job_pair_off = d_job_off; sa.n_jobs = n_jobs;
     sa.uniform_n = uniform_n; sa.wf_idx = d_wf_idx; sa.out = d_out; sa.stage_cap = 0;
     int n;
-    { ProfScope ps(ctx, LOCOHD_PROF_SCORE); n = launch_score(sa, ctx->kp, a->max_count, b->max_count, ctx->stream); }
+    if (a->key_is_w != b->key_is_w) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "environment sets were built with different weight-function modes");
+    // stage in shared memory what a typical pair needs (1.5 x the mean sizes, at most the maxima); larger pairs
+    // read their environments from global memory
+    const double mean_a = a->n_env ? (double)a->total / (double)a->n_env : 0.0;
+    const double mean_b = b->n_env ? (double)b->total / (double)b->n_env : 0.0;
+    uint64_t stage = (uint64_t)(1.5 * (mean_a + mean_b)) + 64;
+    stage = std::min<uint64_t>(stage, (uint64_t)a->max_count + b->max_count);
+    stage = (stage + 63) & ~63ull;
+    { ProfScope ps(ctx, LOCOHD_PROF_SCORE); n = launch_score(sa, ctx->kp, (unsigned)stage, 0, ctx->stream); }
     if (n < 0) return fail(ctx, LOCOHD_ERR_UNSUPPORTED, "shared memory budget exceeded for %d categories", ctx->kp.C);
     ctx->launches += n;
     CU(ctx, cudaGetLastError());
@@ -453,7 +522,7 @@ int locohd_ctx_create(int device, locohd_ctx** out) {
     }
     if ((ce = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMemset(ctx->d_err, 0, sizeof(int))) != cudaSuccess) return bail(ce);
-    if ((ce = cudaMalloc(&ctx->d_scan, sizeof(ScanResult))) != cudaSuccess) return bail(ce);
+    if ((ce = cudaMalloc(&ctx->d_fill, sizeof(FillStats))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMalloc(&ctx->d_sqrt_tbl, kSqrtTableSize * sizeof(double))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMalloc(&ctx->d_rsqrt_tbl, kSqrtTableSize * sizeof(double))) != cudaSuccess) return bail(ce);
     std::vector<double> t(kSqrtTableSize), r(kSqrtTableSize);
@@ -472,7 +541,7 @@ void locohd_ctx_destroy(locohd_ctx* ctx) {
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_cat_w); cudaFree(ctx->d_cat_sw); cudaFree(ctx->d_wfs); cudaFree(ctx->d_tag_pairs);
-    cudaFree(ctx->d_sqrt_tbl); cudaFree(ctx->d_rsqrt_tbl); cudaFree(ctx->d_err); cudaFree(ctx->d_scan);
+    cudaFree(ctx->d_sqrt_tbl); cudaFree(ctx->d_rsqrt_tbl); cudaFree(ctx->d_err); cudaFree(ctx->d_fill);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -734,14 +803,18 @@ static int rows_envset(locohd_ctx* ctx, uint64_t n_rows, uint64_t row_len, const
     if (xyz) ctx->launches += launch_validate_xyz(in.ptr, 3 * row_len, ctx->d_err, ctx->stream);
     locohd_envset* e = new locohd_envset();
     e->ctx = ctx; e->n_env = n_rows; e->total = n_rows * row_len; e->max_count = (unsigned)row_len;
+    e->key_is_w = ctx->kp.n_wf == 1;
     auto bail = [&](int st) { dev_free(ctx, d_cat8); destroy_envset(e); return st; };
     int st;
-    if ((st = dev_alloc(ctx, &e->d_count, n_rows)) || (st = dev_alloc(ctx, &e->d_off, n_rows + 1)) ||
-        (st = alloc_envset_storage(ctx, e, true)))
+    if ((st = dev_alloc(ctx, &e->d_count, n_rows)) || (st = dev_alloc(ctx, &e->d_off, n_rows)) ||
+        (st = alloc_envset_storage(ctx, e, e->total, true)))
         return bail(st);
-    ctx->launches += launch_fill_u64_iota_rows(e->d_off, e->d_count, n_rows, row_len, ctx->stream);
-    ctx->launches += launch_rows_fill(dmx ? in.ptr : nullptr, d_cat8, n_rows, row_len, xyz ? in.ptr : nullptr, ctx->kp,
-                                      env_out(e), ctx->stream);
+    {
+        ProfScope ps(ctx, LOCOHD_PROF_OTHER);
+        ctx->launches += launch_fill_u64_iota_rows(e->d_off, e->d_count, n_rows, row_len, ctx->stream);
+        ctx->launches += launch_rows_fill(dmx ? in.ptr : nullptr, d_cat8, n_rows, row_len, xyz ? in.ptr : nullptr,
+                                          ctx->kp, env_out(ctx, e, e->total), ctx->stream);
+    }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
     if ((st = sync_and_check(ctx))) return bail(st);
@@ -775,18 +848,46 @@ int locohd_envset_dump(locohd_ctx* ctx, const locohd_envset* e, uint64_t* offset
     API_BEGIN(ctx)
     if (!e) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null envset");
     TRY_ST(sync_and_check(ctx));
-    if (offsets) CU(ctx, cudaMemcpy(offsets, e->d_off, (e->n_env + 1) * sizeof(uint64_t), cudaMemcpyDefault));
-    if (distances && e->total) CU(ctx, cudaMemcpy(distances, e->d_dist, e->total * sizeof(double), cudaMemcpyDefault));
-    if (categories && e->total) {
+    // The store is cursor-allocated (arbitrary environment order on the device): the dump is laid out in
+    // environment order, offsets = running sum of the sizes.
+    const uint64_t n = e->n_env;
+    std::vector<uint64_t> off(n), canon(n + 1, 0);
+    std::vector<uint32_t> cnt(n);
+    if (n) {
+        CU(ctx, cudaMemcpy(off.data(), e->d_off, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        CU(ctx, cudaMemcpy(cnt.data(), e->d_count, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    for (uint64_t i = 0; i < n; ++i) canon[i + 1] = canon[i] + cnt[i];
+    const uint64_t total = canon[n];
+    auto put = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        return cudaMemcpy(dst, src, bytes, cudaMemcpyDefault);
+    };
+    if (offsets) CU(ctx, put(offsets, canon.data(), (n + 1) * sizeof(uint64_t)));
+    if (distances && total) {
+        const double* src = e->key_is_w ? e->d_dist : e->d_key;
+        if (!src) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "envset was built without keep_indices: distances are not kept");
+        std::vector<double> raw(e->total), outv(total);
+        CU(ctx, cudaMemcpy(raw.data(), src, e->total * sizeof(double), cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < n; ++i) std::copy(raw.begin() + off[i], raw.begin() + off[i] + cnt[i], outv.begin() + canon[i]);
+        CU(ctx, put(distances, outv.data(), total * sizeof(double)));
+    }
+    if (categories && total) {
         std::vector<uint8_t> c8(e->total);
         CU(ctx, cudaMemcpy(c8.data(), e->d_cat, e->total, cudaMemcpyDeviceToHost));
-        std::vector<uint16_t> c16(e->total);
-        for (uint64_t i = 0; i < e->total; ++i) c16[i] = c8[i] == kUnknownCat8 ? (uint16_t)LOCOHD_UNKNOWN_CATEGORY : c8[i];
-        CU(ctx, cudaMemcpy(categories, c16.data(), e->total * sizeof(uint16_t), cudaMemcpyDefault));
+        std::vector<uint16_t> c16(total);
+        for (uint64_t i = 0; i < n; ++i)
+            for (uint32_t k = 0; k < cnt[i]; ++k) {
+                const uint8_t c = c8[off[i] + k];
+                c16[canon[i] + k] = c == kUnknownCat8 ? (uint16_t)LOCOHD_UNKNOWN_CATEGORY : c;
+            }
+        CU(ctx, put(categories, c16.data(), total * sizeof(uint16_t)));
     }
-    if (prim_indices && e->total) {
+    if (prim_indices && total) {
         if (!e->d_idx) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "envset was built without keep_indices");
-        CU(ctx, cudaMemcpy(prim_indices, e->d_idx, e->total * sizeof(uint32_t), cudaMemcpyDefault));
+        std::vector<uint32_t> raw(e->total), outv(total);
+        CU(ctx, cudaMemcpy(raw.data(), e->d_idx, e->total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < n; ++i) std::copy(raw.begin() + off[i], raw.begin() + off[i] + cnt[i], outv.begin() + canon[i]);
+        CU(ctx, put(prim_indices, outv.data(), total * sizeof(uint32_t)));
     }
     return 0;
     API_END()

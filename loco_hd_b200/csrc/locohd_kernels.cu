@@ -292,147 +292,172 @@ __device__ __forceinline__ uint32_t gather_environment(const StructsView& s, con
 
 constexpr int kEnvWarps = 4;
 
-__global__ void __launch_bounds__(kEnvWarps * 32) env_count_kernel(StructsView s, KParams p, uint64_t n_env,
-                                                                   const uint32_t* __restrict__ anchor_struct,
-                                                                   const uint32_t* __restrict__ anchor_prim,
-                                                                   double threshold, uint32_t* __restrict__ count) {
+// Size probe on a strided sample of the anchors (capacity estimate for the cursor-allocated store).
+__global__ void __launch_bounds__(kEnvWarps * 32) env_count_sample_kernel(StructsView s, KParams p, uint64_t n_sample,
+                                                                          uint64_t stride,
+                                                                          const uint32_t* __restrict__ anchor_struct,
+                                                                          const uint32_t* __restrict__ anchor_prim,
+                                                                          double threshold,
+                                                                          uint32_t* __restrict__ count) {
     const int lane = threadIdx.x & 31;
-    const uint64_t e = (uint64_t)blockIdx.x * kEnvWarps + (threadIdx.x >> 5);
-    if (e >= n_env) return;
-    const AnchorRef a = resolve_anchor(s, anchor_struct, anchor_prim, e, p.err);
+    const uint64_t i = (uint64_t)blockIdx.x * kEnvWarps + (threadIdx.x >> 5);
+    if (i >= n_sample) return;
+    const AnchorRef a = resolve_anchor(s, anchor_struct, anchor_prim, i * stride, p.err);
     uint32_t m = 0;
     if (a.ok) m = gather_environment(s, p, a, threshold, lane, [](uint32_t, double, uint32_t) {});
-    if (lane == 0) count[e] = m;
+    if (lane == 0) count[i] = m;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Per-warp bucket sort in shared memory.
-//   keys are non-NaN doubles; buckets are a monotone function of the key chosen so that spherical
-//   environments fill them evenly (members within distance d grow like d^3), then every entry finds its exact
-//   rank inside its bucket by comparison.  Expected O(M) work per environment instead of O(M log^2 M).
+//   keys are non-NaN doubles.  (1) every entry goes to a bucket that is a monotone function of its key,
+//   (2) buckets are laid out by a warp prefix sum, (3) every lane insertion-sorts a few (mostly 0-2 entry)
+//   buckets, after which `perm` lists the entries in ascending key order, so the caller can emit them with
+//   coalesced stores.  Expected O(M) work per environment.
 // ------------------------------------------------------------------------------------------------
 template <int CAP>
 struct WarpSortLayout {
-    static constexpr int NB = CAP / 2;
+    static constexpr int NB = CAP > 1024 ? 1024 : CAP;  // buckets
     static constexpr int kKeyOff = 0;
     static constexpr int kPayOff = kKeyOff + 8 * CAP;
-    static constexpr int kStartOff = kPayOff + 4 * CAP;
-    static constexpr int kCursorOff = kStartOff + 4 * (NB + 4);
-    static constexpr int kBktOff = kCursorOff + 4 * NB;
-    static constexpr int kPermOff = kBktOff + 2 * CAP;
-    static constexpr int kBytes = kPermOff + 2 * CAP;
+    static constexpr int kEndOff = kPayOff + 4 * CAP;          // u32 [NB]: bucket end offsets
+    static constexpr int kBktOff = kEndOff + 4 * NB;           // u16 [CAP]
+    static constexpr int kPermOff = kBktOff + 2 * CAP;         // u16 [CAP]
+    static constexpr int kBytes = kPermOff + 2 * CAP;          // 16 * CAP + 4 * NB
 };
 
-// KEY_IS_SQUARED: keys are squared distances (bucket ~ x^1.5) else plain distances (bucket ~ x^3).
-template <int CAP, bool KEY_IS_SQUARED, class Emit>
-__device__ __forceinline__ void warp_bucket_sort(unsigned char* smem, uint32_t M, int lane, Emit&& emit) {
+// `scale` maps a key to [0, NB): bucket = clamp(int((float)(key * scale))).  scale <= 0 asks for the scale
+// to be derived from the largest finite key.  Returns with perm[0..M) = entry indices in ascending key order
+// (ties in arrival order) after a __syncwarp.
+template <int CAP>
+__device__ __forceinline__ void warp_bucket_sort(unsigned char* smem, uint32_t M, int lane, double scale) {
     using L = WarpSortLayout<CAP>;
     constexpr int NB = L::NB;
-    double* key = reinterpret_cast<double*>(smem + L::kKeyOff);
-    uint32_t* pay = reinterpret_cast<uint32_t*>(smem + L::kPayOff);
-    uint32_t* start = reinterpret_cast<uint32_t*>(smem + L::kStartOff);
-    uint32_t* cursor = reinterpret_cast<uint32_t*>(smem + L::kCursorOff);
+    const double* key = reinterpret_cast<const double*>(smem + L::kKeyOff);
+    uint32_t* bend = reinterpret_cast<uint32_t*>(smem + L::kEndOff);
     uint16_t* bkt = reinterpret_cast<uint16_t*>(smem + L::kBktOff);
     uint16_t* perm = reinterpret_cast<uint16_t*>(smem + L::kPermOff);
 
-    // largest finite key
-    double kmax = 0.0;
-    for (uint32_t e = lane; e < M; e += 32) {
-        const double k = key[e];
-        if (isfinite(k)) kmax = fmax(kmax, k);
+    if (!(scale > 0.0)) {
+        double kmax = 0.0;
+        for (uint32_t e = lane; e < M; e += 32) {
+            const double k = key[e];
+            if (isfinite(k)) kmax = fmax(kmax, k);
+        }
+        for (int o = 16; o; o >>= 1) kmax = fmax(kmax, __shfl_xor_sync(kFull, kmax, o));
+        scale = (kmax > 0.0) ? ((double)NB * (1.0 - 1e-9)) / kmax : 0.0;
     }
-    for (int o = 16; o; o >>= 1) kmax = fmax(kmax, __shfl_xor_sync(kFull, kmax, o));
-    const double inv = (kmax > 0.0) ? 1.0 / kmax : 0.0;
-
-    for (int b = lane; b < NB; b += 32) start[b] = 0;
+    for (int b = lane; b < NB; b += 32) bend[b] = 0;
     __syncwarp();
     for (uint32_t e = lane; e < M; e += 32) {
-        const float x = (float)(key[e] * inv);
-        const float f = KEY_IS_SQUARED ? x * sqrtf(fmaxf(x, 0.f)) : x * x * x;
-        int b = (int)fminf(f * (float)NB, (float)(NB - 1));  // NaN/negative handled by the max below
+        const float f = (float)(key[e] * scale);        // monotone in the key; NaN only for inf * 0
+        int b = (int)fminf(f, (float)(NB - 1));         // fminf(NaN, x) = x: infinities land in the last bucket
         b = max(b, 0);
         bkt[e] = (uint16_t)b;
-        atomicAdd(&start[b], 1u);
+        atomicAdd(&bend[b], 1u);
     }
     __syncwarp();
-    // exclusive scan over NB buckets: NB/32 consecutive buckets per lane
-    {
+    {   // exclusive prefix over the buckets, NB/32 consecutive buckets per lane; bend[b] := start of bucket b
         constexpr int PER = NB / 32;
-        uint32_t loc[PER];
         uint32_t sum = 0;
-#pragma unroll
-        for (int q = 0; q < PER; ++q) { loc[q] = start[lane * PER + q]; sum += loc[q]; }
+#pragma unroll 8
+        for (int q = 0; q < PER; ++q) sum += bend[lane * PER + q];
         uint32_t incl = sum;
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t v = __shfl_up_sync(kFull, incl, o);
             if (lane >= o) incl += v;
         }
         uint32_t run = incl - sum;
-        __syncwarp();
-#pragma unroll
+#pragma unroll 8
         for (int q = 0; q < PER; ++q) {
-            start[lane * PER + q] = run;
-            cursor[lane * PER + q] = run;
-            run += loc[q];
+            const uint32_t v = bend[lane * PER + q];
+            bend[lane * PER + q] = run;
+            run += v;
         }
-        if (lane == 31) start[NB] = run;
     }
     __syncwarp();
-    for (uint32_t e = lane; e < M; e += 32) {
-        const uint32_t pos = atomicAdd(&cursor[bkt[e]], 1u);
+    for (uint32_t e = lane; e < M; e += 32) {   // scatter; afterwards bend[b] = end of bucket b
+        const uint32_t pos = atomicAdd(&bend[bkt[e]], 1u);
         perm[pos] = (uint16_t)e;
     }
     __syncwarp();
-    for (uint32_t e = lane; e < M; e += 32) {
-        const uint32_t b = bkt[e];
-        const uint32_t s0 = start[b], s1 = start[b + 1];
-        const double k = key[e];
-        uint32_t rank = 0;
-        for (uint32_t t = s0; t < s1; ++t) {
-            const uint32_t f = perm[t];
-            const double kf = key[f];
-            rank += (kf < k || (kf == k && f < e)) ? 1u : 0u;
+    // insertion sort inside every bucket (bucket b = [bend[b-1], bend[b])); lanes own interleaved buckets
+    for (int b = lane; b < NB; b += 32) {
+        const uint32_t s0 = b ? bend[b - 1] : 0u, s1 = bend[b];
+        for (uint32_t t = s0 + 1; t < s1; ++t) {
+            const uint16_t e = perm[t];
+            const double k = key[e];
+            uint32_t u = t;
+            while (u > s0) {
+                const uint16_t f = perm[u - 1];
+                const double kf = key[f];
+                if (kf < k || (kf == k && f < e)) break;
+                perm[u] = f;
+                --u;
+            }
+            perm[u] = e;
         }
-        emit(s0 + rank, k, pay[e]);
     }
+    __syncwarp();
 }
 
-// K1': gather + sort + store.  Processes environments whose size lies in (MIN_M, CAP].
+__device__ __forceinline__ double gather_sort_scale(double threshold, int nb) {
+    const double r2 = threshold * threshold;
+    return (isfinite(r2) && r2 > 0.0) ? ((double)nb * (1.0 - 1e-9)) / r2 : 0.0;  // keys are d^2 < r^2
+}
+
+// K1': gather + sort + store.  The store is allocated with one atomicAdd per environment on a global cursor.
 template <int CAP>
 __global__ void __launch_bounds__(kEnvWarps * 32) env_fill_kernel(StructsView s, KParams p,
                                                                   const uint32_t* __restrict__ anchor_struct,
                                                                   const uint32_t* __restrict__ anchor_prim,
-                                                                  double threshold, EnvOut out, uint32_t min_m) {
+                                                                  double threshold, EnvOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using L = WarpSortLayout<CAP>;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t e = (uint64_t)blockIdx.x * kEnvWarps + wib;
     if (e >= out.n_env) return;
-    const uint32_t expect = out.count[e];
-    if (expect <= min_m || expect > (uint32_t)CAP) return;
     unsigned char* smem = smem_raw + (size_t)wib * L::kBytes;
     double* key = reinterpret_cast<double*>(smem + L::kKeyOff);
     uint32_t* pay = reinterpret_cast<uint32_t*>(smem + L::kPayOff);
+    const uint16_t* perm = reinterpret_cast<const uint16_t*>(smem + L::kPermOff);
 
     const AnchorRef a = resolve_anchor(s, anchor_struct, anchor_prim, e, p.err);
-    if (!a.ok) return;
+    if (!a.ok) {
+        if (lane == 0) { out.count[e] = 0; out.off[e] = 0; }
+        return;
+    }
     const uint32_t M = gather_environment(s, p, a, threshold, lane, [&](uint32_t slot, double d2, uint32_t j) {
         if (slot < (uint32_t)CAP) { key[slot] = d2; pay[slot] = j; }
     });
-    if (M != expect) { raise(p.err, LOCOHD_ERR_CUDA); return; }  // count and fill passes must agree
+    unsigned long long off = 0;
+    if (lane == 0) {
+        off = atomicAdd(&out.stats->cursor, (unsigned long long)M);
+        out.count[e] = M;
+        out.off[e] = off;
+        atomicMax(&out.stats->max_count, M);
+        if (M > (uint32_t)CAP) atomicAdd(&out.stats->n_big, 1u);
+        if (off + M > out.capacity) atomicOr(&out.stats->overflow, 1u);
+    }
+    off = __shfl_sync(kFull, off, 0);
+    if (M > (uint32_t)CAP || off + M > out.capacity) return;  // big path / retry with the exact capacity
     __syncwarp();
-    const uint64_t off = out.off[e];
+    warp_bucket_sort<CAP>(smem, M, lane, gather_sort_scale(threshold, L::NB));
     const PrimRec* pd = s.pd + a.base;
-    warp_bucket_sort<CAP, true>(smem, M, lane, [&](uint32_t pos, double d2, uint32_t j) {
-        out.dist[off + pos] = sqrt(d2);  // utils.rs:1-8
-        const PrimRec* r = pd + j;
+    const WfDev& wf = p.wfs[0];
+    for (uint32_t pos = lane; pos < M; pos += 32) {   // ascending order, coalesced stores
+        const uint32_t en = perm[pos];
+        const double d = sqrt(key[en]);               // utils.rs:1-8
+        const PrimRec* r = pd + pay[en];
+        out.key[off + pos] = out.key_is_w ? wf_cdf(wf, d) : d;
         out.cat[off + pos] = (uint8_t)r->cat;
+        if (out.dist) out.dist[off + pos] = d;
         if (out.idx) out.idx[off + pos] = r->orig;
-    });
+    }
 }
 
-// Environments larger than every shared-memory class: written unsorted, then sorted in place by
-// bitonic_sort_big_kernel.
+// Environments larger than the shared-memory class: written unsorted (plain distances as keys), then sorted in
+// place by bitonic_sort_big_kernel, which also converts the keys to W when the store holds W.
 __global__ void __launch_bounds__(kEnvWarps * 32) env_fill_unsorted_kernel(StructsView s, KParams p,
                                                                            const uint32_t* __restrict__ anchor_struct,
                                                                            const uint32_t* __restrict__ anchor_prim,
@@ -449,7 +474,7 @@ __global__ void __launch_bounds__(kEnvWarps * 32) env_fill_unsorted_kernel(Struc
     const PrimRec* pd = s.pd + a.base;
     const uint32_t M = gather_environment(s, p, a, threshold, lane, [&](uint32_t slot, double d2, uint32_t j) {
         if (slot < expect) {
-            out.dist[off + slot] = sqrt(d2);
+            out.key[off + slot] = sqrt(d2);
             const PrimRec* r = pd + j;
             out.cat[off + slot] = (uint8_t)r->cat;
             if (out.idx) out.idx[off + slot] = r->orig;
@@ -461,12 +486,13 @@ __global__ void __launch_bounds__(kEnvWarps * 32) env_fill_unsorted_kernel(Struc
 // In-place ascending bitonic network (min always to the lower index, so the virtual +inf padding above M
 // never moves).  One CTA per environment with more than min_m members.
 constexpr int kBigThreads = 256;
-__global__ void __launch_bounds__(kBigThreads) bitonic_sort_big_kernel(EnvOut out, uint32_t min_m) {
+__global__ void __launch_bounds__(kBigThreads) bitonic_sort_big_kernel(EnvOut out, KParams p, uint32_t min_m,
+                                                                       int check_first_zero) {
     const uint64_t e = blockIdx.x;
     const uint32_t M = out.count[e];
     if (M <= min_m) return;
     const uint64_t off = out.off[e];
-    double* d = out.dist + off;
+    double* d = out.key + off;
     uint8_t* c = out.cat + off;
     uint32_t* ix = out.idx ? out.idx + off : nullptr;
     uint32_t n2 = 1;
@@ -496,100 +522,14 @@ __global__ void __launch_bounds__(kBigThreads) bitonic_sort_big_kernel(EnvOut ou
             __syncthreads();
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Exclusive scan of the environment sizes (u32 -> u64 offsets) + size-class statistics.
-// ------------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 256;
-constexpr int kScanPer = 8;
-constexpr int kScanTile = kScanThreads * kScanPer;
-
-__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* total) {
-    __shared__ unsigned long long wsum[kScanThreads / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned long long incl = v;
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long u = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += u;
-    }
-    if (lane == 31) wsum[wid] = incl;
-    __syncthreads();
-    unsigned long long base = 0, tot = 0;
-    for (int w = 0; w < kScanThreads / 32; ++w) {
-        if (w < wid) base += wsum[w];
-        tot += wsum[w];
-    }
-    __syncthreads();
-    if (total) *total = tot;
-    return base + incl - v;
-}
-
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t* __restrict__ count, uint64_t n,
-                                                                      uint64_t* __restrict__ block_sums,
-                                                                      ScanResult* res) {
-    const uint64_t t0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPer;
-    unsigned long long sum = 0;
-    unsigned mx = 0, ns = 0, nm = 0, nl = 0, nh = 0;
-    for (int q = 0; q < kScanPer; ++q) {
-        const uint64_t i = t0 + q;
-        if (i < n) {
-            const unsigned c = count[i];
-            sum += c;
-            mx = max(mx, c);
-            if (c <= 256) ++ns; else if (c <= 512) ++nm; else if (c <= 2048) ++nl; else ++nh;
+    if (check_first_zero && threadIdx.x == 0 && d[0] != 0.0) raise(p.err, LOCOHD_ERR_FIRST_NOT_ZERO);
+    if (out.dist || out.key_is_w) {
+        const WfDev& wf = p.wfs[0];
+        for (uint32_t i = threadIdx.x; i < M; i += kBigThreads) {
+            const double v = d[i];
+            if (out.dist) out.dist[off + i] = v;
+            if (out.key_is_w) d[i] = (v < 0.0) ? 0.0 : wf_cdf(wf, v);
         }
-    }
-    unsigned long long tot;
-    block_exclusive_scan(sum, &tot);
-    for (int o = 16; o; o >>= 1) {
-        mx = max(mx, __shfl_xor_sync(kFull, mx, o));
-        ns += __shfl_xor_sync(kFull, ns, o);
-        nm += __shfl_xor_sync(kFull, nm, o);
-        nl += __shfl_xor_sync(kFull, nl, o);
-        nh += __shfl_xor_sync(kFull, nh, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(&res->max_count, mx);
-        if (ns) atomicAdd(&res->n_small, ns);
-        if (nm) atomicAdd(&res->n_medium, nm);
-        if (nl) atomicAdd(&res->n_large, nl);
-        if (nh) atomicAdd(&res->n_huge, nh);
-    }
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
-}
-
-__global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(uint64_t* block_sums, uint64_t n_blocks,
-                                                                       ScanResult* res) {
-    unsigned long long carry = 0;
-    for (uint64_t b0 = 0; b0 < n_blocks; b0 += kScanThreads) {
-        const uint64_t i = b0 + threadIdx.x;
-        const unsigned long long v = (i < n_blocks) ? block_sums[i] : 0ull;
-        unsigned long long tot;
-        const unsigned long long ex = block_exclusive_scan(v, &tot);
-        if (i < n_blocks) block_sums[i] = carry + ex;
-        carry += tot;
-    }
-    if (threadIdx.x == 0) res->total = carry;
-}
-
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ count, uint64_t n,
-                                                                  const uint64_t* __restrict__ block_sums,
-                                                                  uint64_t* __restrict__ off) {
-    const uint64_t t0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPer;
-    unsigned loc[kScanPer];
-    unsigned long long sum = 0;
-    for (int q = 0; q < kScanPer; ++q) {
-        const uint64_t i = t0 + q;
-        loc[q] = (i < n) ? count[i] : 0u;
-        sum += loc[q];
-    }
-    unsigned long long run = block_sums[blockIdx.x] + block_exclusive_scan(sum, nullptr);
-    for (int q = 0; q < kScanPer; ++q) {
-        const uint64_t i = t0 + q;
-        if (i < n) off[i] = run;
-        run += loc[q];
-        if (i + 1 == n) off[n] = run;
     }
 }
 
@@ -598,8 +538,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 // ------------------------------------------------------------------------------------------------
 __global__ void iota_rows_kernel(uint64_t* off, uint32_t* count, uint64_t n_rows, uint64_t row_len) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= n_rows) off[i] = i * row_len;
-    if (i < n_rows) count[i] = (uint32_t)row_len;
+    if (i < n_rows) { off[i] = i * row_len; count[i] = (uint32_t)row_len; }
 }
 
 // distance of point i to point j exactly as utils.rs:1-22 (squares are symmetric, the diagonal is 0)
@@ -621,65 +560,64 @@ __global__ void __launch_bounds__(kEnvWarps * 32) rows_fill_kernel(const double*
     if (row >= n_rows) return;
     unsigned char* smem = smem_raw + (size_t)wib * L::kBytes;
     double* key = reinterpret_cast<double*>(smem + L::kKeyOff);
-    uint32_t* pay = reinterpret_cast<uint32_t*>(smem + L::kPayOff);
+    const uint16_t* perm = reinterpret_cast<const uint16_t*>(smem + L::kPermOff);
     const uint32_t M = (uint32_t)row_len;
     bool bad = false;
     for (uint32_t j = lane; j < M; j += 32) {
         const double d = xyz ? row_distance(xyz, row, j) : dmx[row * row_len + j];
         bad |= isnan(d);
         key[j] = d;
-        pay[j] = j;
     }
     if (__any_sync(kFull, bad)) { raise(p.err, LOCOHD_ERR_NAN); return; }  // partial_cmp().unwrap() panics (utils.rs:28)
     __syncwarp();
+    warp_bucket_sort<CAP>(smem, M, lane, 0.0);
     const uint64_t off = out.off[row];
-    warp_bucket_sort<CAP, false>(smem, M, lane, [&](uint32_t pos, double d, uint32_t j) {
-        out.dist[off + pos] = d;
+    if (key[perm[0]] != 0.0) { raise(p.err, LOCOHD_ERR_FIRST_NOT_ZERO); return; }  // locohd.rs:74-77
+    const WfDev& wf = p.wfs[0];
+    for (uint32_t pos = lane; pos < M; pos += 32) {
+        const uint32_t j = perm[pos];
+        const double d = key[j];
+        out.key[off + pos] = out.key_is_w ? wf_cdf(wf, d) : d;
         out.cat[off + pos] = cat[j];
+        if (out.dist) out.dist[off + pos] = d;
         if (out.idx) out.idx[off + pos] = j;
-    });
+    }
 }
 
 __global__ void rows_copy_kernel(const double* __restrict__ dmx, const uint8_t* __restrict__ cat, uint64_t n_rows,
                                  uint64_t row_len, const double* __restrict__ xyz, KParams p, EnvOut out) {
-    const uint64_t row = blockIdx.y;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < row_len;
-         j += (uint64_t)gridDim.x * blockDim.x) {
-        const double d = xyz ? row_distance(xyz, row, j) : dmx[row * row_len + j];
-        if (isnan(d)) raise(p.err, LOCOHD_ERR_NAN);
-        out.dist[row * row_len + j] = d;
-        out.cat[row * row_len + j] = cat[j];
-        if (out.idx) out.idx[row * row_len + j] = (uint32_t)j;
+    for (uint64_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
+        for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < row_len;
+             j += (uint64_t)gridDim.x * blockDim.x) {
+            const double d = xyz ? row_distance(xyz, row, j) : dmx[row * row_len + j];
+            if (isnan(d)) raise(p.err, LOCOHD_ERR_NAN);
+            out.key[row * row_len + j] = d;
+            out.cat[row * row_len + j] = cat[j];
+            if (out.idx) out.idx[row * row_len + j] = (uint32_t)j;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: scoring.  One warp per anchor pair.
+// K2: scoring.  One warp per anchor pair (persistent warps stride over the pairs).
 // ------------------------------------------------------------------------------------------------
-constexpr int kScoreMaxWarps = 4;
-
-struct ScoreSmem {
-    int per_warp_bytes;
-    int state_bytes;
-};
+constexpr int kScoreMaxWarps = 8;
+constexpr int kFastTable = 512;  // sqrt / rsqrt table entries staged in shared memory by the fast kernel
 
 __host__ __device__ inline int score_state_bytes(int C) { return ((2 * C * 32 * 8 + 2 * C * 32 * 4) + 15) & ~15; }
 __host__ __device__ inline int score_stage_bytes(int cap) { return ((cap * 9 + 16) + 15) & ~15; }
+__host__ __device__ inline int fast_state_bytes(int CP) { return 2 * CP * 32 * 8 + CP * 32 * 4; }
 
-template <bool HELL2>
-__global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a, KParams P, int warps_per_block,
-                                                                    int per_warp_bytes) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint64_t pair = (uint64_t)blockIdx.x * warps_per_block + wib;
-    if (wib >= warps_per_block || pair >= a.n_pairs) return;
-    const int C = P.C;
-    unsigned char* mine = smem_raw + (size_t)wib * per_warp_bytes;
-    double* val = reinterpret_cast<double*>(mine);                         // [2C][32]
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(mine + 2 * C * 32 * 8);    // [2C][32]
-    unsigned char* stage = mine + score_state_bytes(C);
+struct PairEnvs {
+    bool ok;
+    uint64_t oa, ob;
+    uint32_t Ma, Mb;
+};
 
-    // ---- which environments
+// Resolves pair -> (environment of A, environment of B) in explicit or job mode and validates it (warp-uniform).
+__device__ __forceinline__ PairEnvs resolve_pair(const ScoreArgs& a, uint64_t pair, int* err) {
+    PairEnvs r;
+    r.ok = false;
     uint64_t ea, eb;
     if (a.pairs) {
         ea = a.pairs[2 * pair];
@@ -701,156 +639,332 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
         ea = a.jobs[job].a_first + within;
         eb = a.jobs[job].b_first + within;
     }
-    if (ea >= a.a.n_env || eb >= a.b.n_env) { raise(P.err, LOCOHD_ERR_INDEX); return; }
-    const uint64_t oa = a.a.off[ea], ob = a.b.off[eb];
-    const uint32_t Ma = (uint32_t)(a.a.off[ea + 1] - oa), Mb = (uint32_t)(a.b.off[eb + 1] - ob);
-    if (Ma == 0 || Mb == 0) { raise(P.err, LOCOHD_ERR_EMPTY_ENV); return; }        // locohd.rs:74 panics upstream
-    const double* gdA = a.a.dist + oa;
-    const double* gdB = a.b.dist + ob;
-    const uint8_t* gcA = a.a.cat + oa;
-    const uint8_t* gcB = a.b.cat + ob;
-    if (gdA[0] != 0.0 || gdB[0] != 0.0) { raise(P.err, LOCOHD_ERR_FIRST_NOT_ZERO); return; }  // locohd.rs:74-77
+    if (ea >= a.a.n_env || eb >= a.b.n_env) { raise(err, LOCOHD_ERR_INDEX); return r; }
+    r.oa = a.a.off[ea]; r.ob = a.b.off[eb];
+    r.Ma = a.a.count[ea]; r.Mb = a.b.count[eb];
+    if (r.Ma == 0 || r.Mb == 0) { raise(err, LOCOHD_ERR_EMPTY_ENV); return r; }  // locohd.rs:74 panics upstream
+    r.ok = true;
+    return r;
+}
 
-    // ---- stage both environments in shared memory when they fit
-    const double* dA = gdA;
-    const double* dB = gdB;
-    const uint8_t* cA = gcA;
-    const uint8_t* cB = gcB;
-    if ((int)(Ma + Mb) <= a.stage_cap) {
-        double* sd = reinterpret_cast<double*>(stage);
-        uint8_t* sc = stage + (size_t)(Ma + Mb) * 8;
-        for (uint32_t i = lane; i < Ma; i += 32) { sd[i] = gdA[i]; sc[i] = gcA[i]; }
-        for (uint32_t i = lane; i < Mb; i += 32) { sd[Ma + i] = gdB[i]; sc[Ma + i] = gcB[i]; }
-        dA = sd; dB = sd + Ma; cA = sc; cB = sc + Ma;
-        __syncwarp();
-    }
-    const uint32_t catA0 = cA[0], catB0 = cB[0];
-    // events = members after the anchor
-    dA += 1; dB += 1; cA += 1; cB += 1;
-    const uint32_t na = Ma - 1, nb = Mb - 1;
-    const uint32_t E = na + nb;
-    const uint32_t Q = (E + 31) / 32;
-
-    // ---- merge-path split: lane l owns merged events [l*Q, (l+1)*Q); A precedes B on ties
-    const uint32_t diag = min(E, (uint32_t)lane * Q);
+// merge-path split: number of A events among the first `diag` merged events (A precedes B on ties)
+__device__ __forceinline__ uint32_t merge_path(const double* kA, const double* kB, uint32_t na, uint32_t nb,
+                                               uint32_t diag) {
     uint32_t lo = diag > nb ? diag - nb : 0, hi = min(diag, na);
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (dA[mid] <= dB[diag - 1 - mid]) lo = mid + 1; else hi = mid;
+        if (kA[mid] <= kB[diag - 1 - mid]) lo = mid + 1; else hi = mid;
     }
-    uint32_t i = lo, j = diag - lo;
-    uint32_t i1 = __shfl_down_sync(kFull, i, 1), j1 = __shfl_down_sync(kFull, j, 1);
-    if (lane == 31) { i1 = na; j1 = nb; }
+    return lo;
+}
 
-    // ---- category counts before my chunk: per-lane histogram, then exclusive prefix over the lanes
-    for (int r = 0; r < 2 * C; ++r) cnt[r * 32 + lane] = 0;
-    bool unknown = (catA0 >= (uint32_t)C) || (catB0 >= (uint32_t)C);
-    for (uint32_t x = i; x < i1; ++x) {
-        const uint32_t c = cA[x];
-        if (c < (uint32_t)C) cnt[c * 32 + lane] += 1; else unknown = true;
-    }
-    for (uint32_t x = j; x < j1; ++x) {
-        const uint32_t c = cB[x];
-        if (c < (uint32_t)C) cnt[(C + c) * 32 + lane] += 1; else unknown = true;
-    }
-    if (__any_sync(kFull, unknown)) { raise(P.err, LOCOHD_ERR_UNKNOWN_CATEGORY); return; }  // pmf.rs:38-42
-    for (int r = 0; r < 2 * C; ++r) {
-        const uint32_t v = cnt[r * 32 + lane];
-        uint32_t incl = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += u;
+// Generic kernel: any C <= 255, any statistical distance, category weights, per-pair weight functions.
+template <bool HELL2>
+__global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a, KParams P, int warps_per_block,
+                                                                    int per_warp_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (wib >= warps_per_block) return;
+    const int C = P.C;
+    unsigned char* mine = smem_raw + (size_t)wib * per_warp_bytes;
+    double* val = reinterpret_cast<double*>(mine);                         // [2C][32]
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(mine + 2 * C * 32 * 8);    // [2C][32]
+    unsigned char* stage = mine + score_state_bytes(C);
+    const bool key_is_w = a.a.key_is_w != 0;
+
+    for (uint64_t pair = (uint64_t)blockIdx.x * warps_per_block + wib; pair < a.n_pairs;
+         pair += (uint64_t)gridDim.x * warps_per_block) {
+        __syncwarp();
+        const PairEnvs pe = resolve_pair(a, pair, P.err);
+        if (!pe.ok) continue;
+        const uint32_t Ma = pe.Ma, Mb = pe.Mb;
+        const double* gkA = a.a.key + pe.oa;
+        const double* gkB = a.b.key + pe.ob;
+        const uint8_t* gcA = a.a.cat + pe.oa;
+        const uint8_t* gcB = a.b.cat + pe.ob;
+        if (!key_is_w && (gkA[0] != 0.0 || gkB[0] != 0.0)) { raise(P.err, LOCOHD_ERR_FIRST_NOT_ZERO); continue; }
+
+        // ---- stage both environments in shared memory when they fit
+        const double* kA = gkA;
+        const double* kB = gkB;
+        const uint8_t* cA = gcA;
+        const uint8_t* cB = gcB;
+        if ((int)(Ma + Mb) <= a.stage_cap) {
+            double* sd = reinterpret_cast<double*>(stage);
+            uint8_t* sc = stage + (size_t)(Ma + Mb) * 8;
+            for (uint32_t i = lane; i < Ma; i += 32) { sd[i] = gkA[i]; sc[i] = gcA[i]; }
+            for (uint32_t i = lane; i < Mb; i += 32) { sd[Ma + i] = gkB[i]; sc[Ma + i] = gcB[i]; }
+            kA = sd; kB = sd + Ma; cA = sc; cB = sc + Ma;
+            __syncwarp();
         }
-        uint32_t ex = incl - v;
-        if (r == (int)catA0 || r == C + (int)catB0) ex += 1;   // anchors (locohd.rs:82-84)
-        cnt[r * 32 + lane] = ex;
-    }
+        const uint32_t catA0 = cA[0], catB0 = cB[0];
+        const double key0 = fmax(kA[0], kB[0]);   // key of the anchors (W(0) or 0)
+        kA += 1; kB += 1; cA += 1; cB += 1;       // events = members after the anchor
+        const uint32_t na = Ma - 1, nb = Mb - 1;
+        const uint32_t E = na + nb;
+        const uint32_t Q = (E + 31) / 32;
 
-    // ---- state: HELL2 keeps sqrt(weighted count), otherwise the weighted count itself
-    double normA = 0.0, normB = 0.0;
-    uint32_t totA = 0, totB = 0;
-    for (int r = 0; r < C; ++r) {
-        const uint32_t ka = cnt[r * 32 + lane], kb = cnt[(C + r) * 32 + lane];
-        const double w = P.cat_w[r];
-        normA += (double)ka * w; normB += (double)kb * w;
-        totA += ka; totB += kb;
-        if (HELL2) {
-            const double sw = P.cat_sw[r];
-            val[r * 32 + lane] = (ka < (uint32_t)kSqrtTableSize ? __ldg(P.sqrt_tbl + ka) : sqrt((double)ka)) * sw;
-            val[(C + r) * 32 + lane] = (kb < (uint32_t)kSqrtTableSize ? __ldg(P.sqrt_tbl + kb) : sqrt((double)kb)) * sw;
-        } else {
-            val[r * 32 + lane] = (double)ka * w;
-            val[(C + r) * 32 + lane] = (double)kb * w;
+        // ---- merge-path split: lane l owns merged events [l*Q, (l+1)*Q)
+        const uint32_t diag = min(E, (uint32_t)lane * Q);
+        uint32_t i = merge_path(kA, kB, na, nb, diag), j = diag - i;
+        uint32_t i1 = __shfl_down_sync(kFull, i, 1), j1 = __shfl_down_sync(kFull, j, 1);
+        if (lane == 31) { i1 = na; j1 = nb; }
+
+        // ---- category counts before my chunk: per-lane histogram, then exclusive prefix over the lanes
+        for (int r = 0; r < 2 * C; ++r) cnt[r * 32 + lane] = 0;
+        bool unknown = (catA0 >= (uint32_t)C) || (catB0 >= (uint32_t)C);
+        for (uint32_t x = i; x < i1; ++x) {
+            const uint32_t c = cA[x];
+            if (c < (uint32_t)C) cnt[c * 32 + lane] += 1; else unknown = true;
         }
-    }
-    auto inv_sqrt_norm = [&](double norm, uint32_t tot) -> double {
-        if (P.unit_w && tot < (uint32_t)kSqrtTableSize) return __ldg(P.rsqrt_tbl + tot);
-        return 1.0 / sqrt(norm);
-    };
-    double rA = HELL2 ? inv_sqrt_norm(normA, totA) : 0.0;
-    double rB = HELL2 ? inv_sqrt_norm(normB, totB) : 0.0;
+        for (uint32_t x = j; x < j1; ++x) {
+            const uint32_t c = cB[x];
+            if (c < (uint32_t)C) cnt[(C + c) * 32 + lane] += 1; else unknown = true;
+        }
+        if (__any_sync(kFull, unknown)) { raise(P.err, LOCOHD_ERR_UNKNOWN_CATEGORY); continue; }  // pmf.rs:38-42
+        for (int r = 0; r < 2 * C; ++r) {
+            const uint32_t v = cnt[r * 32 + lane];
+            uint32_t incl = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += u;
+            }
+            uint32_t ex = incl - v;
+            if (r == (int)catA0 || r == C + (int)catB0) ex += 1;   // anchors (locohd.rs:82-84)
+            cnt[r * 32 + lane] = ex;
+        }
 
-    auto stat_dist = [&]() -> double {
-        if (HELL2) {
-            // (1/2 * sum (sqrt(p_i) - sqrt(q_i))^2)^(1/2) in difference form (statistical_distances.rs:4-10, e = 2)
-            double acc = 0.0;
-            for (int r = 0; r < C; ++r) {
+        // ---- state: HELL2 keeps sqrt(weighted count), otherwise the weighted count itself
+        double normA = 0.0, normB = 0.0;
+        uint32_t totA = 0, totB = 0;
+        for (int r = 0; r < C; ++r) {
+            const uint32_t ka = cnt[r * 32 + lane], kb = cnt[(C + r) * 32 + lane];
+            const double w = P.cat_w[r];
+            normA += (double)ka * w; normB += (double)kb * w;
+            totA += ka; totB += kb;
+            if (HELL2) {
+                const double sw = P.cat_sw[r];
+                val[r * 32 + lane] = (ka < (uint32_t)kSqrtTableSize ? __ldg(P.sqrt_tbl + ka) : sqrt((double)ka)) * sw;
+                val[(C + r) * 32 + lane] = (kb < (uint32_t)kSqrtTableSize ? __ldg(P.sqrt_tbl + kb) : sqrt((double)kb)) * sw;
+            } else {
+                val[r * 32 + lane] = (double)ka * w;
+                val[(C + r) * 32 + lane] = (double)kb * w;
+            }
+        }
+        auto inv_sqrt_norm = [&](double norm, uint32_t tot) -> double {
+            if (P.unit_w && tot < (uint32_t)kSqrtTableSize) return __ldg(P.rsqrt_tbl + tot);
+            return 1.0 / sqrt(norm);
+        };
+        double rA = HELL2 ? inv_sqrt_norm(normA, totA) : 0.0;
+        double rB = HELL2 ? inv_sqrt_norm(normB, totB) : 0.0;
+
+        auto stat_dist = [&]() -> double {
+            if (HELL2) {
+                // (1/2 * sum (sqrt(p_i) - sqrt(q_i))^2)^(1/2) in difference form (statistical_distances.rs:4-10, e = 2);
                 // both products are rounded before the subtraction (no FMA contraction): identical compositions
                 // must give exactly 0, as they do upstream
-                const double u = __dmul_rn(val[r * 32 + lane], rA) - __dmul_rn(val[(C + r) * 32 + lane], rB);
-                acc = fma(u, u, acc);
+                double acc = 0.0;
+                for (int r = 0; r < C; ++r) {
+                    const double u = __dmul_rn(val[r * 32 + lane], rA) - __dmul_rn(val[(C + r) * 32 + lane], rB);
+                    acc = fma(u, u, acc);
+                }
+                return sqrt(0.5 * acc);
+            } else {
+                auto p1 = [&](int r) { return val[r * 32 + lane] / normA; };
+                auto p2 = [&](int r) { return val[(C + r) * 32 + lane] / normB; };
+                return sd_run(P.sd_kind, P.sd_p0, P.sd_p1, C, p1, p2);
+            }
+        };
+
+        const WfDev& wf = P.wfs[a.wf_idx ? a.wf_idx[pair] : 0];
+        auto weight = [&](double k) -> double { return key_is_w ? k : wf_cdf(wf, k); };
+        double kprev = key0;
+        if (i > 0) kprev = kA[i - 1];
+        if (j > 0) kprev = fmax(kprev, kB[j - 1]);
+        double wprev = weight(kprev);
+        double h = stat_dist();
+        double acc = 0.0;
+
+        // ---- walk my chunk
+        double ta = (i < i1) ? kA[i] : 0.0, tb = (j < j1) ? kB[j] : 0.0;
+        while (i < i1 || j < j1) {
+            const bool takeA = (i < i1) && (!(j < j1) || ta <= tb);
+            const double t = takeA ? ta : tb;
+            const uint32_t c = takeA ? cA[i] : cB[j];
+            const double w = weight(t);
+            acc = fma(w - wprev, h, acc);
+            wprev = w;
+            const int row = (takeA ? 0 : C) + (int)c;
+            const uint32_t k = cnt[row * 32 + lane] + 1;
+            cnt[row * 32 + lane] = k;
+            const double wc = P.cat_w[c];
+            if (HELL2) {
+                val[row * 32 + lane] = (k < (uint32_t)kSqrtTableSize ? __ldg(P.sqrt_tbl + k) : sqrt((double)k)) * P.cat_sw[c];
+            } else {
+                val[row * 32 + lane] = (double)k * wc;
+            }
+            if (takeA) {
+                normA += wc; totA += 1;
+                if (HELL2) rA = inv_sqrt_norm(normA, totA);
+                ++i;
+                if (i < i1) ta = kA[i];
+            } else {
+                normB += wc; totB += 1;
+                if (HELL2) rB = inv_sqrt_norm(normB, totB);
+                ++j;
+                if (j < j1) tb = kB[j];
+            }
+            h = stat_dist();
+        }
+        // ---- tail to infinity (locohd.rs:165-171, 204-221): owned by the last lane, whose state is final
+        if (lane == 31) acc = fma(wf.w_inf - wprev, h, acc);
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+        if (lane == 0) a.out[pair] = acc;
+    }
+}
+
+// Fast kernel: Hellinger-2, unit category weights, C <= CP (8 or 16).  Per-lane state lives in shared memory as
+// double2 pairs read with LDS.128 at compile-time offsets, the (A, B) counts of a category share one 32-bit word,
+// sqrt / rsqrt tables sit in shared memory, and with KEY_IS_W the environments already hold W(distance).
+template <int CP, bool KEY_IS_W>
+__global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreArgs a, KParams P, int warps_per_block,
+                                                                         int per_warp_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* s_sqrt = reinterpret_cast<double*>(smem_raw);
+    double* s_rsqrt = s_sqrt + kFastTable;
+    for (int k = threadIdx.x; k < kFastTable; k += blockDim.x) {
+        s_sqrt[k] = P.sqrt_tbl[k];
+        s_rsqrt[k] = P.rsqrt_tbl[k];
+    }
+    __syncthreads();
+    if (wib >= warps_per_block) return;
+    const int C = P.C;
+    unsigned char* mine = smem_raw + 2 * kFastTable * 8 + (size_t)wib * per_warp_bytes;
+    double2* val2 = reinterpret_cast<double2*>(mine);                        // [2][CP/2][32]
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(mine + 2 * CP * 32 * 8);     // [CP][32]: A count | B count << 16
+    unsigned char* stage = mine + fast_state_bytes(CP);
+    double* valf = reinterpret_cast<double*>(mine);
+    auto sqrt_of = [&](uint32_t k) -> double { return k < (uint32_t)kFastTable ? s_sqrt[k] : sqrt((double)k); };
+    auto rsqrt_of = [&](uint32_t k) -> double { return k < (uint32_t)kFastTable ? s_rsqrt[k] : 1.0 / sqrt((double)k); };
+
+    for (uint64_t pair = (uint64_t)blockIdx.x * warps_per_block + wib; pair < a.n_pairs;
+         pair += (uint64_t)gridDim.x * warps_per_block) {
+        __syncwarp();
+        const PairEnvs pe = resolve_pair(a, pair, P.err);
+        if (!pe.ok) continue;
+        const uint32_t Ma = pe.Ma, Mb = pe.Mb;
+        const double* gkA = a.a.key + pe.oa;
+        const double* gkB = a.b.key + pe.ob;
+        const uint8_t* gcA = a.a.cat + pe.oa;
+        const uint8_t* gcB = a.b.cat + pe.ob;
+        if (!KEY_IS_W && (gkA[0] != 0.0 || gkB[0] != 0.0)) { raise(P.err, LOCOHD_ERR_FIRST_NOT_ZERO); continue; }
+
+        const double* kA = gkA;
+        const double* kB = gkB;
+        const uint8_t* cA = gcA;
+        const uint8_t* cB = gcB;
+        if ((int)(Ma + Mb) <= a.stage_cap) {
+            double* sd = reinterpret_cast<double*>(stage);
+            uint8_t* sc = stage + (size_t)(Ma + Mb) * 8;
+            for (uint32_t i = lane; i < Ma; i += 32) { sd[i] = gkA[i]; sc[i] = gcA[i]; }
+            for (uint32_t i = lane; i < Mb; i += 32) { sd[Ma + i] = gkB[i]; sc[Ma + i] = gcB[i]; }
+            kA = sd; kB = sd + Ma; cA = sc; cB = sc + Ma;
+            __syncwarp();
+        }
+        const uint32_t catA0 = cA[0], catB0 = cB[0];
+        const double key0 = fmax(kA[0], kB[0]);
+        kA += 1; kB += 1; cA += 1; cB += 1;
+        const uint32_t na = Ma - 1, nb = Mb - 1;
+        const uint32_t E = na + nb;
+        const uint32_t Q = (E + 31) / 32;
+        const uint32_t diag = min(E, (uint32_t)lane * Q);
+        uint32_t i = merge_path(kA, kB, na, nb, diag), j = diag - i;
+        uint32_t i1 = __shfl_down_sync(kFull, i, 1), j1 = __shfl_down_sync(kFull, j, 1);
+        if (lane == 31) { i1 = na; j1 = nb; }
+
+        // ---- packed per-lane histogram of my chunk, exclusive prefix over the lanes, anchors added
+#pragma unroll
+        for (int r = 0; r < CP; ++r) cnt[r * 32 + lane] = 0;
+        bool unknown = (catA0 >= (uint32_t)C) || (catB0 >= (uint32_t)C);
+        for (uint32_t x = i; x < i1; ++x) {
+            const uint32_t c = cA[x];
+            if (c < (uint32_t)C) cnt[c * 32 + lane] += 1u; else unknown = true;
+        }
+        for (uint32_t x = j; x < j1; ++x) {
+            const uint32_t c = cB[x];
+            if (c < (uint32_t)C) cnt[c * 32 + lane] += 0x10000u; else unknown = true;
+        }
+        if (__any_sync(kFull, unknown)) { raise(P.err, LOCOHD_ERR_UNKNOWN_CATEGORY); continue; }  // pmf.rs:38-42
+        uint32_t totA = 0, totB = 0;
+#pragma unroll
+        for (int r = 0; r < CP; ++r) {
+            const uint32_t v = cnt[r * 32 + lane];
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += u;
+            }
+            uint32_t ex = incl - v;
+            if (r == (int)catA0) ex += 1u;          // anchors (locohd.rs:82-84)
+            if (r == (int)catB0) ex += 0x10000u;
+            cnt[r * 32 + lane] = ex;
+            const uint32_t ka = ex & 0xffffu, kb = ex >> 16;
+            totA += ka; totB += kb;
+            valf[((r >> 1) * 32 + lane) * 2 + (r & 1)] = sqrt_of(ka);
+            valf[((CP / 2 + (r >> 1)) * 32 + lane) * 2 + (r & 1)] = sqrt_of(kb);
+        }
+        double rA = rsqrt_of(totA), rB = rsqrt_of(totB);
+
+        auto stat_dist = [&]() -> double {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < CP / 2; ++q) {
+                const double2 va = val2[q * 32 + lane], vb = val2[(CP / 2 + q) * 32 + lane];
+                const double u0 = __dmul_rn(va.x, rA) - __dmul_rn(vb.x, rB);
+                const double u1 = __dmul_rn(va.y, rA) - __dmul_rn(vb.y, rB);
+                acc = fma(u0, u0, acc);
+                acc = fma(u1, u1, acc);
             }
             return sqrt(0.5 * acc);
-        } else {
-            auto p1 = [&](int r) { return val[r * 32 + lane] / normA; };
-            auto p2 = [&](int r) { return val[(C + r) * 32 + lane] / normB; };
-            return sd_run(P.sd_kind, P.sd_p0, P.sd_p1, C, p1, p2);
-        }
-    };
+        };
 
-    const WfDev& wf = P.wfs[a.wf_idx ? a.wf_idx[pair] : 0];
-    double tprev = 0.0;
-    if (i > 0) tprev = dA[i - 1];
-    if (j > 0) tprev = fmax(tprev, dB[j - 1]);
-    double wprev = wf_cdf(wf, tprev);
-    double h = stat_dist();
-    double acc = 0.0;
+        const WfDev& wf = P.wfs[(!KEY_IS_W && a.wf_idx) ? a.wf_idx[pair] : 0];
+        auto weight = [&](double k) -> double { return KEY_IS_W ? k : wf_cdf(wf, k); };
+        double kprev = key0;
+        if (i > 0) kprev = kA[i - 1];
+        if (j > 0) kprev = fmax(kprev, kB[j - 1]);
+        double wprev = weight(kprev);
+        double h = stat_dist();
+        double acc = 0.0;
 
-    // ---- walk my chunk
-    double ta = (i < i1) ? dA[i] : 0.0, tb = (j < j1) ? dB[j] : 0.0;
-    while (i < i1 || j < j1) {
-        const bool takeA = (i < i1) && (!(j < j1) || ta <= tb);
-        const double t = takeA ? ta : tb;
-        const uint32_t c = takeA ? cA[i] : cB[j];
-        const double w = wf_cdf(wf, t);
-        acc = fma(w - wprev, h, acc);
-        wprev = w;
-        const int row = (takeA ? 0 : C) + (int)c;
-        const uint32_t k = cnt[row * 32 + lane] + 1;
-        cnt[row * 32 + lane] = k;
-        const double wc = P.cat_w[c];
-        if (HELL2) {
-            val[row * 32 + lane] = (k < (uint32_t)kSqrtTableSize ? __ldg(P.sqrt_tbl + k) : sqrt((double)k)) * P.cat_sw[c];
-        } else {
-            val[row * 32 + lane] = (double)k * wc;
+        double ta = (i < i1) ? kA[i] : 0.0, tb = (j < j1) ? kB[j] : 0.0;
+        while (i < i1 || j < j1) {
+            const bool takeA = (i < i1) && (!(j < j1) || ta <= tb);
+            const double w = weight(takeA ? ta : tb);
+            const uint32_t c = takeA ? cA[i] : cB[j];
+            acc = fma(w - wprev, h, acc);
+            wprev = w;
+            const uint32_t word = cnt[c * 32 + lane] + (takeA ? 1u : 0x10000u);
+            cnt[c * 32 + lane] = word;
+            const uint32_t k = takeA ? (word & 0xffffu) : (word >> 16);
+            valf[(((takeA ? 0 : CP / 2) + (c >> 1)) * 32 + lane) * 2 + (c & 1)] = sqrt_of(k);
+            if (takeA) {
+                ++totA; rA = rsqrt_of(totA);
+                ++i;
+                if (i < i1) ta = kA[i];
+            } else {
+                ++totB; rB = rsqrt_of(totB);
+                ++j;
+                if (j < j1) tb = kB[j];
+            }
+            h = stat_dist();
         }
-        if (takeA) {
-            normA += wc; totA += 1;
-            if (HELL2) rA = inv_sqrt_norm(normA, totA);
-            ++i;
-            if (i < i1) ta = dA[i];
-        } else {
-            normB += wc; totB += 1;
-            if (HELL2) rB = inv_sqrt_norm(normB, totB);
-            ++j;
-            if (j < j1) tb = dB[j];
-        }
-        h = stat_dist();
+        if (lane == 31) acc = fma(wf.w_inf - wprev, h, acc);
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+        if (lane == 0) a.out[pair] = acc;
     }
-    // ---- tail to infinity (locohd.rs:165-171, 204-221): owned by the last lane, whose state is final
-    if (lane == 31) acc = fma(wf_cdf(wf, INFINITY) - wprev, h, acc);
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
-    if (lane == 0) a.out[pair] = acc;
 }
 
 __global__ void job_means_kernel(const double* __restrict__ scores, const uint64_t* __restrict__ job_pair_off,
@@ -1009,58 +1123,51 @@ int launch_build_cells(const StructsView& s, double threshold, cudaStream_t st) 
     return 1;
 }
 
-int launch_env_count(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* anchor_struct,
-                     const uint32_t* anchor_prim, double threshold, uint32_t* count, cudaStream_t st) {
-    if (!n_env) return 0;
-    env_count_kernel<<<blocks_for(n_env, kEnvWarps), kEnvWarps * 32, 0, st>>>(s, p, n_env, anchor_struct, anchor_prim,
-                                                                              threshold, count);
+int launch_env_count_sample(const StructsView& s, const KParams& p, uint64_t n_sample, uint64_t stride,
+                            const uint32_t* anchor_struct, const uint32_t* anchor_prim, double threshold,
+                            uint32_t* count, cudaStream_t st) {
+    if (!n_sample) return 0;
+    env_count_sample_kernel<<<blocks_for(n_sample, kEnvWarps), kEnvWarps * 32, 0, st>>>(s, p, n_sample, stride,
+                                                                                        anchor_struct, anchor_prim,
+                                                                                        threshold, count);
     return 1;
-}
-
-uint64_t scan_scratch_entries(uint64_t n) { return (n + kScanTile - 1) / kScanTile + 1; }
-
-int launch_scan_counts(const uint32_t* count, uint64_t n, uint64_t* off, uint64_t* block_sums, ScanResult* res,
-                       cudaStream_t st) {
-    cudaMemsetAsync(res, 0, sizeof(ScanResult), st);
-    if (!n) { cudaMemsetAsync(off, 0, sizeof(uint64_t), st); return 0; }
-    const unsigned nb = blocks_for(n, kScanTile);
-    scan_tile_sums_kernel<<<nb, kScanThreads, 0, st>>>(count, n, block_sums, res);
-    scan_block_sums_kernel<<<1, kScanThreads, 0, st>>>(block_sums, nb, res);
-    scan_apply_kernel<<<nb, kScanThreads, 0, st>>>(count, n, block_sums, off);
-    return 3;
 }
 
 template <int CAP>
 static int launch_env_fill_class(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
-                                 const uint32_t* anchor_prim, double threshold, const EnvOut& out, uint32_t min_m,
-                                 cudaStream_t st) {
+                                 const uint32_t* anchor_prim, double threshold, const EnvOut& out, cudaStream_t st) {
     const int smem = WarpSortLayout<CAP>::kBytes * kEnvWarps;
     cudaFuncSetAttribute(env_fill_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     env_fill_kernel<CAP><<<blocks_for(out.n_env, kEnvWarps), kEnvWarps * 32, smem, st>>>(s, p, anchor_struct,
-                                                                                        anchor_prim, threshold, out,
-                                                                                        min_m);
+                                                                                        anchor_prim, threshold, out);
     return 1;
 }
 
 int launch_env_fill(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
-                    const uint32_t* anchor_prim, double threshold, const EnvOut& out, const ScanResult& cls,
-                    cudaStream_t st) {
+                    const uint32_t* anchor_prim, double threshold, const EnvOut& out, int cap_class, cudaStream_t st) {
+    cudaMemsetAsync(out.stats, 0, sizeof(FillStats), st);
     if (!out.n_env) return 0;
-    int launches = 0;
-    if (cls.n_small) launches += launch_env_fill_class<256>(s, p, anchor_struct, anchor_prim, threshold, out, 0, st);
-    if (cls.n_medium) launches += launch_env_fill_class<512>(s, p, anchor_struct, anchor_prim, threshold, out, 256, st);
-    if (cls.n_large) launches += launch_env_fill_class<2048>(s, p, anchor_struct, anchor_prim, threshold, out, 512, st);
-    if (cls.n_huge) {
-        env_fill_unsorted_kernel<<<blocks_for(out.n_env, kEnvWarps), kEnvWarps * 32, 0, st>>>(
-            s, p, anchor_struct, anchor_prim, threshold, out, 2048);
-        bitonic_sort_big_kernel<<<(unsigned)out.n_env, kBigThreads, 0, st>>>(out, 2048);
-        launches += 2;
+    switch (cap_class) {
+        case 256: return launch_env_fill_class<256>(s, p, anchor_struct, anchor_prim, threshold, out, st);
+        case 512: return launch_env_fill_class<512>(s, p, anchor_struct, anchor_prim, threshold, out, st);
+        case 1024: return launch_env_fill_class<1024>(s, p, anchor_struct, anchor_prim, threshold, out, st);
+        default: return launch_env_fill_class<2048>(s, p, anchor_struct, anchor_prim, threshold, out, st);
     }
-    return launches;
+}
+
+int launch_env_fill_big(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
+                        const uint32_t* anchor_prim, double threshold, const EnvOut& out, int cap_class,
+                        cudaStream_t st) {
+    if (!out.n_env) return 0;
+    env_fill_unsorted_kernel<<<blocks_for(out.n_env, kEnvWarps), kEnvWarps * 32, 0, st>>>(
+        s, p, anchor_struct, anchor_prim, threshold, out, (uint32_t)cap_class);
+    bitonic_sort_big_kernel<<<(unsigned)out.n_env, kBigThreads, 0, st>>>(out, p, (uint32_t)cap_class, 0);
+    return 2;
 }
 
 int launch_fill_u64_iota_rows(uint64_t* off, uint32_t* count, uint64_t n_rows, uint64_t row_len, cudaStream_t st) {
-    iota_rows_kernel<<<blocks_for(n_rows + 1, 256), 256, 0, st>>>(off, count, n_rows, row_len);
+    if (!n_rows) return 0;
+    iota_rows_kernel<<<blocks_for(n_rows, 256), 256, 0, st>>>(off, count, n_rows, row_len);
     return 1;
 }
 
@@ -1079,39 +1186,72 @@ int launch_rows_fill(const double* dmx, const uint8_t* cat, uint64_t n_rows, uin
     if (!n_rows || !row_len) return 0;
     if (row_len <= 256) return launch_rows_class<256>(dmx, cat, n_rows, row_len, xyz, p, out, st);
     if (row_len <= 512) return launch_rows_class<512>(dmx, cat, n_rows, row_len, xyz, p, out, st);
+    if (row_len <= 1024) return launch_rows_class<1024>(dmx, cat, n_rows, row_len, xyz, p, out, st);
     if (row_len <= 2048) return launch_rows_class<2048>(dmx, cat, n_rows, row_len, xyz, p, out, st);
-    dim3 grid((unsigned)((row_len + 255) / 256), (unsigned)n_rows);
+    dim3 grid((unsigned)((row_len + 255) / 256), (unsigned)(n_rows > 32768 ? 32768 : n_rows));
     if (grid.x > 64) grid.x = 64;
     rows_copy_kernel<<<grid, 256, 0, st>>>(dmx, cat, n_rows, row_len, xyz, p, out);
-    bitonic_sort_big_kernel<<<(unsigned)n_rows, kBigThreads, 0, st>>>(out, 0);
+    bitonic_sort_big_kernel<<<(unsigned)n_rows, kBigThreads, 0, st>>>(out, p, 0, 1);
     return 2;
 }
 
-int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_members_a, unsigned max_members_b,
-                 cudaStream_t st) {
+template <class K>
+static unsigned persistent_grid(K kernel, int threads, int smem, uint64_t n_pairs, int warps) {
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+    if (occ < 1) occ = 1;
+    const uint64_t need = (n_pairs + warps - 1) / warps;
+    const uint64_t cap = (uint64_t)sms * occ * 8;
+    return (unsigned)(need < cap ? need : cap);
+}
+
+template <class K>
+static int launch_score_kernel(K kernel, const ScoreArgs& a, const KParams& p, int warps, int per_warp, int smem,
+                               cudaStream_t st) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const unsigned grid = persistent_grid(kernel, warps * 32, smem, a.n_pairs, warps);
+    kernel<<<grid, warps * 32, smem, st>>>(a, p, warps, per_warp);
+    return 1;
+}
+
+int launch_score(const ScoreArgs& args, const KParams& p, unsigned stage_members, unsigned unused, cudaStream_t st) {
+    (void)unused;
     if (!args.n_pairs) return 0;
     ScoreArgs a = args;
+    const int budget = 100 * 1024;  // per CTA: two CTAs per SM
+    const bool key_is_w = args.a.key_is_w != 0;
+    const bool fast = p.hell2 && p.unit_w && p.C <= 16;
+    int cap = (int)(stage_members > 4096u ? 4096u : stage_members);
+    if (fast) {
+        const int CP = p.C <= 8 ? 8 : 16;
+        const int tables = 2 * kFastTable * 8;
+        int per_warp = fast_state_bytes(CP) + score_stage_bytes(cap);
+        if (tables + per_warp > 200 * 1024) { cap = 0; per_warp = fast_state_bytes(CP) + score_stage_bytes(0); }
+        int warps = (budget - tables) / per_warp;
+        if (warps > kScoreMaxWarps) warps = kScoreMaxWarps;
+        if (warps < 1) warps = 1;
+        a.stage_cap = cap;
+        const int smem = tables + per_warp * warps;
+        if (CP == 8) {
+            return key_is_w ? launch_score_kernel(score_fast_kernel<8, true>, a, p, warps, per_warp, smem, st)
+                            : launch_score_kernel(score_fast_kernel<8, false>, a, p, warps, per_warp, smem, st);
+        }
+        return key_is_w ? launch_score_kernel(score_fast_kernel<16, true>, a, p, warps, per_warp, smem, st)
+                        : launch_score_kernel(score_fast_kernel<16, false>, a, p, warps, per_warp, smem, st);
+    }
     const int state = score_state_bytes(p.C);
-    const int budget = 200 * 1024;
-    // stage both environments when a warp's share of shared memory allows it
-    uint64_t want = (uint64_t)max_members_a + max_members_b;
-    int cap = (int)(want > 4096 ? 4096 : want);
     int per_warp = state + score_stage_bytes(cap);
-    if (per_warp > budget) { cap = 0; per_warp = state + score_stage_bytes(0); }
+    if (per_warp > 200 * 1024) { cap = 0; per_warp = state + score_stage_bytes(0); }
+    if (per_warp > 220 * 1024) return -1;
     int warps = budget / per_warp;
     if (warps > kScoreMaxWarps) warps = kScoreMaxWarps;
-    if (warps < 1) return -1;
+    if (warps < 1) warps = 1;
     a.stage_cap = cap;
     const int smem = per_warp * warps;
-    const unsigned grid = blocks_for(args.n_pairs, (unsigned)warps);
-    if (p.hell2) {
-        cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        score_kernel<true><<<grid, warps * 32, smem, st>>>(a, p, warps, per_warp);
-    } else {
-        cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        score_kernel<false><<<grid, warps * 32, smem, st>>>(a, p, warps, per_warp);
-    }
-    return 1;
+    return p.hell2 ? launch_score_kernel(score_kernel<true>, a, p, warps, per_warp, smem, st)
+                   : launch_score_kernel(score_kernel<false>, a, p, warps, per_warp, smem, st);
 }
 
 int launch_job_means(const double* scores, const uint64_t* job_pair_off, uint64_t n_jobs, double* means,

@@ -62,28 +62,32 @@ struct StructsView {
 
 struct EnvView {
     uint64_t n_env;
-    const uint64_t* off;   // [n_env + 1]
-    const double* dist;    // sorted ascending per environment
+    const uint64_t* off;    // [n_env] first member of every environment (any order, no overlap)
+    const uint32_t* count;  // [n_env] members per environment
+    const double* key;      // ascending per environment: W(distance) when key_is_w, else the distance
     const uint8_t* cat;
-    const uint32_t* idx;   // primitive index (original order) or nullptr
+    int key_is_w;
+};
+
+struct FillStats {  // written by the fill kernels, read back by the host
+    unsigned long long cursor;  // members allocated so far (== total when the launch is over)
+    unsigned int max_count;
+    unsigned int n_big;         // environments larger than the shared-memory class of the launch
+    unsigned int overflow;      // some environment did not fit below `capacity`
+    unsigned int pad;
 };
 
 struct EnvOut {
     uint64_t n_env;
-    const uint64_t* off;
-    const uint32_t* count;
-    double* dist;
+    uint64_t* off;
+    uint32_t* count;
+    double* key;
     uint8_t* cat;
-    uint32_t* idx;  // may be nullptr
-};
-
-struct ScanResult {  // written by the scan kernels, read back by the host
-    unsigned long long total;
-    unsigned int max_count;
-    unsigned int n_small;   // count <= 256
-    unsigned int n_medium;  // 256 < count <= 512
-    unsigned int n_large;   // 512 < count <= 2048
-    unsigned int n_huge;    // > 2048
+    double* dist;     // plain distances (debug/parity) or nullptr
+    uint32_t* idx;    // primitive indices (debug/parity) or nullptr
+    uint64_t capacity;
+    FillStats* stats;
+    int key_is_w;
 };
 
 struct ScoreArgs {
@@ -103,14 +107,17 @@ struct ScoreArgs {
 int launch_convert_categories(const uint16_t* in, uint8_t* out, uint64_t n, int C, cudaStream_t st);
 int launch_validate_xyz(const double* xyz, uint64_t n3, int* err, cudaStream_t st);
 int launch_build_cells(const StructsView& s, double threshold, cudaStream_t st);
-int launch_env_count(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* anchor_struct,
-                     const uint32_t* anchor_prim, double threshold, uint32_t* count, cudaStream_t st);
-int launch_scan_counts(const uint32_t* count, uint64_t n, uint64_t* off, uint64_t* block_sums, ScanResult* res,
-                       cudaStream_t st);
-uint64_t scan_scratch_entries(uint64_t n);
+// sampled size probe: environment sizes of anchors 0, stride, 2*stride, ... (n_sample of them) -> count[n_sample]
+int launch_env_count_sample(const StructsView& s, const KParams& p, uint64_t n_sample, uint64_t stride,
+                            const uint32_t* anchor_struct, const uint32_t* anchor_prim, double threshold,
+                            uint32_t* count, cudaStream_t st);
+// gather + sort + store with cursor allocation; cap_class in {256, 512, 1024, 2048}
 int launch_env_fill(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
-                    const uint32_t* anchor_prim, double threshold, const EnvOut& out, const ScanResult& classes,
-                    cudaStream_t st);
+                    const uint32_t* anchor_prim, double threshold, const EnvOut& out, int cap_class, cudaStream_t st);
+// second stage for environments larger than cap_class (after the host saw stats.n_big > 0)
+int launch_env_fill_big(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
+                        const uint32_t* anchor_prim, double threshold, const EnvOut& out, int cap_class,
+                        cudaStream_t st);
 int launch_rows_fill(const double* dmx, const uint8_t* cat, uint64_t n_rows, uint64_t row_len, const double* xyz,
                      const KParams& p, const EnvOut& out, cudaStream_t st);
 int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_members_a, unsigned max_members_b,

@@ -20,6 +20,7 @@ struct WfDev {
     int int_b;         // kumaraswamy: exponent b likewise
     double inv_range;  // uniform / kumaraswamy: 1 / (x_max - x_min)
     double inv_norm;   // hyper_exp: 1 / sum(a_i)
+    double w_inf;      // CDF(+inf), evaluated on the host (1 except for degenerate dagum parameters)
     double p[LOCOHD_MAX_WF_PARAMS];
 };
 

