@@ -98,12 +98,13 @@ typedef struct locohd_params {
 
 typedef enum locohd_prof_group {
     LOCOHD_PROF_CELLS = 0,   /* K0 build_cells_kernel */
-    LOCOHD_PROF_COUNT = 1,   /* K1 env_count_kernel */
+    LOCOHD_PROF_COUNT = 1,   /* K1a env_tile_kernel<false>: upper-bound environment sizes */
     LOCOHD_PROF_SCAN = 2,    /* scan of the environment sizes */
-    LOCOHD_PROF_FILL = 3,    /* K1' env_fill_kernel (+ big-environment sort) */
-    LOCOHD_PROF_SCORE = 4,   /* K2 score_kernel */
-    LOCOHD_PROF_OTHER = 5,   /* conversions, validation, means, row sorting, ... */
-    LOCOHD_PROF_GROUPS = 6
+    LOCOHD_PROF_FILL = 3,    /* K1b env_tile_kernel<true>: exact gather into the store */
+    LOCOHD_PROF_SCORE = 4,   /* K2 score_fast_kernel / score_kernel */
+    LOCOHD_PROF_OTHER = 5,   /* anchor ordering, conversions, validation, means, row copies, ... */
+    LOCOHD_PROF_SORT = 6,    /* K1c env_sort_kernel: per-environment sort, CDF, key packing */
+    LOCOHD_PROF_GROUPS = 7
 } locohd_prof_group;
 
 typedef struct locohd_ctx locohd_ctx;            /* one GPU + one stream + one LoCoHD parameter set */

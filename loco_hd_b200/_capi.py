@@ -190,7 +190,7 @@ class Context:
     def synchronize(self):
         self._check(self.lib.locohd_ctx_synchronize(self.h))
 
-    PROF_GROUPS = ("cells", "count", "scan", "fill", "score", "other")
+    PROF_GROUPS = ("cells", "count", "scan", "fill", "score", "other", "sort")
 
     def profile_enable(self, on: bool = True):
         self._check(self.lib.locohd_ctx_profile_enable(self.h, int(on)))

@@ -38,7 +38,7 @@ struct locohd_ctx {
     double* d_sqrt_tbl = nullptr;
     double* d_rsqrt_tbl = nullptr;
     int* d_err = nullptr;
-    FillStats* d_fill = nullptr;
+    ScanStats* d_scan = nullptr;   // two slots: [0] anchor order, [1] environment sizes
     // per-kernel-group event timing
     bool prof_on = false;
     struct ProfRec { int group; cudaEvent_t a, b; };
@@ -76,30 +76,32 @@ struct locohd_structs {
     PrimRec* d_pd = nullptr;
     uint32_t* d_sorted_pos = nullptr;
     uint32_t* d_cell_start = nullptr;
+    uint32_t* d_cell_fill = nullptr;
     bool cells_valid = false;
     double cell_threshold = 0.0;
     StructsView view() const {
         StructsView v;
         v.n_structs = n_structs; v.prim_off = d_prim_off; v.xyz = d_xyz; v.cat = d_cat; v.tag = d_tag;
         v.meta = d_meta; v.pf = d_pf; v.pd = d_pd; v.sorted_pos = d_sorted_pos; v.cell_start = d_cell_start;
+        v.cell_fill = d_cell_fill;
         return v;
     }
 };
 
 struct locohd_envset {
     locohd_ctx* ctx = nullptr;
-    uint64_t n_env = 0, total = 0;
+    uint64_t n_env = 0, total = 0;   // total = members actually stored (sum of the sizes)
+    uint64_t capacity = 0;           // entries of the store (even-rounded upper bounds)
     unsigned max_count = 0;
     bool key_is_w = false;
-    uint64_t* d_off = nullptr;
+    uint64_t* d_off = nullptr;       // [n_env + 1]
     uint32_t* d_count = nullptr;
-    double* d_key = nullptr;
-    uint8_t* d_cat = nullptr;
-    double* d_dist = nullptr;   // plain distances, kept only for locohd_envset_dump when the keys hold W
-    uint32_t* d_idx = nullptr;
+    uint64_t* d_key = nullptr;       // packed keys (see EnvView)
+    double* d_dist = nullptr;        // plain distances, kept only for locohd_envset_dump
+    uint32_t* d_idx = nullptr;       // primitive indices, kept only for locohd_envset_dump
     EnvView view() const {
         EnvView v;
-        v.n_env = n_env; v.off = d_off; v.count = d_count; v.key = d_key; v.cat = d_cat; v.key_is_w = key_is_w ? 1 : 0;
+        v.n_env = n_env; v.off = d_off; v.count = d_count; v.key = d_key; v.key_is_w = key_is_w ? 1 : 0;
         return v;
     }
 };
@@ -248,6 +250,8 @@ int make_wf(locohd_ctx* ctx, const locohd_weight_function& in, WfDev* out) {
     w.kind = in.kind;
     w.n = in.n_params;
     w.int_a = w.int_b = -1;
+    w.monotone = 0;
+    w.pad = 0;
     w.inv_range = w.inv_norm = 0.0;
     if (in.n_params < 0 || in.n_params > LOCOHD_MAX_WF_PARAMS)
         return fail(ctx, LOCOHD_ERR_BAD_PARAM, "weight function with %d parameters (max %d)", in.n_params,
@@ -279,6 +283,7 @@ int make_wf(locohd_ctx* ctx, const locohd_weight_function& in, WfDev* out) {
             if (p[1] <= 0.0) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"uniform\" the second parameter must be positive!");
             if (!(p[0] < p[1])) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "For function \"uniform\" the first parameter must be smaller than the second!");
             w.inv_range = 1.0 / (p[1] - p[0]);
+            w.monotone = 1;
             break;
         case LOCOHD_WF_KUMARASWAMY:
             if (in.n_params != 4)
@@ -290,6 +295,7 @@ int make_wf(locohd_ctx* ctx, const locohd_weight_function& in, WfDev* out) {
             w.inv_range = 1.0 / (p[1] - p[0]);
             w.int_a = small_int_exponent(p[2]);
             w.int_b = small_int_exponent(p[3]);
+            w.monotone = (w.int_a >= 0 && w.int_b >= 0) ? 1 : 0;
             break;
         default:
             return fail(ctx, LOCOHD_ERR_BAD_PARAM, "No function implemented with kind %d!", in.kind);
@@ -321,8 +327,8 @@ int ensure_cells(locohd_structs* s, double threshold) {
     return 0;
 }
 
-int read_fill_stats(locohd_ctx* ctx, FillStats* host) {
-    CU(ctx, cudaMemcpyAsync(host, ctx->d_fill, sizeof(FillStats), cudaMemcpyDeviceToHost, ctx->stream));
+int read_scan_stats(locohd_ctx* ctx, int slot, ScanStats* host) {
+    CU(ctx, cudaMemcpyAsync(host, ctx->d_scan + slot, sizeof(ScanStats), cudaMemcpyDeviceToHost, ctx->stream));
     return sync_and_check(ctx);
 }
 
@@ -330,103 +336,86 @@ void destroy_envset(locohd_envset* e) {
     if (!e) return;
     locohd_ctx* ctx = e->ctx;
     DeviceGuard g(ctx->device);
-    dev_free(ctx, e->d_off); dev_free(ctx, e->d_count); dev_free(ctx, e->d_key); dev_free(ctx, e->d_cat);
-    dev_free(ctx, e->d_dist); dev_free(ctx, e->d_idx);
+    dev_free(ctx, e->d_off); dev_free(ctx, e->d_count); dev_free(ctx, e->d_key); dev_free(ctx, e->d_dist);
+    dev_free(ctx, e->d_idx);
     delete e;
 }
 
-void free_envset_storage(locohd_ctx* ctx, locohd_envset* e) {
-    dev_free(ctx, e->d_key); dev_free(ctx, e->d_cat); dev_free(ctx, e->d_dist); dev_free(ctx, e->d_idx);
-}
-
-int alloc_envset_storage(locohd_ctx* ctx, locohd_envset* e, uint64_t capacity, bool debug) {
-    TRY_ST(dev_alloc(ctx, &e->d_key, capacity));
-    TRY_ST(dev_alloc(ctx, &e->d_cat, capacity));
-    if (debug) {
-        TRY_ST(dev_alloc(ctx, &e->d_idx, capacity));
-        if (e->key_is_w) TRY_ST(dev_alloc(ctx, &e->d_dist, capacity));
-    }
-    return 0;
-}
-
-EnvOut env_out(locohd_ctx* ctx, const locohd_envset* e, uint64_t capacity) {
-    EnvOut o;
-    o.n_env = e->n_env; o.off = e->d_off; o.count = e->d_count; o.key = e->d_key; o.cat = e->d_cat;
-    o.dist = e->d_dist; o.idx = e->d_idx; o.capacity = capacity; o.stats = ctx->d_fill; o.key_is_w = e->key_is_w ? 1 : 0;
-    return o;
-}
-
-// kd-tree build + env_from_idx for a list of anchors (locohd.rs:504-542): cell lists, a sampled size probe to
-// choose the shared-memory class and the store capacity, then one gather+sort+store launch whose store is
-// allocated by a device cursor; the rare overflow is repeated with the exact capacity.
+// kd-tree build + env_from_idx for a list of anchors (locohd.rs:504-542):
+//   K0 cells (cached per threshold) -> anchors into cell order -> K1a upper-bound sizes -> scan -> store allocation
+//   -> K1b exact gather into the store -> K1c per-environment sort + CDF + key packing.
+// One host synchronisation (the store size) per call.
 int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const uint32_t* d_anchor_struct,
                  const uint32_t* d_anchor_prim, double threshold, int keep_indices, locohd_envset** out) {
     if (!(threshold > 0.0))  // NaN included: nothing passes `d2 < r*r`, the reference then panics on dists[0]
         return fail(ctx, LOCOHD_ERR_EMPTY_ENV, "threshold_distance must be positive (got %g): every environment would be empty", threshold);
+    if (n_anchors > 0xFFFFFFF0ull) return fail(ctx, LOCOHD_ERR_UNSUPPORTED, "more than 2^32 anchors in one call");
     TRY_ST(ensure_cells(s, threshold));
     locohd_envset* e = new locohd_envset();
     e->ctx = ctx;
     e->n_env = n_anchors;
     e->key_is_w = ctx->kp.n_wf == 1;  // a single weight function: the store holds W(distance) directly
-    auto bail = [&](int st) { destroy_envset(e); return st; };
+    uint32_t *d_order = nullptr, *d_slot_cnt = nullptr, *d_ub = nullptr;
+    uint64_t *d_slot_off = nullptr, *d_scratch = nullptr;
+    uint8_t* d_cat = nullptr;
+    auto release = [&]() {
+        dev_free(ctx, d_order); dev_free(ctx, d_slot_cnt); dev_free(ctx, d_ub); dev_free(ctx, d_slot_off);
+        dev_free(ctx, d_scratch); dev_free(ctx, d_cat);
+    };
+    auto bail = [&](int st) { release(); destroy_envset(e); return st; };
     int st;
-    if ((st = dev_alloc(ctx, &e->d_count, n_anchors))) return bail(st);
-    if ((st = dev_alloc(ctx, &e->d_off, n_anchors))) return bail(st);
+    if ((st = dev_alloc(ctx, &e->d_count, n_anchors)) || (st = dev_alloc(ctx, &e->d_off, n_anchors + 1))) return bail(st);
     const StructsView sv = s->view();
-    if (n_anchors == 0) { *out = e; return 0; }
-
-    // ---- size probe on a strided sample
-    const uint64_t want = std::max<uint64_t>(2048, n_anchors / 64);
-    const uint64_t stride = std::max<uint64_t>(1, n_anchors / want);
-    const uint64_t n_sample = (n_anchors + stride - 1) / stride;
-    std::vector<uint32_t> sample(n_sample);
+    if (n_anchors == 0) {
+        cudaMemsetAsync(e->d_off, 0, sizeof(uint64_t), ctx->stream);
+        *out = e;
+        return 0;
+    }
+    const uint64_t n_prims = s->n_prims;
+    const uint64_t scratch_n = std::max(scan_scratch_entries(n_prims + 1), scan_scratch_entries(n_anchors));
+    if ((st = dev_alloc(ctx, &d_order, n_anchors)) || (st = dev_alloc(ctx, &d_slot_cnt, n_prims + 1)) ||
+        (st = dev_alloc(ctx, &d_slot_off, n_prims + 2)) || (st = dev_alloc(ctx, &d_scratch, scratch_n)) ||
+        (st = dev_alloc(ctx, &d_ub, n_anchors)))
+        return bail(st);
     {
-        uint32_t* d_sample = nullptr;
-        if ((st = dev_alloc(ctx, &d_sample, n_sample))) return bail(st);
-        { ProfScope ps(ctx, LOCOHD_PROF_COUNT);
-          ctx->launches += launch_env_count_sample(sv, ctx->kp, n_sample, stride, d_anchor_struct, d_anchor_prim,
-                                                   threshold, d_sample, ctx->stream); }
-        cudaError_t ce = cudaMemcpyAsync(sample.data(), d_sample, n_sample * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
-        st = ce == cudaSuccess ? sync_and_check(ctx) : fail(ctx, LOCOHD_ERR_CUDA, "copy failed: %s", cudaGetErrorString(ce));
-        dev_free(ctx, d_sample);
-        if (st) return bail(st);
+        ProfScope ps(ctx, LOCOHD_PROF_OTHER);
+        ctx->launches += launch_anchor_order(sv, ctx->kp, n_anchors, d_anchor_struct, d_anchor_prim, n_prims, d_slot_cnt,
+                                             d_slot_off, d_scratch, ctx->d_scan, d_order, ctx->stream);
     }
-    uint64_t sum = 0;
-    uint32_t smax = 0;
-    for (uint32_t c : sample) { sum += c; smax = std::max(smax, c); }
-    const double mean = (double)sum / (double)n_sample;
-    uint64_t capacity = (uint64_t)(mean * 1.10 * (double)n_anchors) + 64ull * smax + 4096;
-    if (n_sample == n_anchors) capacity = sum;  // the probe saw everything
-    int cap_class = 2048;
-    for (int c : {256, 512, 1024, 2048}) if ((double)smax * 1.2 <= (double)c) { cap_class = c; break; }
-
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        if ((st = alloc_envset_storage(ctx, e, capacity, keep_indices != 0))) return bail(st);
-        { ProfScope ps(ctx, LOCOHD_PROF_FILL);
-          ctx->launches += launch_env_fill(sv, ctx->kp, d_anchor_struct, d_anchor_prim, threshold,
-                                           env_out(ctx, e, capacity), cap_class, ctx->stream); }
-        FillStats fs{};
-        if ((st = read_fill_stats(ctx, &fs))) return bail(st);
-        e->total = fs.cursor;
-        e->max_count = fs.max_count;
-        if (!fs.overflow) {
-            if (fs.n_big) {
-                ProfScope ps(ctx, LOCOHD_PROF_FILL);
-                ctx->launches += launch_env_fill_big(sv, ctx->kp, d_anchor_struct, d_anchor_prim, threshold,
-                                                     env_out(ctx, e, capacity), cap_class, ctx->stream);
-            }
-            cudaError_t ce = cudaGetLastError();
-            if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
-            *out = e;
-            return 0;
-        }
-        // the estimate was too small: the cursor now holds the exact total
-        free_envset_storage(ctx, e);
-        capacity = fs.cursor;
-        if (fs.max_count > (unsigned)cap_class && cap_class < 2048)
-            for (int c : {512, 1024, 2048}) if (c > cap_class && (fs.max_count <= (unsigned)c || c == 2048)) { cap_class = c; break; }
+    {
+        ProfScope ps(ctx, LOCOHD_PROF_COUNT);
+        ctx->launches += launch_env_count(sv, ctx->kp, n_anchors, d_order, d_anchor_struct, d_anchor_prim, threshold,
+                                          d_ub, ctx->stream);
     }
-    return bail(fail(ctx, LOCOHD_ERR_CUDA, "environment store allocation failed twice"));
+    {
+        ProfScope ps(ctx, LOCOHD_PROF_SCAN);
+        ctx->launches += launch_scan(d_ub, n_anchors, 1, e->d_off, d_scratch, ctx->d_scan + 1, ctx->stream);
+    }
+    ScanStats ss{};
+    if ((st = read_scan_stats(ctx, 1, &ss))) return bail(st);
+    e->capacity = ss.total + 2;
+    e->max_count = ss.max_value;   // upper bound of every environment size
+    if ((st = dev_alloc(ctx, &e->d_key, e->capacity)) || (st = dev_alloc(ctx, &d_cat, e->capacity))) return bail(st);
+    if (keep_indices) {
+        if ((st = dev_alloc(ctx, &e->d_idx, e->capacity)) || (st = dev_alloc(ctx, &e->d_dist, e->capacity))) return bail(st);
+    }
+    EnvBuild b{};
+    b.n_env = n_anchors; b.order = d_order; b.ub = d_ub; b.off = e->d_off; b.count = e->d_count; b.key = e->d_key;
+    b.cat = d_cat; b.idx = e->d_idx; b.dist = e->d_dist; b.key_is_w = e->key_is_w ? 1 : 0; b.check_first_zero = 0;
+    {
+        ProfScope ps(ctx, LOCOHD_PROF_FILL);
+        ctx->launches += launch_env_fill(sv, ctx->kp, d_anchor_struct, d_anchor_prim, threshold, b, ctx->stream);
+    }
+    {
+        ProfScope ps(ctx, LOCOHD_PROF_SORT);
+        ctx->launches += launch_env_sort(ctx->kp, b, e->max_count, threshold, ctx->stream);
+    }
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
+    e->total = ss.total;  // stored entries (upper bound of the member count; exact sizes are in d_count)
+    release();            // stream-ordered: freed after the kernels above have run
+    *out = e;
+    return 0;
 }
 
 int run_score(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_pairs,
@@ -435,17 +424,13 @@ int run_score(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, u
     ScoreArgs sa{};
     sa.a = a->view(); sa.b = b->view();
     sa.n_pairs = n_pairs; sa.pairs = d_pairs; sa.jobs = d_jobs; sa.job_pair_off = d_job_off; sa.n_jobs = n_jobs;
-    sa.uniform_n = uniform_n; sa.wf_idx = d_wf_idx; sa.out = d_out; sa.stage_cap = 0;
+    sa.uniform_n = uniform_n; sa.wf_idx = d_wf_idx; sa.out = d_out; sa.stage_cap = 0; sa.only_unstaged = 0; sa.table_n = 0;
     int n;
     if (a->key_is_w != b->key_is_w) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "environment sets were built with different weight-function modes");
-    // stage in shared memory what a typical pair needs (1.5 x the mean sizes, at most the maxima); larger pairs
-    // read their environments from global memory
     const double mean_a = a->n_env ? (double)a->total / (double)a->n_env : 0.0;
     const double mean_b = b->n_env ? (double)b->total / (double)b->n_env : 0.0;
-    uint64_t stage = (uint64_t)(1.5 * (mean_a + mean_b)) + 64;
-    stage = std::min<uint64_t>(stage, (uint64_t)a->max_count + b->max_count);
-    stage = (stage + 63) & ~63ull;
-    { ProfScope ps(ctx, LOCOHD_PROF_SCORE); n = launch_score(sa, ctx->kp, (unsigned)stage, 0, ctx->stream); }
+    { ProfScope ps(ctx, LOCOHD_PROF_SCORE);
+      n = launch_score(sa, ctx->kp, a->max_count, b->max_count, mean_a, mean_b, ctx->stream); }
     if (n < 0) return fail(ctx, LOCOHD_ERR_UNSUPPORTED, "shared memory budget exceeded for %d categories", ctx->kp.C);
     ctx->launches += n;
     CU(ctx, cudaGetLastError());
@@ -522,7 +507,7 @@ int locohd_ctx_create(int device, locohd_ctx** out) {
     }
     if ((ce = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMemset(ctx->d_err, 0, sizeof(int))) != cudaSuccess) return bail(ce);
-    if ((ce = cudaMalloc(&ctx->d_fill, sizeof(FillStats))) != cudaSuccess) return bail(ce);
+    if ((ce = cudaMalloc(&ctx->d_scan, 2 * sizeof(ScanStats))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMalloc(&ctx->d_sqrt_tbl, kSqrtTableSize * sizeof(double))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMalloc(&ctx->d_rsqrt_tbl, kSqrtTableSize * sizeof(double))) != cudaSuccess) return bail(ce);
     std::vector<double> t(kSqrtTableSize), r(kSqrtTableSize);
@@ -541,7 +526,7 @@ void locohd_ctx_destroy(locohd_ctx* ctx) {
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_cat_w); cudaFree(ctx->d_cat_sw); cudaFree(ctx->d_wfs); cudaFree(ctx->d_tag_pairs);
-    cudaFree(ctx->d_sqrt_tbl); cudaFree(ctx->d_rsqrt_tbl); cudaFree(ctx->d_err); cudaFree(ctx->d_fill);
+    cudaFree(ctx->d_sqrt_tbl); cudaFree(ctx->d_rsqrt_tbl); cudaFree(ctx->d_err); cudaFree(ctx->d_scan);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -724,7 +709,8 @@ int locohd_structs_create(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* p
         (st = dev_alloc(ctx, &s->d_cat, n)) || (st = dev_alloc(ctx, &s->d_tag, n)) ||
         (st = dev_alloc(ctx, &s->d_meta, n_structs)) || (st = dev_alloc(ctx, &s->d_pf, n)) ||
         (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_sorted_pos, n)) ||
-        (st = dev_alloc(ctx, &s->d_cell_start, n_structs * (uint64_t)kCellStride)))
+        (st = dev_alloc(ctx, &s->d_cell_start, cell_entries(n, n_structs))) ||
+        (st = dev_alloc(ctx, &s->d_cell_fill, cell_entries(n, n_structs))))
         return bail(st);
     cudaError_t ce = cudaMemcpyAsync(s->d_prim_off, offs.data(), offs.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
     if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(s->d_xyz, xyz, 3 * n * sizeof(double), cudaMemcpyDefault, ctx->stream);
@@ -749,7 +735,7 @@ void locohd_structs_destroy(locohd_structs* s) {
     DeviceGuard g(ctx->device);
     dev_free(ctx, s->d_prim_off); dev_free(ctx, s->d_xyz); dev_free(ctx, s->d_cat); dev_free(ctx, s->d_tag);
     dev_free(ctx, s->d_meta); dev_free(ctx, s->d_pf); dev_free(ctx, s->d_pd); dev_free(ctx, s->d_sorted_pos);
-    dev_free(ctx, s->d_cell_start);
+    dev_free(ctx, s->d_cell_start); dev_free(ctx, s->d_cell_fill);
     delete s;
 }
 
@@ -802,23 +788,33 @@ static int rows_envset(locohd_ctx* ctx, uint64_t n_rows, uint64_t row_len, const
     ctx->launches += launch_convert_categories(cat16.ptr, d_cat8, row_len, ctx->kp.C, ctx->stream);
     if (xyz) ctx->launches += launch_validate_xyz(in.ptr, 3 * row_len, ctx->d_err, ctx->stream);
     locohd_envset* e = new locohd_envset();
-    e->ctx = ctx; e->n_env = n_rows; e->total = n_rows * row_len; e->max_count = (unsigned)row_len;
+    const uint64_t row_stride = (row_len + 1) & ~1ull;
+    e->ctx = ctx; e->n_env = n_rows; e->total = n_rows * row_stride; e->capacity = e->total + 2;
+    e->max_count = (unsigned)row_len;
     e->key_is_w = ctx->kp.n_wf == 1;
-    auto bail = [&](int st) { dev_free(ctx, d_cat8); destroy_envset(e); return st; };
+    uint8_t* d_cat = nullptr;
+    auto bail = [&](int st) { dev_free(ctx, d_cat8); dev_free(ctx, d_cat); destroy_envset(e); return st; };
     int st;
-    if ((st = dev_alloc(ctx, &e->d_count, n_rows)) || (st = dev_alloc(ctx, &e->d_off, n_rows)) ||
-        (st = alloc_envset_storage(ctx, e, e->total, true)))
+    if ((st = dev_alloc(ctx, &e->d_count, n_rows)) || (st = dev_alloc(ctx, &e->d_off, n_rows + 1)) ||
+        (st = dev_alloc(ctx, &e->d_key, e->capacity)) || (st = dev_alloc(ctx, &d_cat, e->capacity)) ||
+        (st = dev_alloc(ctx, &e->d_idx, e->capacity)) || (st = dev_alloc(ctx, &e->d_dist, e->capacity)))
         return bail(st);
+    EnvBuild b{};
+    b.n_env = n_rows; b.off = e->d_off; b.count = e->d_count; b.key = e->d_key; b.cat = d_cat; b.idx = e->d_idx;
+    b.dist = e->d_dist; b.key_is_w = e->key_is_w ? 1 : 0; b.check_first_zero = 1;
     {
         ProfScope ps(ctx, LOCOHD_PROF_OTHER);
-        ctx->launches += launch_fill_u64_iota_rows(e->d_off, e->d_count, n_rows, row_len, ctx->stream);
-        ctx->launches += launch_rows_fill(dmx ? in.ptr : nullptr, d_cat8, n_rows, row_len, xyz ? in.ptr : nullptr,
-                                          ctx->kp, env_out(ctx, e, e->total), ctx->stream);
+        ctx->launches += launch_rows_copy(dmx ? in.ptr : nullptr, d_cat8, n_rows, row_len, xyz ? in.ptr : nullptr,
+                                          ctx->kp, e->d_off, e->d_count, b, ctx->stream);
+    }
+    {
+        ProfScope ps(ctx, LOCOHD_PROF_SORT);
+        ctx->launches += launch_env_sort(ctx->kp, b, e->max_count, 0.0, ctx->stream);
     }
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
     if ((st = sync_and_check(ctx))) return bail(st);
-    dev_free(ctx, d_cat8);
+    dev_free(ctx, d_cat8); dev_free(ctx, d_cat);
     *out = e;
     return 0;
 }
@@ -841,53 +837,73 @@ int locohd_envset_from_coords(locohd_ctx* ctx, uint64_t n_points, const double* 
 
 void locohd_envset_destroy(locohd_envset* e) { destroy_envset(e); }
 uint64_t locohd_envset_size(const locohd_envset* e) { return e ? e->n_env : 0; }
-uint64_t locohd_envset_total_members(const locohd_envset* e) { return e ? e->total : 0; }
+uint64_t locohd_envset_total_members(const locohd_envset* e) {
+    if (!e || !e->n_env) return 0;
+    // exact member count = sum of the sizes (the store itself is sized by upper bounds)
+    DeviceGuard g(e->ctx->device);
+    cudaStreamSynchronize(e->ctx->stream);
+    std::vector<uint32_t> cnt(e->n_env);
+    if (cudaMemcpy(cnt.data(), e->d_count, e->n_env * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    uint64_t t = 0;
+    for (uint32_t c : cnt) t += c;
+    return t;
+}
 
 int locohd_envset_dump(locohd_ctx* ctx, const locohd_envset* e, uint64_t* offsets, double* distances,
                        uint16_t* categories, uint32_t* prim_indices) {
     API_BEGIN(ctx)
     if (!e) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null envset");
     TRY_ST(sync_and_check(ctx));
-    // The store is cursor-allocated (arbitrary environment order on the device): the dump is laid out in
-    // environment order, offsets = running sum of the sizes.
+    // The store leaves slack after every environment (its offsets come from upper bounds): the dump is compact,
+    // offsets = running sum of the exact sizes.
     const uint64_t n = e->n_env;
-    std::vector<uint64_t> off(n), canon(n + 1, 0);
+    std::vector<uint64_t> off(n + 1, 0), canon(n + 1, 0);
     std::vector<uint32_t> cnt(n);
     if (n) {
-        CU(ctx, cudaMemcpy(off.data(), e->d_off, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        CU(ctx, cudaMemcpy(off.data(), e->d_off, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
         CU(ctx, cudaMemcpy(cnt.data(), e->d_count, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
     for (uint64_t i = 0; i < n; ++i) canon[i + 1] = canon[i] + cnt[i];
     const uint64_t total = canon[n];
-    auto put = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
-        return cudaMemcpy(dst, src, bytes, cudaMemcpyDefault);
-    };
-    if (offsets) CU(ctx, put(offsets, canon.data(), (n + 1) * sizeof(uint64_t)));
+    if (offsets) CU(ctx, cudaMemcpy(offsets, canon.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyDefault));
+    std::vector<uint64_t> keys;
+    if ((categories || (distances && !e->d_dist)) && total) {
+        keys.resize(e->capacity);
+        CU(ctx, cudaMemcpy(keys.data(), e->d_key, e->capacity * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
     if (distances && total) {
-        const double* src = e->key_is_w ? e->d_dist : e->d_key;
-        if (!src) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "envset was built without keep_indices: distances are not kept");
-        std::vector<double> raw(e->total), outv(total);
-        CU(ctx, cudaMemcpy(raw.data(), src, e->total * sizeof(double), cudaMemcpyDeviceToHost));
-        for (uint64_t i = 0; i < n; ++i) std::copy(raw.begin() + off[i], raw.begin() + off[i] + cnt[i], outv.begin() + canon[i]);
-        CU(ctx, put(distances, outv.data(), total * sizeof(double)));
+        std::vector<double> outv(total);
+        if (e->d_dist) {
+            std::vector<double> raw(e->capacity);
+            CU(ctx, cudaMemcpy(raw.data(), e->d_dist, e->capacity * sizeof(double), cudaMemcpyDeviceToHost));
+            for (uint64_t i = 0; i < n; ++i) std::copy(raw.begin() + off[i], raw.begin() + off[i] + cnt[i], outv.begin() + canon[i]);
+        } else if (!e->key_is_w) {
+            // without the parity arrays the distances are only known up to the 8 mantissa bits that hold the category
+            for (uint64_t i = 0; i < n; ++i)
+                for (uint32_t k = 0; k < cnt[i]; ++k) {
+                    const uint64_t bits = keys[off[i] + k] & ~kCatMask;
+                    std::memcpy(&outv[canon[i] + k], &bits, sizeof(double));
+                }
+        } else {
+            return fail(ctx, LOCOHD_ERR_BAD_PARAM, "envset was built without keep_indices: distances are not kept");
+        }
+        CU(ctx, cudaMemcpy(distances, outv.data(), total * sizeof(double), cudaMemcpyDefault));
     }
     if (categories && total) {
-        std::vector<uint8_t> c8(e->total);
-        CU(ctx, cudaMemcpy(c8.data(), e->d_cat, e->total, cudaMemcpyDeviceToHost));
         std::vector<uint16_t> c16(total);
         for (uint64_t i = 0; i < n; ++i)
             for (uint32_t k = 0; k < cnt[i]; ++k) {
-                const uint8_t c = c8[off[i] + k];
+                const uint8_t c = (uint8_t)(keys[off[i] + k] & kCatMask);
                 c16[canon[i] + k] = c == kUnknownCat8 ? (uint16_t)LOCOHD_UNKNOWN_CATEGORY : c;
             }
-        CU(ctx, put(categories, c16.data(), total * sizeof(uint16_t)));
+        CU(ctx, cudaMemcpy(categories, c16.data(), total * sizeof(uint16_t), cudaMemcpyDefault));
     }
     if (prim_indices && total) {
         if (!e->d_idx) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "envset was built without keep_indices");
-        std::vector<uint32_t> raw(e->total), outv(total);
-        CU(ctx, cudaMemcpy(raw.data(), e->d_idx, e->total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> raw(e->capacity), outv(total);
+        CU(ctx, cudaMemcpy(raw.data(), e->d_idx, e->capacity * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         for (uint64_t i = 0; i < n; ++i) std::copy(raw.begin() + off[i], raw.begin() + off[i] + cnt[i], outv.begin() + canon[i]);
-        CU(ctx, put(prim_indices, outv.data(), total * sizeof(uint32_t)));
+        CU(ctx, cudaMemcpy(prim_indices, outv.data(), total * sizeof(uint32_t), cudaMemcpyDefault));
     }
     return 0;
     API_END()
@@ -1017,7 +1033,8 @@ int locohd_from_primitives(locohd_ctx* ctx, uint64_t n_a, const double* xyz_a, c
         (st = dev_alloc(ctx, &s->d_cat, n)) || (st = dev_alloc(ctx, &s->d_tag, n)) ||
         (st = dev_alloc(ctx, &s->d_meta, 2)) || (st = dev_alloc(ctx, &s->d_pf, n)) ||
         (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_sorted_pos, n)) ||
-        (st = dev_alloc(ctx, &s->d_cell_start, 2 * (uint64_t)kCellStride)))
+        (st = dev_alloc(ctx, &s->d_cell_start, cell_entries(n, 2))) ||
+        (st = dev_alloc(ctx, &s->d_cell_fill, cell_entries(n, 2))))
         return cleanup(st);
     const uint64_t offs[3] = {0, n_a, n};
     cudaError_t ce = cudaMemcpyAsync(s->d_prim_off, offs, sizeof offs, cudaMemcpyHostToDevice, ctx->stream);

@@ -1,17 +1,22 @@
 // locohd_kernels.cu — hand-written sm_100a kernels of the LoCoHD per-anchor scoring path.
 //
 // Pipeline (all FP64 where the reference is FP64; no tensor cores: there is no dense contraction):
-//   K0  build_cells_kernel   one CTA per structure: bounding box, cell grid, counting sort of the primitives
-//                            into cell order (replaces KdTree::build_by_ordered_float, locohd.rs:504-510)
-//   K1  env_count_kernel     one warp per anchor: float4 prefilter over the 27 neighbour cells + exact FP64
-//                            membership test (kd-tree `within_radius` predicate) + tag rule (locohd.rs:521-528)
-//   K1' env_fill_kernel      same gather, staged in shared memory, per-warp bucket sort by distance
-//                            (utils::sort_together, utils.rs:25-39), written to the environment store
-//   K2  score_kernel         one warp per anchor pair: merge-path split of the two sorted environments over the
-//                            32 lanes, per-lane category counts by warp prefix sums, per-lane walk that
-//                            accumulates dW * H (stat_dist_integral, locohd.rs:61-226, as a flat prefix scan)
-// plus the small kernels around them (scan of counts, row sorting for from_dmxs/from_coords, the exact-order
-// sequential walk for from_anchors, leaf-math probes).
+//   K0   build_cells_kernel     one CTA per structure: bounding box, half-radius cell grid, counting sort of the
+//                               primitives into cell order (replaces KdTree::build_by_ordered_float, locohd.rs:504-510)
+//   Ka   anchor_slot_* kernels  put the requested anchors into cell order, so that the 32 lanes of a warp work on
+//                               neighbouring anchors and read the same candidate cells
+//   K1a  env_tile_kernel<false> one THREAD per anchor: FP32 prefilter over the candidate cells, counts the
+//                               survivors (upper bound of the environment size) -> scan -> store offsets
+//   K1b  env_tile_kernel<true>  same traversal; survivors are re-tested in FP64 with the kd-tree predicate, the tag
+//                               rule is applied and (distance, category) is written unsorted into the store
+//                               (kdtree.within_radius + filter + euclidean_distance, locohd.rs:521-538)
+//   K1c  env_sort_kernel<CAP>   one warp per environment: bucket sort by distance in shared memory, CDF evaluation,
+//                               packed keys written back in place (utils::sort_together, utils.rs:25-39)
+//   K2   score_fast_kernel /    one warp per anchor pair: merge-path split of the two sorted environments over the
+//        score_kernel           32 lanes, per-lane category counts by warp prefix sums, per-lane walk that
+//                               accumulates dW * H (stat_dist_integral, locohd.rs:61-226, as a flat prefix scan)
+// plus the small kernels around them (scans, rows of from_dmxs/from_coords, the exact-order sequential walk of
+// from_anchors, leaf-math probes).
 #include "locohd_kernels.cuh"
 
 #include <cfloat>
@@ -24,12 +29,6 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ void raise(int* err, int code) { atomicCAS(err, 0, code); }
-
-__device__ __forceinline__ unsigned lanemask_lt() {
-    unsigned m;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-    return m;
-}
 
 // ------------------------------------------------------------------------------------------------
 // small utility kernels
@@ -49,9 +48,97 @@ __global__ void validate_xyz_kernel(const double* __restrict__ xyz, uint64_t n3,
 }
 
 // ------------------------------------------------------------------------------------------------
-// K0: cell list.  One CTA (256 threads) per structure.
+// Exclusive scan of u32 values into u64 offsets (three kernels: tile sums, scan of the sums, apply).
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 8;
+constexpr int kScanTile = kScanThreads * kScanPer;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* total) {
+    __shared__ unsigned long long wsum[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long u = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    unsigned long long base = 0, tot = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+        if (w < wid) base += wsum[w];
+        tot += wsum[w];
+    }
+    __syncthreads();
+    if (total) *total = tot;
+    return base + incl - v;
+}
+
+__device__ __forceinline__ unsigned scan_value(unsigned v, int round_even) { return round_even ? (v + 1u) & ~1u : v; }
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t* __restrict__ values, uint64_t n,
+                                                                      int round_even,
+                                                                      uint64_t* __restrict__ block_sums,
+                                                                      ScanStats* stats) {
+    const uint64_t t0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPer;
+    unsigned long long sum = 0;
+    unsigned mx = 0;
+    for (int q = 0; q < kScanPer; ++q) {
+        const uint64_t i = t0 + q;
+        if (i < n) {
+            const unsigned c = values[i];
+            sum += scan_value(c, round_even);
+            mx = max(mx, c);
+        }
+    }
+    unsigned long long tot;
+    block_exclusive_scan(sum, &tot);
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(&stats->max_value, mx);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(uint64_t* block_sums, uint64_t n_blocks,
+                                                                       ScanStats* stats) {
+    unsigned long long carry = 0;
+    for (uint64_t b0 = 0; b0 < n_blocks; b0 += kScanThreads) {
+        const uint64_t i = b0 + threadIdx.x;
+        const unsigned long long v = (i < n_blocks) ? block_sums[i] : 0ull;
+        unsigned long long tot;
+        const unsigned long long ex = block_exclusive_scan(v, &tot);
+        if (i < n_blocks) block_sums[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) stats->total = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ values, uint64_t n,
+                                                                  int round_even,
+                                                                  const uint64_t* __restrict__ block_sums,
+                                                                  uint64_t* __restrict__ off) {
+    const uint64_t t0 = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPer;
+    unsigned loc[kScanPer];
+    unsigned long long sum = 0;
+    for (int q = 0; q < kScanPer; ++q) {
+        const uint64_t i = t0 + q;
+        loc[q] = (i < n) ? scan_value(values[i], round_even) : 0u;
+        sum += loc[q];
+    }
+    unsigned long long run = block_sums[blockIdx.x] + block_exclusive_scan(sum, nullptr);
+    for (int q = 0; q < kScanPer; ++q) {
+        const uint64_t i = t0 + q;
+        if (i < n) off[i] = run;
+        run += loc[q];
+        if (i + 1 == n) off[n] = run;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: cell list.  One CTA (256 threads) per structure; cell edge = half the radius (search +-2 cells), enlarged
+// when the structure would need more than max(2 N, 8) cells.
 // ------------------------------------------------------------------------------------------------
 constexpr int kCellThreads = 256;
+constexpr int kMaxCellsAxis = 1024;
 
 __device__ __forceinline__ int cell_coord(double rel, double inv_cell, int n) {
     int c = (int)(rel * inv_cell);
@@ -61,13 +148,14 @@ __device__ __forceinline__ int cell_coord(double rel, double inv_cell, int n) {
 __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s, double threshold) {
     __shared__ double red[6][kCellThreads / 32];
     __shared__ StructMeta sm_meta;
-    __shared__ uint32_t hist[kMaxCells];
-    __shared__ uint32_t warp_tot[kCellThreads / 32];
+    __shared__ unsigned long long sh_carry;
 
     const uint64_t sid = blockIdx.x;
     const uint64_t base = s.prim_off[sid];
     const uint32_t n = (uint32_t)(s.prim_off[sid + 1] - base);
     const double* xyz = s.xyz + 3 * base;
+    uint32_t* cell_start = s.cell_start + cell_base(base, sid);
+    uint32_t* cell_fill = s.cell_fill + cell_base(base, sid);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     // ---- bounding box
@@ -98,16 +186,27 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
         if (n == 0) { lo[0] = lo[1] = lo[2] = 0.0; hi[0] = hi[1] = hi[2] = 0.0; }
         const double ext[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
         const double emax = fmax(ext[0], fmax(ext[1], ext[2]));
-        // cell edge slightly larger than the radius so that rounding can never push a neighbour two cells away
-        double inv_cell = 1.0 / (threshold * (1.0 + 1e-6));
+        const long long max_cells = max(2ll * (long long)n, 8ll);
+        // cell edge slightly larger than half the radius: with reach = floor(r / edge * (1 + 1e-6)) + 1 rounding can
+        // never push a member of the environment outside the visited cells
+        double inv_cell = 2.0 / (threshold * (1.0 + 1e-6));
         if (!(inv_cell > 0.0) || !isfinite(inv_cell)) inv_cell = 0.0;  // infinite radius: a single cell
-        if (emax * inv_cell > (double)kMaxCellsAxis - 0.001) inv_cell = ((double)kMaxCellsAxis - 0.001) / emax;
         StructMeta m;
+        for (int it = 0; it < 200; ++it) {
+            m.nx = (int)fmin(ext[0] * inv_cell, 1.0e6) + 1;
+            m.ny = (int)fmin(ext[1] * inv_cell, 1.0e6) + 1;
+            m.nz = (int)fmin(ext[2] * inv_cell, 1.0e6) + 1;
+            if ((long long)m.nx * m.ny * m.nz <= max_cells && m.nx <= kMaxCellsAxis && m.ny <= kMaxCellsAxis &&
+                m.nz <= kMaxCellsAxis)
+                break;
+            inv_cell *= 0.8;
+        }
+        if ((long long)m.nx * m.ny * m.nz > max_cells) { inv_cell = 0.0; m.nx = m.ny = m.nz = 1; }
         m.ox = lo[0]; m.oy = lo[1]; m.oz = lo[2];
         m.inv_cell = inv_cell;
-        m.nx = min(kMaxCellsAxis, (int)(ext[0] * inv_cell) + 1);
-        m.ny = min(kMaxCellsAxis, (int)(ext[1] * inv_cell) + 1);
-        m.nz = min(kMaxCellsAxis, (int)(ext[2] * inv_cell) + 1);
+        const double span = threshold * inv_cell * (1.0 + 1e-6);  // radius in cells
+        m.reach = (inv_cell > 0.0 && isfinite(span)) ? (int)fmin(span, 2.0e6) + 1 : 0;
+        if (inv_cell == 0.0) m.reach = 0;
         // FP32 prefilter: relative coordinates are rounded to f32 (error <= emax * 2^-24 each); the bound below
         // is generous (see DESIGN.md "prefilter margin").
         const double delta = 4.0 * emax * 5.9604644775390625e-8;
@@ -116,62 +215,52 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
         float tf = (t2 < 3.0e38) ? (float)t2 : INFINITY;
         if (isfinite(tf)) tf = nextafterf(tf, INFINITY);
         m.thr2f = tf;
+        m.pad[0] = m.pad[1] = m.pad[2] = 0;
         sm_meta = m;
         s.meta[sid] = m;
+        sh_carry = 0;
     }
-    for (int c = tid; c < kMaxCells; c += kCellThreads) hist[c] = 0;
     __syncthreads();
     const StructMeta m = sm_meta;
     const int ncell = m.nx * m.ny * m.nz;
+    for (int c = tid; c <= ncell; c += kCellThreads) cell_start[c] = 0;
+    __syncthreads();
 
-    // ---- histogram
+    // ---- histogram (global atomics: the grid can be larger than shared memory)
     for (uint32_t i = tid; i < n; i += kCellThreads) {
         const double x = xyz[3 * (uint64_t)i], y = xyz[3 * (uint64_t)i + 1], z = xyz[3 * (uint64_t)i + 2];
         const int cx = cell_coord(x - m.ox, m.inv_cell, m.nx);
         const int cy = cell_coord(y - m.oy, m.inv_cell, m.ny);
         const int cz = cell_coord(z - m.oz, m.inv_cell, m.nz);
-        atomicAdd(&hist[(cz * m.ny + cy) * m.nx + cx], 1u);
+        atomicAdd(&cell_start[(cz * m.ny + cy) * m.nx + cx], 1u);
     }
     __syncthreads();
 
-    // ---- exclusive scan of hist[0..ncell) (16 entries per thread, kMaxCells = 4096)
-    constexpr int kPer = kMaxCells / kCellThreads;
-    uint32_t local[kPer];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-        const int c = tid * kPer + q;
-        local[q] = (c < ncell) ? hist[c] : 0u;
-        sum += local[q];
-    }
-    uint32_t incl = sum;
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_tot[wid] = incl;
-    __syncthreads();
-    uint32_t wbase = 0;
-    for (int w = 0; w < wid; ++w) wbase += warp_tot[w];
-    uint32_t run = wbase + incl - sum;
-    __syncthreads();
-    uint32_t* cell_start = s.cell_start + sid * kCellStride;
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-        const int c = tid * kPer + q;
-        if (c < ncell) { hist[c] = run; cell_start[c] = run; }
-        run += local[q];
+    // ---- exclusive scan over the cells, kCellThreads cells per round
+    for (int c0 = 0; c0 < ncell; c0 += kCellThreads) {
+        const int c = c0 + tid;
+        const unsigned long long v = (c < ncell) ? cell_start[c] : 0u;
+        unsigned long long tot;
+        const unsigned long long ex = block_exclusive_scan(v, &tot);
+        const unsigned long long carry = sh_carry;
+        if (c < ncell) {
+            cell_start[c] = (uint32_t)(carry + ex);
+            cell_fill[c] = (uint32_t)(carry + ex);
+        }
+        __syncthreads();
+        if (tid == 0) sh_carry = carry + tot;
+        __syncthreads();
     }
     if (tid == 0) cell_start[ncell] = n;
     __syncthreads();
 
-    // ---- scatter into cell order (hist now holds the running cursor of each cell)
+    // ---- scatter into cell order
     for (uint32_t i = tid; i < n; i += kCellThreads) {
         const double x = xyz[3 * (uint64_t)i], y = xyz[3 * (uint64_t)i + 1], z = xyz[3 * (uint64_t)i + 2];
         const int cx = cell_coord(x - m.ox, m.inv_cell, m.nx);
         const int cy = cell_coord(y - m.oy, m.inv_cell, m.ny);
         const int cz = cell_coord(z - m.oz, m.inv_cell, m.nz);
-        const uint32_t pos = atomicAdd(&hist[(cz * m.ny + cy) * m.nx + cx], 1u);
+        const uint32_t pos = atomicAdd(&cell_fill[(cz * m.ny + cy) * m.nx + cx], 1u);
         PrimRec r;
         r.x = x; r.y = y; r.z = z;
         r.orig = i;
@@ -184,7 +273,7 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: neighbour gather.  One warp per anchor.
+// Tag rule
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool tag_pair_in_table(const KParams& p, uint32_t a, uint32_t b) {
     const uint64_t key = ((uint64_t)a << 32) | b;
@@ -208,156 +297,245 @@ __device__ __forceinline__ bool tag_rule_accepts(const KParams& p, uint32_t anch
     return p.tpr_accepted_pairs ? acc : !acc;
 }
 
-struct AnchorRef {
-    bool ok;
-    uint64_t base;       // first primitive of the structure
-    uint32_t jpos;       // cell-sorted position of the anchor
-    const uint32_t* cell_start;
-    StructMeta m;
-};
-
-__device__ __forceinline__ AnchorRef resolve_anchor(const StructsView& s, const uint32_t* anchor_struct,
-                                                    const uint32_t* anchor_prim, uint64_t e, int* err) {
-    AnchorRef a;
+// ------------------------------------------------------------------------------------------------
+// Ka: anchors in cell order.  slot = global cell-sorted position of the anchor's primitive.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool anchor_slot(const StructsView& s, const uint32_t* anchor_struct,
+                                            const uint32_t* anchor_prim, uint64_t e, int* err, uint64_t* slot) {
     const uint64_t sid = anchor_struct ? anchor_struct[e] : 0;
     const uint32_t prim = anchor_prim[e];
-    a.ok = false;
-    if (sid >= s.n_structs) { raise(err, LOCOHD_ERR_INDEX); return a; }
-    a.base = s.prim_off[sid];
-    const uint64_t n = s.prim_off[sid + 1] - a.base;
-    if (prim >= n) { raise(err, LOCOHD_ERR_INDEX); return a; }  // prim_seq[anchor_idx] panics upstream (locohd.rs:521)
-    a.jpos = s.sorted_pos[a.base + prim];
-    a.cell_start = s.cell_start + sid * kCellStride;
-    a.m = s.meta[sid];
-    a.ok = true;
-    return a;
+    if (sid >= s.n_structs) { raise(err, LOCOHD_ERR_INDEX); return false; }
+    const uint64_t base = s.prim_off[sid];
+    if (prim >= s.prim_off[sid + 1] - base) { raise(err, LOCOHD_ERR_INDEX); return false; }  // locohd.rs:521 panics
+    *slot = base + s.sorted_pos[base + prim];
+    return true;
 }
 
-// Visits every member of the anchor's environment.  `emit(slot, d2, j)` is called by the lane that owns an
-// accepted primitive (j = cell-sorted position), with slot = running index inside the environment.
-// Membership = box test + d^2 < r^2 with unfused FP64 arithmetic in the kd-tree crate's operation order
-// (neighbour minus anchor; ((dx^2 + dy^2) + dz^2)); the anchor itself is always kept, others must pass the tag rule
-// (locohd.rs:521-528).  Returns the environment size (warp-uniform).
-template <class Emit>
-__device__ __forceinline__ uint32_t gather_environment(const StructsView& s, const KParams& p, const AnchorRef& a,
-                                                       double threshold, int lane, Emit&& emit) {
-    const PrimRec q = s.pd[a.base + a.jpos];
-    const float4 qf = s.pf[a.base + a.jpos];
+__global__ void anchor_slot_count_kernel(StructsView s, KParams p, uint64_t n_env,
+                                         const uint32_t* __restrict__ anchor_struct,
+                                         const uint32_t* __restrict__ anchor_prim, uint32_t* slot_cnt) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_env) return;
+    uint64_t slot = 0;
+    anchor_slot(s, anchor_struct, anchor_prim, e, p.err, &slot);  // invalid anchors go to slot 0 (the call fails)
+    atomicAdd(&slot_cnt[slot], 1u);
+}
+
+__global__ void anchor_slot_scatter_kernel(StructsView s, KParams p, uint64_t n_env,
+                                           const uint32_t* __restrict__ anchor_struct,
+                                           const uint32_t* __restrict__ anchor_prim, uint32_t* slot_cnt,
+                                           const uint64_t* __restrict__ slot_off, uint32_t* __restrict__ order) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_env) return;
+    uint64_t slot = 0;
+    anchor_slot(s, anchor_struct, anchor_prim, e, p.err, &slot);
+    const uint32_t k = atomicSub(&slot_cnt[slot], 1u) - 1u;
+    order[slot_off[slot] + k] = (uint32_t)e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a / K1b: one thread per anchor, anchors taken in cell order.
+//   Every lane walks the candidate cells of its own anchor (rows of 2*reach+1 cells are contiguous in the
+//   cell-sorted arrays); neighbouring lanes sit in the same or adjacent cells, so their float4 loads hit the same
+//   lines.  FILL: FP32 survivors are parked in a small per-lane list and the whole warp re-tests them together in
+//   FP64 — box test + ((dx^2 + dy^2) + dz^2) < r^2 with unfused arithmetic, the kd-tree crate's predicate and
+//   operation order; the anchor itself is always kept, others must pass the tag rule (locohd.rs:521-528).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileThreads = 128;
+constexpr int kPend = 16;
+
+template <bool FILL>
+__global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, KParams p, uint64_t n_env,
+                                                                const uint32_t* __restrict__ order,
+                                                                const uint32_t* __restrict__ anchor_struct,
+                                                                const uint32_t* __restrict__ anchor_prim,
+                                                                double threshold, uint32_t* __restrict__ ub,
+                                                                EnvBuild b) {
+    __shared__ uint32_t pend[FILL ? kPend : 1][kTileThreads];
+    const int tid = threadIdx.x;
+    const uint64_t t = (uint64_t)blockIdx.x * kTileThreads + tid;
+    bool active = t < n_env;
+    const uint64_t e = active ? order[t] : 0;
+    uint64_t base = 0;
+    uint32_t jpos = 0;
+    StructMeta m;
+    m.nx = m.ny = m.nz = 1; m.reach = 0; m.inv_cell = 0.0; m.ox = m.oy = m.oz = 0.0; m.thr2f = 0.f;
+    const uint32_t* cell_start = s.cell_start;
+    if (active) {
+        const uint64_t sid = anchor_struct ? anchor_struct[e] : 0;
+        const uint32_t prim = anchor_prim[e];
+        if (sid >= s.n_structs || prim >= s.prim_off[sid + 1] - s.prim_off[sid]) {
+            raise(p.err, LOCOHD_ERR_INDEX);
+            active = false;
+        } else {
+            base = s.prim_off[sid];
+            jpos = s.sorted_pos[base + prim];
+            m = s.meta[sid];
+            cell_start = s.cell_start + cell_base(base, sid);
+        }
+    }
+    PrimRec q;
+    q.x = q.y = q.z = 0.0; q.orig = 0; q.cat = 0;
+    float4 qf = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) { q = s.pd[base + jpos]; qf = s.pf[base + jpos]; }
     const uint32_t qtag = __float_as_uint(qf.w);
     const double r2 = __dmul_rn(threshold, threshold);
-    const double lox = q.x - threshold, hix = q.x + threshold;
-    const double loy = q.y - threshold, hiy = q.y + threshold;
-    const double loz = q.z - threshold, hiz = q.z + threshold;
-    const StructMeta& m = a.m;
     const int cx = cell_coord(q.x - m.ox, m.inv_cell, m.nx);
     const int cy = cell_coord(q.y - m.oy, m.inv_cell, m.ny);
     const int cz = cell_coord(q.z - m.oz, m.inv_cell, m.nz);
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, m.nx - 1);
-    const unsigned lt = lanemask_lt();
-    uint32_t total = 0;
-    for (int zz = max(cz - 1, 0); zz <= min(cz + 1, m.nz - 1); ++zz) {
-        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, m.ny - 1); ++yy) {
-            const int row = (zz * m.ny + yy) * m.nx;
-            const uint32_t beg = __ldg(a.cell_start + row + x0);
-            const uint32_t end = __ldg(a.cell_start + row + x1 + 1);
-            for (uint32_t j0 = beg; j0 < end; j0 += 32) {
-                const uint32_t j = j0 + lane;
-                bool pass = false;
-                float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < end) {
-                    c = __ldg(s.pf + a.base + j);
-                    const float dx = c.x - qf.x, dy = c.y - qf.y, dz = c.z - qf.z;
-                    const float d2f = dx * dx + dy * dy + dz * dz;
-                    pass = d2f <= m.thr2f;
+    const int x0 = max(cx - m.reach, 0), x1 = min(cx + m.reach, m.nx - 1);
+    int reach = active ? m.reach : 0;
+    for (int o = 16; o; o >>= 1) reach = max(reach, __shfl_xor_sync(kFull, reach, o));   // warp-uniform loop bounds
+
+    const float4* pf = s.pf + base;
+    const PrimRec* pd = s.pd + base;
+    const uint64_t off = (FILL && active) ? b.off[e] : 0;
+    const uint32_t cap = (FILL && active) ? b.ub[e] : 0;
+    uint32_t cnt = 0, np = 0;
+
+    auto flush = [&]() {
+        uint32_t mx = np;
+        for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+        for (uint32_t k = 0; k < mx; ++k) {
+            if (k < np) {
+                const uint32_t j = pend[FILL ? k : 0][tid];
+                const PrimRec r = pd[j];
+                const bool in_box = !(r.x < q.x - threshold) && !(r.x > q.x + threshold) &&
+                                    !(r.y < q.y - threshold) && !(r.y > q.y + threshold) &&
+                                    !(r.z < q.z - threshold) && !(r.z > q.z + threshold);
+                const double ex = r.x - q.x, ey = r.y - q.y, ez = r.z - q.z;
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+                bool acc = in_box && (d2 < r2);
+                if (acc && j != jpos) acc = tag_rule_accepts(p, qtag, __float_as_uint(__ldg(&pf[j].w)));
+                if (acc) {
+                    if (cnt < cap) {
+                        b.key[off + cnt] = (uint64_t)__double_as_longlong(sqrt(d2));  // utils.rs:1-8
+                        b.cat[off + cnt] = (uint8_t)r.cat;
+                        if (b.idx) b.idx[off + cnt] = r.orig;
+                    }
+                    ++cnt;
                 }
-                bool acc = false;
-                double d2 = 0.0;
-                if (pass) {
-                    const PrimRec r = s.pd[a.base + j];
-                    const bool in_box = !(r.x < lox) && !(r.x > hix) && !(r.y < loy) && !(r.y > hiy) &&
-                                        !(r.z < loz) && !(r.z > hiz);
-                    const double ex = r.x - q.x, ey = r.y - q.y, ez = r.z - q.z;
-                    d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-                    acc = in_box && (d2 < r2);
-                    if (acc && j != a.jpos) acc = tag_rule_accepts(p, qtag, __float_as_uint(c.w));
+            }
+        }
+        np = 0;
+    };
+
+    for (int dz = -reach; dz <= reach; ++dz) {
+        for (int dy = -reach; dy <= reach; ++dy) {
+            const int zz = cz + dz, yy = cy + dy;
+            uint32_t j = 0, end = 0;
+            if (active && abs(dz) <= m.reach && abs(dy) <= m.reach && zz >= 0 && zz < m.nz && yy >= 0 && yy < m.ny) {
+                const int row = (zz * m.ny + yy) * m.nx;
+                j = __ldg(cell_start + row + x0);
+                end = __ldg(cell_start + row + x1 + 1);
+            }
+            while (__any_sync(kFull, j < end)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (j < end) {
+                        const float4 c = __ldg(pf + j);
+                        const float dx = c.x - qf.x, dyf = c.y - qf.y, dzf = c.z - qf.z;
+                        const float d2f = dx * dx + dyf * dyf + dzf * dzf;
+                        if (d2f <= m.thr2f) {
+                            if (FILL) { pend[FILL ? np : 0][tid] = j; ++np; } else { ++cnt; }
+                        }
+                        ++j;
+                    }
                 }
-                const unsigned bal = __ballot_sync(kFull, acc);
-                if (acc) emit(total + __popc(bal & lt), d2, j);
-                total += __popc(bal);
+                if (FILL && __any_sync(kFull, np > (uint32_t)(kPend - 4))) flush();
             }
         }
     }
-    return total;
-}
-
-constexpr int kEnvWarps = 4;
-
-// Size probe on a strided sample of the anchors (capacity estimate for the cursor-allocated store).
-__global__ void __launch_bounds__(kEnvWarps * 32) env_count_sample_kernel(StructsView s, KParams p, uint64_t n_sample,
-                                                                          uint64_t stride,
-                                                                          const uint32_t* __restrict__ anchor_struct,
-                                                                          const uint32_t* __restrict__ anchor_prim,
-                                                                          double threshold,
-                                                                          uint32_t* __restrict__ count) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t i = (uint64_t)blockIdx.x * kEnvWarps + (threadIdx.x >> 5);
-    if (i >= n_sample) return;
-    const AnchorRef a = resolve_anchor(s, anchor_struct, anchor_prim, i * stride, p.err);
-    uint32_t m = 0;
-    if (a.ok) m = gather_environment(s, p, a, threshold, lane, [](uint32_t, double, uint32_t) {});
-    if (lane == 0) count[i] = m;
+    if (FILL) {
+        flush();
+        if (active) {
+            if (cnt > cap) raise(p.err, LOCOHD_ERR_CUDA);  // the FP32 count is an upper bound by construction
+            b.count[e] = min(cnt, cap);
+        }
+    } else if (active) {
+        ub[e] = cnt;
+    } else if (t < n_env) {
+        ub[e] = 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-warp bucket sort in shared memory.
-//   keys are non-NaN doubles.  (1) every entry goes to a bucket that is a monotone function of its key,
-//   (2) buckets are laid out by a warp prefix sum, (3) every lane insertion-sorts a few (mostly 0-2 entry)
-//   buckets, after which `perm` lists the entries in ascending key order, so the caller can emit them with
-//   coalesced stores.  Expected O(M) work per environment.
+// K1c: per-warp bucket sort of one environment, in place in the store.
+//   (1) every member goes to a bucket that is a monotone function of its distance, (2) buckets are laid out by a
+//   warp prefix sum, (3) every lane insertion-sorts a few (mostly 0-2 member) buckets; `perm` then lists the
+//   members in ascending order, and they are written back with coalesced stores as packed keys:
+//   f64 bits of W(d) (or of d) with the low mantissa byte replaced by the category.
 // ------------------------------------------------------------------------------------------------
-template <int CAP>
-struct WarpSortLayout {
+constexpr int kSortWarps = 4;
+
+template <int CAP, bool DEBUG>
+struct SortLayout {
     static constexpr int NB = CAP > 1024 ? 1024 : CAP;  // buckets
-    static constexpr int kKeyOff = 0;
-    static constexpr int kPayOff = kKeyOff + 8 * CAP;
-    static constexpr int kEndOff = kPayOff + 4 * CAP;          // u32 [NB]: bucket end offsets
-    static constexpr int kBktOff = kEndOff + 4 * NB;           // u16 [CAP]
-    static constexpr int kPermOff = kBktOff + 2 * CAP;         // u16 [CAP]
-    static constexpr int kBytes = kPermOff + 2 * CAP;          // 16 * CAP + 4 * NB
+    static constexpr int kKeyOff = 0;                           // f64 [CAP]
+    static constexpr int kIdxOff = kKeyOff + 8 * CAP;           // u32 [CAP] (DEBUG)
+    static constexpr int kEndOff = kIdxOff + (DEBUG ? 4 * CAP : 0);  // u32 [NB]
+    static constexpr int kBktOff = kEndOff + 4 * NB;            // u16 [CAP]
+    static constexpr int kPermOff = kBktOff + 2 * CAP;          // u16 [CAP]
+    static constexpr int kCatOff = kPermOff + 2 * CAP;          // u8 [CAP]
+    static constexpr int kBytes = (kCatOff + CAP + 15) & ~15;
 };
 
-// `scale` maps a key to [0, NB): bucket = clamp(int((float)(key * scale))).  scale <= 0 asks for the scale
-// to be derived from the largest finite key.  Returns with perm[0..M) = entry indices in ascending key order
-// (ties in arrival order) after a __syncwarp.
-template <int CAP>
-__device__ __forceinline__ void warp_bucket_sort(unsigned char* smem, uint32_t M, int lane, double scale) {
-    using L = WarpSortLayout<CAP>;
+__device__ __forceinline__ uint64_t pack_key(double w, uint32_t cat) {
+    w = w + 0.0;                 // -0.0 -> +0.0
+    w = fmax(w, 0.0);            // a CDF that rounds to a tiny negative value must not set the sign bit
+    return ((uint64_t)__double_as_longlong(w) & ~kCatMask) | (uint64_t)(cat & 0xFFu);
+}
+
+template <int CAP, bool DEBUG>
+__global__ void __launch_bounds__(kSortWarps * 32) env_sort_kernel(KParams p, EnvBuild b, uint32_t min_m,
+                                                                   double scale) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using L = SortLayout<CAP, DEBUG>;
     constexpr int NB = L::NB;
-    const double* key = reinterpret_cast<const double*>(smem + L::kKeyOff);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t e = (uint64_t)blockIdx.x * kSortWarps + wib;
+    if (e >= b.n_env) return;
+    const uint32_t M = b.count[e];
+    if (M <= min_m || M > (uint32_t)CAP) return;
+    unsigned char* smem = smem_raw + (size_t)wib * L::kBytes;
+    double* key = reinterpret_cast<double*>(smem + L::kKeyOff);
+    uint32_t* sidx = reinterpret_cast<uint32_t*>(smem + L::kIdxOff);
     uint32_t* bend = reinterpret_cast<uint32_t*>(smem + L::kEndOff);
     uint16_t* bkt = reinterpret_cast<uint16_t*>(smem + L::kBktOff);
     uint16_t* perm = reinterpret_cast<uint16_t*>(smem + L::kPermOff);
+    uint8_t* scat = smem + L::kCatOff;
+    const uint64_t off = b.off[e];
+    uint64_t* gkey = b.key + off;
 
-    if (!(scale > 0.0)) {
-        double kmax = 0.0;
-        for (uint32_t e = lane; e < M; e += 32) {
-            const double k = key[e];
-            if (isfinite(k)) kmax = fmax(kmax, k);
-        }
+    // ---- load
+    bool bad = false;
+    double kmax = 0.0;
+    for (uint32_t i = lane; i < M; i += 32) {
+        const double d = __longlong_as_double((long long)gkey[i]);
+        bad |= isnan(d);
+        if (isfinite(d)) kmax = fmax(kmax, d);
+        key[i] = d;
+        scat[i] = b.cat[off + i];
+        if (DEBUG) sidx[i] = b.idx[off + i];
+    }
+    if (__any_sync(kFull, bad)) { raise(p.err, LOCOHD_ERR_NAN); return; }  // partial_cmp().unwrap() panics (utils.rs:28)
+    if (!(scale > 0.0)) {   // rows mode: bucket scale from the largest finite distance
         for (int o = 16; o; o >>= 1) kmax = fmax(kmax, __shfl_xor_sync(kFull, kmax, o));
-        scale = (kmax > 0.0) ? ((double)NB * (1.0 - 1e-9)) / kmax : 0.0;
+        scale = (kmax > 0.0) ? (1.0 - 1e-9) / kmax : 0.0;
     }
-    for (int b = lane; b < NB; b += 32) bend[b] = 0;
+    for (int q = lane; q < NB; q += 32) bend[q] = 0;
     __syncwarp();
-    for (uint32_t e = lane; e < M; e += 32) {
-        const float f = (float)(key[e] * scale);        // monotone in the key; NaN only for inf * 0
-        int b = (int)fminf(f, (float)(NB - 1));         // fminf(NaN, x) = x: infinities land in the last bucket
-        b = max(b, 0);
-        bkt[e] = (uint16_t)b;
-        atomicAdd(&bend[b], 1u);
+    // ---- bucket = NB * (d * scale)^2: members of a spherical environment grow like d^2 per unit distance
+    for (uint32_t i = lane; i < M; i += 32) {
+        const float x = (float)(key[i] * scale);       // monotone in the key; NaN only for inf * 0
+        const float f = x * fabsf(x) * (float)NB;
+        int q = (int)fminf(f, (float)(NB - 1));        // fminf(NaN, y) = y: infinities land in the last bucket
+        q = max(q, 0);
+        bkt[i] = (uint16_t)q;
+        atomicAdd(&bend[q], 1u);
     }
     __syncwarp();
-    {   // exclusive prefix over the buckets, NB/32 consecutive buckets per lane; bend[b] := start of bucket b
+    {   // exclusive prefix over the buckets, NB/32 consecutive buckets per lane; bend[q] := start of bucket q
         constexpr int PER = NB / 32;
         uint32_t sum = 0;
 #pragma unroll 8
@@ -376,133 +554,86 @@ __device__ __forceinline__ void warp_bucket_sort(unsigned char* smem, uint32_t M
         }
     }
     __syncwarp();
-    for (uint32_t e = lane; e < M; e += 32) {   // scatter; afterwards bend[b] = end of bucket b
-        const uint32_t pos = atomicAdd(&bend[bkt[e]], 1u);
-        perm[pos] = (uint16_t)e;
+    for (uint32_t i = lane; i < M; i += 32) {   // scatter; afterwards bend[q] = end of bucket q
+        const uint32_t pos = atomicAdd(&bend[bkt[i]], 1u);
+        perm[pos] = (uint16_t)i;
     }
     __syncwarp();
-    // insertion sort inside every bucket (bucket b = [bend[b-1], bend[b])); lanes own interleaved buckets
-    for (int b = lane; b < NB; b += 32) {
-        const uint32_t s0 = b ? bend[b - 1] : 0u, s1 = bend[b];
+    // ---- insertion sort inside every bucket; order = (distance, category, slot)
+    for (int q = lane; q < NB; q += 32) {
+        const uint32_t s0 = q ? bend[q - 1] : 0u, s1 = bend[q];
         for (uint32_t t = s0 + 1; t < s1; ++t) {
-            const uint16_t e = perm[t];
-            const double k = key[e];
+            const uint16_t en = perm[t];
+            const double k = key[en];
+            const uint32_t c = scat[en];
             uint32_t u = t;
             while (u > s0) {
                 const uint16_t f = perm[u - 1];
                 const double kf = key[f];
-                if (kf < k || (kf == k && f < e)) break;
+                const uint32_t cf = scat[f];
+                if (kf < k || (kf == k && (cf < c || (cf == c && f < en)))) break;
                 perm[u] = f;
                 --u;
             }
-            perm[u] = e;
+            perm[u] = en;
         }
     }
     __syncwarp();
-}
-
-__device__ __forceinline__ double gather_sort_scale(double threshold, int nb) {
-    const double r2 = threshold * threshold;
-    return (isfinite(r2) && r2 > 0.0) ? ((double)nb * (1.0 - 1e-9)) / r2 : 0.0;  // keys are d^2 < r^2
-}
-
-// K1': gather + sort + store.  The store is allocated with one atomicAdd per environment on a global cursor.
-template <int CAP>
-__global__ void __launch_bounds__(kEnvWarps * 32) env_fill_kernel(StructsView s, KParams p,
-                                                                  const uint32_t* __restrict__ anchor_struct,
-                                                                  const uint32_t* __restrict__ anchor_prim,
-                                                                  double threshold, EnvOut out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    using L = WarpSortLayout<CAP>;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint64_t e = (uint64_t)blockIdx.x * kEnvWarps + wib;
-    if (e >= out.n_env) return;
-    unsigned char* smem = smem_raw + (size_t)wib * L::kBytes;
-    double* key = reinterpret_cast<double*>(smem + L::kKeyOff);
-    uint32_t* pay = reinterpret_cast<uint32_t*>(smem + L::kPayOff);
-    const uint16_t* perm = reinterpret_cast<const uint16_t*>(smem + L::kPermOff);
-
-    const AnchorRef a = resolve_anchor(s, anchor_struct, anchor_prim, e, p.err);
-    if (!a.ok) {
-        if (lane == 0) { out.count[e] = 0; out.off[e] = 0; }
-        return;
-    }
-    const uint32_t M = gather_environment(s, p, a, threshold, lane, [&](uint32_t slot, double d2, uint32_t j) {
-        if (slot < (uint32_t)CAP) { key[slot] = d2; pay[slot] = j; }
-    });
-    unsigned long long off = 0;
-    if (lane == 0) {
-        off = atomicAdd(&out.stats->cursor, (unsigned long long)M);
-        out.count[e] = M;
-        out.off[e] = off;
-        atomicMax(&out.stats->max_count, M);
-        if (M > (uint32_t)CAP) atomicAdd(&out.stats->n_big, 1u);
-        if (off + M > out.capacity) atomicOr(&out.stats->overflow, 1u);
-    }
-    off = __shfl_sync(kFull, off, 0);
-    if (M > (uint32_t)CAP || off + M > out.capacity) return;  // big path / retry with the exact capacity
-    __syncwarp();
-    warp_bucket_sort<CAP>(smem, M, lane, gather_sort_scale(threshold, L::NB));
-    const PrimRec* pd = s.pd + a.base;
+    if (b.check_first_zero && key[perm[0]] != 0.0) { raise(p.err, LOCOHD_ERR_FIRST_NOT_ZERO); return; }  // locohd.rs:74-77
+    // ---- write back in ascending order (coalesced): packed keys, plus plain distances / indices for parity dumps
     const WfDev& wf = p.wfs[0];
-    for (uint32_t pos = lane; pos < M; pos += 32) {   // ascending order, coalesced stores
-        const uint32_t en = perm[pos];
-        const double d = sqrt(key[en]);               // utils.rs:1-8
-        const PrimRec* r = pd + pay[en];
-        out.key[off + pos] = out.key_is_w ? wf_cdf(wf, d) : d;
-        out.cat[off + pos] = (uint8_t)r->cat;
-        if (out.dist) out.dist[off + pos] = d;
-        if (out.idx) out.idx[off + pos] = r->orig;
+    const bool fix_monotone = b.key_is_w && !wf.monotone;
+    uint64_t carry = 0;
+    for (uint32_t pos0 = 0; pos0 < M; pos0 += 32) {
+        const uint32_t pos = pos0 + lane;
+        uint64_t packed = 0;
+        if (pos < M) {
+            const uint32_t en = perm[pos];
+            const double d = key[en];
+            const double w = b.key_is_w ? ((d < 0.0) ? 0.0 : wf_cdf(wf, d)) : d;
+            packed = pack_key(w, scat[en]);
+            if (b.dist) b.dist[off + pos] = d;
+            if (DEBUG) b.idx[off + pos] = sidx[en];
+        }
+        if (fix_monotone) {
+            // pow/exp based CDFs are not guaranteed to be monotone to the last bit: keep the weights non-decreasing
+            uint64_t wbits = packed & ~kCatMask;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t v = __shfl_up_sync(kFull, wbits, o);
+                if (lane >= o) wbits = max(wbits, v);
+            }
+            wbits = max(wbits, carry);
+            carry = __shfl_sync(kFull, wbits, 31);
+            packed = wbits | (packed & kCatMask);
+        }
+        if (pos < M) gkey[pos] = packed;
     }
 }
 
-// Environments larger than the shared-memory class: written unsorted (plain distances as keys), then sorted in
-// place by bitonic_sort_big_kernel, which also converts the keys to W when the store holds W.
-__global__ void __launch_bounds__(kEnvWarps * 32) env_fill_unsorted_kernel(StructsView s, KParams p,
-                                                                           const uint32_t* __restrict__ anchor_struct,
-                                                                           const uint32_t* __restrict__ anchor_prim,
-                                                                           double threshold, EnvOut out,
-                                                                           uint32_t min_m) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t e = (uint64_t)blockIdx.x * kEnvWarps + (threadIdx.x >> 5);
-    if (e >= out.n_env) return;
-    const uint32_t expect = out.count[e];
-    if (expect <= min_m) return;
-    const AnchorRef a = resolve_anchor(s, anchor_struct, anchor_prim, e, p.err);
-    if (!a.ok) return;
-    const uint64_t off = out.off[e];
-    const PrimRec* pd = s.pd + a.base;
-    const uint32_t M = gather_environment(s, p, a, threshold, lane, [&](uint32_t slot, double d2, uint32_t j) {
-        if (slot < expect) {
-            out.key[off + slot] = sqrt(d2);
-            const PrimRec* r = pd + j;
-            out.cat[off + slot] = (uint8_t)r->cat;
-            if (out.idx) out.idx[off + slot] = r->orig;
-        }
-    });
-    if (M != expect) raise(p.err, LOCOHD_ERR_CUDA);
-}
-
-// In-place ascending bitonic network (min always to the lower index, so the virtual +inf padding above M
-// never moves).  One CTA per environment with more than min_m members.
+// In-place ascending bitonic network for environments that exceed every shared-memory class (min always to the
+// lower index, so the virtual +inf padding above M never moves).  One CTA per such environment.
 constexpr int kBigThreads = 256;
-__global__ void __launch_bounds__(kBigThreads) bitonic_sort_big_kernel(EnvOut out, KParams p, uint32_t min_m,
-                                                                       int check_first_zero) {
+__global__ void __launch_bounds__(kBigThreads) env_sort_big_kernel(KParams p, EnvBuild b, uint32_t min_m) {
+    __shared__ unsigned long long sh_carry;
     const uint64_t e = blockIdx.x;
-    const uint32_t M = out.count[e];
+    const uint32_t M = b.count[e];
     if (M <= min_m) return;
-    const uint64_t off = out.off[e];
-    double* d = out.key + off;
-    uint8_t* c = out.cat + off;
-    uint32_t* ix = out.idx ? out.idx + off : nullptr;
+    const uint64_t off = b.off[e];
+    double* d = reinterpret_cast<double*>(b.key + off);
+    uint8_t* c = b.cat + off;
+    uint32_t* ix = b.idx ? b.idx + off : nullptr;
+    bool bad = false;
+    for (uint32_t i = threadIdx.x; i < M; i += kBigThreads) bad |= isnan(d[i]);
+    if (__syncthreads_or(bad)) { if (threadIdx.x == 0) raise(p.err, LOCOHD_ERR_NAN); return; }
     uint32_t n2 = 1;
     while (n2 < M) n2 <<= 1;
     auto cex = [&](uint32_t i, uint32_t q) {
         if (q < M) {
             const double di = d[i], dq = d[q];
-            if (dq < di) {
+            const uint8_t ci = c[i], cq = c[q];
+            if (dq < di || (dq == di && cq < ci)) {
                 d[i] = dq; d[q] = di;
-                const uint8_t t = c[i]; c[i] = c[q]; c[q] = t;
+                c[i] = cq; c[q] = ci;
                 if (ix) { const uint32_t u = ix[i]; ix[i] = ix[q]; ix[q] = u; }
             }
         }
@@ -522,78 +653,59 @@ __global__ void __launch_bounds__(kBigThreads) bitonic_sort_big_kernel(EnvOut ou
             __syncthreads();
         }
     }
-    if (check_first_zero && threadIdx.x == 0 && d[0] != 0.0) raise(p.err, LOCOHD_ERR_FIRST_NOT_ZERO);
-    if (out.dist || out.key_is_w) {
-        const WfDev& wf = p.wfs[0];
-        for (uint32_t i = threadIdx.x; i < M; i += kBigThreads) {
+    if (b.check_first_zero && d[0] != 0.0) { if (threadIdx.x == 0) raise(p.err, LOCOHD_ERR_FIRST_NOT_ZERO); return; }
+    // ---- pack (sequential carry keeps non-monotone CDFs non-decreasing)
+    const WfDev& wf = p.wfs[0];
+    const bool fix_monotone = b.key_is_w && !wf.monotone;
+    if (threadIdx.x == 0) sh_carry = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < M; i0 += kBigThreads) {
+        const uint32_t i = i0 + threadIdx.x;
+        uint64_t packed = 0;
+        if (i < M) {
             const double v = d[i];
-            if (out.dist) out.dist[off + i] = v;
-            if (out.key_is_w) d[i] = (v < 0.0) ? 0.0 : wf_cdf(wf, v);
+            if (b.dist) b.dist[off + i] = v;
+            const double w = b.key_is_w ? ((v < 0.0) ? 0.0 : wf_cdf(wf, v)) : v;
+            packed = pack_key(w, c[i]);
         }
+        if (fix_monotone) {
+            __shared__ unsigned long long tile[kBigThreads];
+            tile[threadIdx.x] = packed & ~kCatMask;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long run = sh_carry;
+                for (int t = 0; t < kBigThreads; ++t) { run = max(run, tile[t]); tile[t] = run; }
+                sh_carry = run;
+            }
+            __syncthreads();
+            packed = tile[threadIdx.x] | (packed & kCatMask);
+            __syncthreads();
+        }
+        if (i < M) b.key[off + i] = packed;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Rows as environments (from_dmxs / from_coords): every row is sorted by distance.
+// Rows as environments (from_dmxs / from_coords): every row is copied unsorted into the store and then sorted by
+// the same kernels.  Distance of point i to point j exactly as utils.rs:1-22 (the diagonal is 0).
 // ------------------------------------------------------------------------------------------------
-__global__ void iota_rows_kernel(uint64_t* off, uint32_t* count, uint64_t n_rows, uint64_t row_len) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_rows) { off[i] = i * row_len; count[i] = (uint32_t)row_len; }
-}
-
-// distance of point i to point j exactly as utils.rs:1-22 (squares are symmetric, the diagonal is 0)
 __device__ __forceinline__ double row_distance(const double* xyz, uint64_t i, uint64_t j) {
     if (i == j) return 0.0;
     const double ex = xyz[3 * i] - xyz[3 * j], ey = xyz[3 * i + 1] - xyz[3 * j + 1], ez = xyz[3 * i + 2] - xyz[3 * j + 2];
     return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)));
 }
 
-template <int CAP>
-__global__ void __launch_bounds__(kEnvWarps * 32) rows_fill_kernel(const double* __restrict__ dmx,
-                                                                   const uint8_t* __restrict__ cat, uint64_t n_rows,
-                                                                   uint64_t row_len, const double* __restrict__ xyz,
-                                                                   KParams p, EnvOut out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    using L = WarpSortLayout<CAP>;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint64_t row = (uint64_t)blockIdx.x * kEnvWarps + wib;
-    if (row >= n_rows) return;
-    unsigned char* smem = smem_raw + (size_t)wib * L::kBytes;
-    double* key = reinterpret_cast<double*>(smem + L::kKeyOff);
-    const uint16_t* perm = reinterpret_cast<const uint16_t*>(smem + L::kPermOff);
-    const uint32_t M = (uint32_t)row_len;
-    bool bad = false;
-    for (uint32_t j = lane; j < M; j += 32) {
-        const double d = xyz ? row_distance(xyz, row, j) : dmx[row * row_len + j];
-        bad |= isnan(d);
-        key[j] = d;
-    }
-    if (__any_sync(kFull, bad)) { raise(p.err, LOCOHD_ERR_NAN); return; }  // partial_cmp().unwrap() panics (utils.rs:28)
-    __syncwarp();
-    warp_bucket_sort<CAP>(smem, M, lane, 0.0);
-    const uint64_t off = out.off[row];
-    if (key[perm[0]] != 0.0) { raise(p.err, LOCOHD_ERR_FIRST_NOT_ZERO); return; }  // locohd.rs:74-77
-    const WfDev& wf = p.wfs[0];
-    for (uint32_t pos = lane; pos < M; pos += 32) {
-        const uint32_t j = perm[pos];
-        const double d = key[j];
-        out.key[off + pos] = out.key_is_w ? wf_cdf(wf, d) : d;
-        out.cat[off + pos] = cat[j];
-        if (out.dist) out.dist[off + pos] = d;
-        if (out.idx) out.idx[off + pos] = j;
-    }
-}
-
 __global__ void rows_copy_kernel(const double* __restrict__ dmx, const uint8_t* __restrict__ cat, uint64_t n_rows,
-                                 uint64_t row_len, const double* __restrict__ xyz, KParams p, EnvOut out) {
+                                 uint64_t row_len, uint64_t row_stride, const double* __restrict__ xyz,
+                                 uint64_t* off, uint32_t* count, EnvBuild b) {
     for (uint64_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { off[row] = row * row_stride; count[row] = (uint32_t)row_len; }
         for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < row_len;
              j += (uint64_t)gridDim.x * blockDim.x) {
             const double d = xyz ? row_distance(xyz, row, j) : dmx[row * row_len + j];
-            if (isnan(d)) raise(p.err, LOCOHD_ERR_NAN);
-            out.key[row * row_len + j] = d;
-            out.cat[row * row_len + j] = cat[j];
-            if (out.idx) out.idx[row * row_len + j] = (uint32_t)j;
+            b.key[row * row_stride + j] = (uint64_t)__double_as_longlong(d);
+            b.cat[row * row_stride + j] = cat[j];
+            if (b.idx) b.idx[row * row_stride + j] = (uint32_t)j;
         }
     }
 }
@@ -602,10 +714,9 @@ __global__ void rows_copy_kernel(const double* __restrict__ dmx, const uint8_t* 
 // K2: scoring.  One warp per anchor pair (persistent warps stride over the pairs).
 // ------------------------------------------------------------------------------------------------
 constexpr int kScoreMaxWarps = 8;
-constexpr int kFastTable = 512;  // sqrt / rsqrt table entries staged in shared memory by the fast kernel
+constexpr uint64_t kWMask = ~kCatMask;
 
 __host__ __device__ inline int score_state_bytes(int C) { return ((2 * C * 32 * 8 + 2 * C * 32 * 4) + 15) & ~15; }
-__host__ __device__ inline int score_stage_bytes(int cap) { return ((cap * 9 + 16) + 15) & ~15; }
 __host__ __device__ inline int fast_state_bytes(int CP) { return 2 * CP * 32 * 8 + CP * 32 * 4; }
 
 struct PairEnvs {
@@ -647,18 +758,22 @@ __device__ __forceinline__ PairEnvs resolve_pair(const ScoreArgs& a, uint64_t pa
     return r;
 }
 
-// merge-path split: number of A events among the first `diag` merged events (A precedes B on ties)
-__device__ __forceinline__ uint32_t merge_path(const double* kA, const double* kB, uint32_t na, uint32_t nb,
+// merge-path split: number of A events among the first `diag` merged events (A precedes B on ties; the category
+// byte does not take part in the order)
+__device__ __forceinline__ uint32_t merge_path(const uint64_t* kA, const uint64_t* kB, uint32_t na, uint32_t nb,
                                                uint32_t diag) {
     uint32_t lo = diag > nb ? diag - nb : 0, hi = min(diag, na);
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (kA[mid] <= kB[diag - 1 - mid]) lo = mid + 1; else hi = mid;
+        if ((kA[mid] & kWMask) <= (kB[diag - 1 - mid] & kWMask)) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
 
-// Generic kernel: any C <= 255, any statistical distance, category weights, per-pair weight functions.
+__device__ __forceinline__ double key_value(uint64_t k) { return __longlong_as_double((long long)(k & kWMask)); }
+
+// Generic kernel: any C <= 255, any statistical distance, category weights, per-pair weight functions, environments
+// of any size (read from global memory when they do not fit the shared-memory stage).
 template <bool HELL2>
 __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a, KParams P, int warps_per_block,
                                                                     int per_warp_bytes) {
@@ -669,7 +784,7 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
     unsigned char* mine = smem_raw + (size_t)wib * per_warp_bytes;
     double* val = reinterpret_cast<double*>(mine);                         // [2C][32]
     uint32_t* cnt = reinterpret_cast<uint32_t*>(mine + 2 * C * 32 * 8);    // [2C][32]
-    unsigned char* stage = mine + score_state_bytes(C);
+    uint64_t* stage = reinterpret_cast<uint64_t*>(mine + score_state_bytes(C));
     const bool key_is_w = a.a.key_is_w != 0;
 
     for (uint64_t pair = (uint64_t)blockIdx.x * warps_per_block + wib; pair < a.n_pairs;
@@ -678,28 +793,21 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
         const PairEnvs pe = resolve_pair(a, pair, P.err);
         if (!pe.ok) continue;
         const uint32_t Ma = pe.Ma, Mb = pe.Mb;
-        const double* gkA = a.a.key + pe.oa;
-        const double* gkB = a.b.key + pe.ob;
-        const uint8_t* gcA = a.a.cat + pe.oa;
-        const uint8_t* gcB = a.b.cat + pe.ob;
-        if (!key_is_w && (gkA[0] != 0.0 || gkB[0] != 0.0)) { raise(P.err, LOCOHD_ERR_FIRST_NOT_ZERO); continue; }
-
-        // ---- stage both environments in shared memory when they fit
-        const double* kA = gkA;
-        const double* kB = gkB;
-        const uint8_t* cA = gcA;
-        const uint8_t* cB = gcB;
-        if ((int)(Ma + Mb) <= a.stage_cap) {
-            double* sd = reinterpret_cast<double*>(stage);
-            uint8_t* sc = stage + (size_t)(Ma + Mb) * 8;
-            for (uint32_t i = lane; i < Ma; i += 32) { sd[i] = gkA[i]; sc[i] = gcA[i]; }
-            for (uint32_t i = lane; i < Mb; i += 32) { sd[Ma + i] = gkB[i]; sc[Ma + i] = gcB[i]; }
-            kA = sd; kB = sd + Ma; cA = sc; cB = sc + Ma;
+        const uint32_t Ma_pad = (Ma + 1) & ~1u, Mb_pad = (Mb + 1) & ~1u;
+        if (a.only_unstaged && (int)(Ma_pad + Mb_pad) <= a.only_unstaged) continue;  // the fast kernel scored it
+        const uint64_t* kA = a.a.key + pe.oa;
+        const uint64_t* kB = a.b.key + pe.ob;
+        if ((int)(Ma_pad + Mb_pad) <= a.stage_cap) {
+            for (uint32_t i = lane; i < Ma; i += 32) stage[i] = kA[i];
+            for (uint32_t i = lane; i < Mb; i += 32) stage[Ma_pad + i] = kB[i];
+            kA = stage; kB = stage + Ma_pad;
             __syncwarp();
         }
-        const uint32_t catA0 = cA[0], catB0 = cB[0];
-        const double key0 = fmax(kA[0], kB[0]);   // key of the anchors (W(0) or 0)
-        kA += 1; kB += 1; cA += 1; cB += 1;       // events = members after the anchor
+        const uint64_t keyA0 = kA[0], keyB0 = kB[0];
+        if (!key_is_w && ((keyA0 & kWMask) != 0 || (keyB0 & kWMask) != 0)) { raise(P.err, LOCOHD_ERR_FIRST_NOT_ZERO); continue; }
+        const uint32_t catA0 = (uint32_t)(keyA0 & kCatMask), catB0 = (uint32_t)(keyB0 & kCatMask);
+        const uint64_t key0 = max(keyA0 & kWMask, keyB0 & kWMask);   // anchors: W(0) or distance 0
+        kA += 1; kB += 1;                                            // events = members after the anchor
         const uint32_t na = Ma - 1, nb = Mb - 1;
         const uint32_t E = na + nb;
         const uint32_t Q = (E + 31) / 32;
@@ -714,11 +822,11 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
         for (int r = 0; r < 2 * C; ++r) cnt[r * 32 + lane] = 0;
         bool unknown = (catA0 >= (uint32_t)C) || (catB0 >= (uint32_t)C);
         for (uint32_t x = i; x < i1; ++x) {
-            const uint32_t c = cA[x];
+            const uint32_t c = (uint32_t)(kA[x] & kCatMask);
             if (c < (uint32_t)C) cnt[c * 32 + lane] += 1; else unknown = true;
         }
         for (uint32_t x = j; x < j1; ++x) {
-            const uint32_t c = cB[x];
+            const uint32_t c = (uint32_t)(kB[x] & kCatMask);
             if (c < (uint32_t)C) cnt[(C + c) * 32 + lane] += 1; else unknown = true;
         }
         if (__any_sync(kFull, unknown)) { raise(P.err, LOCOHD_ERR_UNKNOWN_CATEGORY); continue; }  // pmf.rs:38-42
@@ -777,21 +885,21 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
         };
 
         const WfDev& wf = P.wfs[a.wf_idx ? a.wf_idx[pair] : 0];
-        auto weight = [&](double k) -> double { return key_is_w ? k : wf_cdf(wf, k); };
-        double kprev = key0;
-        if (i > 0) kprev = kA[i - 1];
-        if (j > 0) kprev = fmax(kprev, kB[j - 1]);
+        auto weight = [&](uint64_t k) -> double { return key_is_w ? key_value(k) : wf_cdf(wf, key_value(k)); };
+        uint64_t kprev = key0;
+        if (i > 0) kprev = kA[i - 1] & kWMask;
+        if (j > 0) kprev = max(kprev, kB[j - 1] & kWMask);
         double wprev = weight(kprev);
         double h = stat_dist();
         double acc = 0.0;
 
         // ---- walk my chunk
-        double ta = (i < i1) ? kA[i] : 0.0, tb = (j < j1) ? kB[j] : 0.0;
+        uint64_t ra = (i < i1) ? kA[i] : 0, rb = (j < j1) ? kB[j] : 0;
         while (i < i1 || j < j1) {
-            const bool takeA = (i < i1) && (!(j < j1) || ta <= tb);
-            const double t = takeA ? ta : tb;
-            const uint32_t c = takeA ? cA[i] : cB[j];
-            const double w = weight(t);
+            const bool takeA = (i < i1) && (!(j < j1) || (ra & kWMask) <= (rb & kWMask));
+            const uint64_t raw = takeA ? ra : rb;
+            const uint32_t c = (uint32_t)(raw & kCatMask);
+            const double w = weight(raw);
             acc = fma(w - wprev, h, acc);
             wprev = w;
             const int row = (takeA ? 0 : C) + (int)c;
@@ -807,12 +915,12 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
                 normA += wc; totA += 1;
                 if (HELL2) rA = inv_sqrt_norm(normA, totA);
                 ++i;
-                if (i < i1) ta = kA[i];
+                if (i < i1) ra = kA[i];
             } else {
                 normB += wc; totB += 1;
                 if (HELL2) rB = inv_sqrt_norm(normB, totB);
                 ++j;
-                if (j < j1) tb = kB[j];
+                if (j < j1) rb = kB[j];
             }
             h = stat_dist();
         }
@@ -823,30 +931,38 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
     }
 }
 
-// Fast kernel: Hellinger-2, unit category weights, C <= CP (8 or 16).  Per-lane state lives in shared memory as
-// double2 pairs read with LDS.128 at compile-time offsets, the (A, B) counts of a category share one 32-bit word,
-// sqrt / rsqrt tables sit in shared memory, and with KEY_IS_W the environments already hold W(distance).
-template <int CP, bool KEY_IS_W>
+// Fast kernel: Hellinger-2, unit category weights, C <= CP (8 or 16), both environments staged in shared memory.
+// Per-lane state lives in shared memory as double2 pairs read with LDS.128 at compile-time offsets, the (A, B)
+// counts of a category share one 32-bit word, sqrt / rsqrt tables sit in shared memory, and with KEY_IS_W the
+// environments already hold W(distance).  Pairs that do not fit the stage are left to score_kernel.
+template <int CP, bool KEY_IS_W, bool CHECK>
 __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreArgs a, KParams P, int warps_per_block,
                                                                          int per_warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int table_n = a.table_n;
     double* s_sqrt = reinterpret_cast<double*>(smem_raw);
-    double* s_rsqrt = s_sqrt + kFastTable;
-    for (int k = threadIdx.x; k < kFastTable; k += blockDim.x) {
+    double* s_rsqrt = s_sqrt + table_n;
+    for (int k = threadIdx.x; k < table_n; k += blockDim.x) {
         s_sqrt[k] = P.sqrt_tbl[k];
         s_rsqrt[k] = P.rsqrt_tbl[k];
     }
     __syncthreads();
     if (wib >= warps_per_block) return;
     const int C = P.C;
-    unsigned char* mine = smem_raw + 2 * kFastTable * 8 + (size_t)wib * per_warp_bytes;
+    unsigned char* mine = smem_raw + (size_t)2 * table_n * 8 + (size_t)wib * per_warp_bytes;
     double2* val2 = reinterpret_cast<double2*>(mine);                        // [2][CP/2][32]
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(mine + 2 * CP * 32 * 8);     // [CP][32]: A count | B count << 16
-    unsigned char* stage = mine + fast_state_bytes(CP);
     double* valf = reinterpret_cast<double*>(mine);
-    auto sqrt_of = [&](uint32_t k) -> double { return k < (uint32_t)kFastTable ? s_sqrt[k] : sqrt((double)k); };
-    auto rsqrt_of = [&](uint32_t k) -> double { return k < (uint32_t)kFastTable ? s_rsqrt[k] : 1.0 / sqrt((double)k); };
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(mine + 2 * CP * 32 * 8);     // [CP][32]: A count | B count << 16
+    uint64_t* stage = reinterpret_cast<uint64_t*>(mine + fast_state_bytes(CP));
+    auto sqrt_of = [&](uint32_t k) -> double {
+        if (CHECK && k >= (uint32_t)table_n) return sqrt((double)k);
+        return s_sqrt[k];
+    };
+    auto rsqrt_of = [&](uint32_t k) -> double {
+        if (CHECK && k >= (uint32_t)table_n) return 1.0 / sqrt((double)k);
+        return s_rsqrt[k];
+    };
 
     for (uint64_t pair = (uint64_t)blockIdx.x * warps_per_block + wib; pair < a.n_pairs;
          pair += (uint64_t)gridDim.x * warps_per_block) {
@@ -854,27 +970,24 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
         const PairEnvs pe = resolve_pair(a, pair, P.err);
         if (!pe.ok) continue;
         const uint32_t Ma = pe.Ma, Mb = pe.Mb;
-        const double* gkA = a.a.key + pe.oa;
-        const double* gkB = a.b.key + pe.ob;
-        const uint8_t* gcA = a.a.cat + pe.oa;
-        const uint8_t* gcB = a.b.cat + pe.ob;
-        if (!KEY_IS_W && (gkA[0] != 0.0 || gkB[0] != 0.0)) { raise(P.err, LOCOHD_ERR_FIRST_NOT_ZERO); continue; }
-
-        const double* kA = gkA;
-        const double* kB = gkB;
-        const uint8_t* cA = gcA;
-        const uint8_t* cB = gcB;
-        if ((int)(Ma + Mb) <= a.stage_cap) {
-            double* sd = reinterpret_cast<double*>(stage);
-            uint8_t* sc = stage + (size_t)(Ma + Mb) * 8;
-            for (uint32_t i = lane; i < Ma; i += 32) { sd[i] = gkA[i]; sc[i] = gcA[i]; }
-            for (uint32_t i = lane; i < Mb; i += 32) { sd[Ma + i] = gkB[i]; sc[Ma + i] = gcB[i]; }
-            kA = sd; kB = sd + Ma; cA = sc; cB = sc + Ma;
-            __syncwarp();
+        const uint32_t Ma_pad = (Ma + 1) & ~1u, Mb_pad = (Mb + 1) & ~1u;
+        if ((int)(Ma_pad + Mb_pad) > a.stage_cap) continue;   // left to the generic kernel (second pass)
+        {   // environments start at even offsets: 16-byte loads
+            const ulonglong2* gA = reinterpret_cast<const ulonglong2*>(a.a.key + pe.oa);
+            const ulonglong2* gB = reinterpret_cast<const ulonglong2*>(a.b.key + pe.ob);
+            ulonglong2* sA = reinterpret_cast<ulonglong2*>(stage);
+            ulonglong2* sB = reinterpret_cast<ulonglong2*>(stage + Ma_pad);
+            for (uint32_t i = lane; i < Ma_pad / 2; i += 32) sA[i] = gA[i];
+            for (uint32_t i = lane; i < Mb_pad / 2; i += 32) sB[i] = gB[i];
         }
-        const uint32_t catA0 = cA[0], catB0 = cB[0];
-        const double key0 = fmax(kA[0], kB[0]);
-        kA += 1; kB += 1; cA += 1; cB += 1;
+        __syncwarp();
+        const uint64_t* kA = stage;
+        const uint64_t* kB = stage + Ma_pad;
+        const uint64_t keyA0 = kA[0], keyB0 = kB[0];
+        if (!KEY_IS_W && ((keyA0 & kWMask) != 0 || (keyB0 & kWMask) != 0)) { raise(P.err, LOCOHD_ERR_FIRST_NOT_ZERO); continue; }
+        const uint32_t catA0 = (uint32_t)(keyA0 & kCatMask), catB0 = (uint32_t)(keyB0 & kCatMask);
+        const uint64_t key0 = max(keyA0 & kWMask, keyB0 & kWMask);
+        kA += 1; kB += 1;
         const uint32_t na = Ma - 1, nb = Mb - 1;
         const uint32_t E = na + nb;
         const uint32_t Q = (E + 31) / 32;
@@ -888,11 +1001,11 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
         for (int r = 0; r < CP; ++r) cnt[r * 32 + lane] = 0;
         bool unknown = (catA0 >= (uint32_t)C) || (catB0 >= (uint32_t)C);
         for (uint32_t x = i; x < i1; ++x) {
-            const uint32_t c = cA[x];
+            const uint32_t c = reinterpret_cast<const uint8_t*>(kA + x)[0];
             if (c < (uint32_t)C) cnt[c * 32 + lane] += 1u; else unknown = true;
         }
         for (uint32_t x = j; x < j1; ++x) {
-            const uint32_t c = cB[x];
+            const uint32_t c = reinterpret_cast<const uint8_t*>(kB + x)[0];
             if (c < (uint32_t)C) cnt[c * 32 + lane] += 0x10000u; else unknown = true;
         }
         if (__any_sync(kFull, unknown)) { raise(P.err, LOCOHD_ERR_UNKNOWN_CATEGORY); continue; }  // pmf.rs:38-42
@@ -918,6 +1031,7 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
         double rA = rsqrt_of(totA), rB = rsqrt_of(totB);
 
         auto stat_dist = [&]() -> double {
+            // difference form of the Hellinger distance; products rounded before the subtraction (see score_kernel)
             double acc = 0.0;
 #pragma unroll
             for (int q = 0; q < CP / 2; ++q) {
@@ -931,19 +1045,20 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
         };
 
         const WfDev& wf = P.wfs[(!KEY_IS_W && a.wf_idx) ? a.wf_idx[pair] : 0];
-        auto weight = [&](double k) -> double { return KEY_IS_W ? k : wf_cdf(wf, k); };
-        double kprev = key0;
-        if (i > 0) kprev = kA[i - 1];
-        if (j > 0) kprev = fmax(kprev, kB[j - 1]);
+        auto weight = [&](uint64_t k) -> double { return KEY_IS_W ? key_value(k) : wf_cdf(wf, key_value(k)); };
+        uint64_t kprev = key0;
+        if (i > 0) kprev = kA[i - 1] & kWMask;
+        if (j > 0) kprev = max(kprev, kB[j - 1] & kWMask);
         double wprev = weight(kprev);
         double h = stat_dist();
         double acc = 0.0;
 
-        double ta = (i < i1) ? kA[i] : 0.0, tb = (j < j1) ? kB[j] : 0.0;
+        uint64_t ra = (i < i1) ? kA[i] : 0, rb = (j < j1) ? kB[j] : 0;
         while (i < i1 || j < j1) {
-            const bool takeA = (i < i1) && (!(j < j1) || ta <= tb);
-            const double w = weight(takeA ? ta : tb);
-            const uint32_t c = takeA ? cA[i] : cB[j];
+            const bool takeA = (i < i1) && (!(j < j1) || (ra & kWMask) <= (rb & kWMask));
+            const uint64_t raw = takeA ? ra : rb;
+            const uint32_t c = (uint32_t)(raw & kCatMask);
+            const double w = weight(raw);
             acc = fma(w - wprev, h, acc);
             wprev = w;
             const uint32_t word = cnt[c * 32 + lane] + (takeA ? 1u : 0x10000u);
@@ -953,11 +1068,11 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
             if (takeA) {
                 ++totA; rA = rsqrt_of(totA);
                 ++i;
-                if (i < i1) ta = kA[i];
+                if (i < i1) ra = kA[i];
             } else {
                 ++totB; rB = rsqrt_of(totB);
                 ++j;
-                if (j < j1) tb = kB[j];
+                if (j < j1) rb = kB[j];
             }
             h = stat_dist();
         }
@@ -1123,76 +1238,87 @@ int launch_build_cells(const StructsView& s, double threshold, cudaStream_t st) 
     return 1;
 }
 
-int launch_env_count_sample(const StructsView& s, const KParams& p, uint64_t n_sample, uint64_t stride,
-                            const uint32_t* anchor_struct, const uint32_t* anchor_prim, double threshold,
-                            uint32_t* count, cudaStream_t st) {
-    if (!n_sample) return 0;
-    env_count_sample_kernel<<<blocks_for(n_sample, kEnvWarps), kEnvWarps * 32, 0, st>>>(s, p, n_sample, stride,
-                                                                                        anchor_struct, anchor_prim,
-                                                                                        threshold, count);
+uint64_t scan_scratch_entries(uint64_t n) { return (n + kScanTile - 1) / kScanTile + 1; }
+
+int launch_scan(const uint32_t* values, uint64_t n, int round_even, uint64_t* off, uint64_t* scratch, ScanStats* stats,
+                cudaStream_t st) {
+    cudaMemsetAsync(stats, 0, sizeof(ScanStats), st);
+    if (!n) { cudaMemsetAsync(off, 0, sizeof(uint64_t), st); return 0; }
+    const unsigned nb = blocks_for(n, kScanTile);
+    scan_tile_sums_kernel<<<nb, kScanThreads, 0, st>>>(values, n, round_even, scratch, stats);
+    scan_block_sums_kernel<<<1, kScanThreads, 0, st>>>(scratch, nb, stats);
+    scan_apply_kernel<<<nb, kScanThreads, 0, st>>>(values, n, round_even, scratch, off);
+    return 3;
+}
+
+int launch_anchor_order(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* anchor_struct,
+                        const uint32_t* anchor_prim, uint64_t n_prims, uint32_t* slot_cnt, uint64_t* slot_off,
+                        uint64_t* scan_scratch, ScanStats* stats, uint32_t* order, cudaStream_t st) {
+    if (!n_env) return 0;
+    cudaMemsetAsync(slot_cnt, 0, (n_prims + 1) * sizeof(uint32_t), st);
+    anchor_slot_count_kernel<<<blocks_for(n_env, 256), 256, 0, st>>>(s, p, n_env, anchor_struct, anchor_prim, slot_cnt);
+    int n = 1 + launch_scan(slot_cnt, n_prims + 1, 0, slot_off, scan_scratch, stats, st);
+    anchor_slot_scatter_kernel<<<blocks_for(n_env, 256), 256, 0, st>>>(s, p, n_env, anchor_struct, anchor_prim,
+                                                                      slot_cnt, slot_off, order);
+    return n + 1;
+}
+
+int launch_env_count(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* order,
+                     const uint32_t* anchor_struct, const uint32_t* anchor_prim, double threshold, uint32_t* ub,
+                     cudaStream_t st) {
+    if (!n_env) return 0;
+    EnvBuild none{};
+    env_tile_kernel<false><<<blocks_for(n_env, kTileThreads), kTileThreads, 0, st>>>(s, p, n_env, order, anchor_struct,
+                                                                                    anchor_prim, threshold, ub, none);
     return 1;
 }
 
-template <int CAP>
-static int launch_env_fill_class(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
-                                 const uint32_t* anchor_prim, double threshold, const EnvOut& out, cudaStream_t st) {
-    const int smem = WarpSortLayout<CAP>::kBytes * kEnvWarps;
-    cudaFuncSetAttribute(env_fill_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    env_fill_kernel<CAP><<<blocks_for(out.n_env, kEnvWarps), kEnvWarps * 32, smem, st>>>(s, p, anchor_struct,
-                                                                                        anchor_prim, threshold, out);
+int launch_env_fill(const StructsView& s, const KParams& p, const uint32_t* anchor_struct, const uint32_t* anchor_prim,
+                    double threshold, const EnvBuild& b, cudaStream_t st) {
+    if (!b.n_env) return 0;
+    env_tile_kernel<true><<<blocks_for(b.n_env, kTileThreads), kTileThreads, 0, st>>>(
+        s, p, b.n_env, b.order, anchor_struct, anchor_prim, threshold, nullptr, b);
     return 1;
 }
 
-int launch_env_fill(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
-                    const uint32_t* anchor_prim, double threshold, const EnvOut& out, int cap_class, cudaStream_t st) {
-    cudaMemsetAsync(out.stats, 0, sizeof(FillStats), st);
-    if (!out.n_env) return 0;
-    switch (cap_class) {
-        case 256: return launch_env_fill_class<256>(s, p, anchor_struct, anchor_prim, threshold, out, st);
-        case 512: return launch_env_fill_class<512>(s, p, anchor_struct, anchor_prim, threshold, out, st);
-        case 1024: return launch_env_fill_class<1024>(s, p, anchor_struct, anchor_prim, threshold, out, st);
-        default: return launch_env_fill_class<2048>(s, p, anchor_struct, anchor_prim, threshold, out, st);
+template <int CAP, bool DEBUG>
+static int launch_sort_class(const KParams& p, const EnvBuild& b, uint32_t min_m, double scale, cudaStream_t st) {
+    const int smem = SortLayout<CAP, DEBUG>::kBytes * kSortWarps;
+    cudaFuncSetAttribute(env_sort_kernel<CAP, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    env_sort_kernel<CAP, DEBUG><<<blocks_for(b.n_env, kSortWarps), kSortWarps * 32, smem, st>>>(p, b, min_m, scale);
+    return 1;
+}
+
+template <bool DEBUG>
+static int launch_env_sort_t(const KParams& p, const EnvBuild& b, unsigned max_count, double scale, cudaStream_t st) {
+    int n = 0;
+    n += launch_sort_class<256, DEBUG>(p, b, 0, scale, st);
+    if (max_count > 256) n += launch_sort_class<512, DEBUG>(p, b, 256, scale, st);
+    if (max_count > 512) n += launch_sort_class<1024, DEBUG>(p, b, 512, scale, st);
+    if (max_count > 1024) n += launch_sort_class<2048, DEBUG>(p, b, 1024, scale, st);
+    if (max_count > 2048) {
+        env_sort_big_kernel<<<(unsigned)b.n_env, kBigThreads, 0, st>>>(p, b, 2048);
+        ++n;
     }
+    return n;
 }
 
-int launch_env_fill_big(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
-                        const uint32_t* anchor_prim, double threshold, const EnvOut& out, int cap_class,
-                        cudaStream_t st) {
-    if (!out.n_env) return 0;
-    env_fill_unsorted_kernel<<<blocks_for(out.n_env, kEnvWarps), kEnvWarps * 32, 0, st>>>(
-        s, p, anchor_struct, anchor_prim, threshold, out, (uint32_t)cap_class);
-    bitonic_sort_big_kernel<<<(unsigned)out.n_env, kBigThreads, 0, st>>>(out, p, (uint32_t)cap_class, 0);
-    return 2;
+int launch_env_sort(const KParams& p, const EnvBuild& b, unsigned max_count, double threshold, cudaStream_t st) {
+    if (!b.n_env) return 0;
+    // gather mode: distances are below the threshold; rows mode (threshold <= 0): scale from the data
+    const double scale = (threshold > 0.0 && std::isfinite(threshold)) ? (1.0 - 1e-9) / threshold : 0.0;
+    return b.idx ? launch_env_sort_t<true>(p, b, max_count, scale, st) : launch_env_sort_t<false>(p, b, max_count, scale, st);
 }
 
-int launch_fill_u64_iota_rows(uint64_t* off, uint32_t* count, uint64_t n_rows, uint64_t row_len, cudaStream_t st) {
-    if (!n_rows) return 0;
-    iota_rows_kernel<<<blocks_for(n_rows, 256), 256, 0, st>>>(off, count, n_rows, row_len);
-    return 1;
-}
-
-template <int CAP>
-static int launch_rows_class(const double* dmx, const uint8_t* cat, uint64_t n_rows, uint64_t row_len,
-                             const double* xyz, const KParams& p, const EnvOut& out, cudaStream_t st) {
-    const int smem = WarpSortLayout<CAP>::kBytes * kEnvWarps;
-    cudaFuncSetAttribute(rows_fill_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    rows_fill_kernel<CAP><<<blocks_for(n_rows, kEnvWarps), kEnvWarps * 32, smem, st>>>(dmx, cat, n_rows, row_len, xyz,
-                                                                                      p, out);
-    return 1;
-}
-
-int launch_rows_fill(const double* dmx, const uint8_t* cat, uint64_t n_rows, uint64_t row_len, const double* xyz,
-                     const KParams& p, const EnvOut& out, cudaStream_t st) {
+int launch_rows_copy(const double* dmx, const uint8_t* cat, uint64_t n_rows, uint64_t row_len, const double* xyz,
+                     const KParams& p, uint64_t* off, uint32_t* count, const EnvBuild& b, cudaStream_t st) {
+    (void)p;
     if (!n_rows || !row_len) return 0;
-    if (row_len <= 256) return launch_rows_class<256>(dmx, cat, n_rows, row_len, xyz, p, out, st);
-    if (row_len <= 512) return launch_rows_class<512>(dmx, cat, n_rows, row_len, xyz, p, out, st);
-    if (row_len <= 1024) return launch_rows_class<1024>(dmx, cat, n_rows, row_len, xyz, p, out, st);
-    if (row_len <= 2048) return launch_rows_class<2048>(dmx, cat, n_rows, row_len, xyz, p, out, st);
+    const uint64_t row_stride = (row_len + 1) & ~1ull;
     dim3 grid((unsigned)((row_len + 255) / 256), (unsigned)(n_rows > 32768 ? 32768 : n_rows));
     if (grid.x > 64) grid.x = 64;
-    rows_copy_kernel<<<grid, 256, 0, st>>>(dmx, cat, n_rows, row_len, xyz, p, out);
-    bitonic_sort_big_kernel<<<(unsigned)n_rows, kBigThreads, 0, st>>>(out, p, 0, 1);
-    return 2;
+    rows_copy_kernel<<<grid, 256, 0, st>>>(dmx, cat, n_rows, row_len, row_stride, xyz, off, count, b);
+    return 1;
 }
 
 template <class K>
@@ -1216,42 +1342,77 @@ static int launch_score_kernel(K kernel, const ScoreArgs& a, const KParams& p, i
     return 1;
 }
 
-int launch_score(const ScoreArgs& args, const KParams& p, unsigned stage_members, unsigned unused, cudaStream_t st) {
-    (void)unused;
-    if (!args.n_pairs) return 0;
+static int launch_generic(const ScoreArgs& args, const KParams& p, unsigned stage_want, int only_unstaged,
+                          cudaStream_t st) {
     ScoreArgs a = args;
-    const int budget = 100 * 1024;  // per CTA: two CTAs per SM
-    const bool key_is_w = args.a.key_is_w != 0;
-    const bool fast = p.hell2 && p.unit_w && p.C <= 16;
-    int cap = (int)(stage_members > 4096u ? 4096u : stage_members);
-    if (fast) {
-        const int CP = p.C <= 8 ? 8 : 16;
-        const int tables = 2 * kFastTable * 8;
-        int per_warp = fast_state_bytes(CP) + score_stage_bytes(cap);
-        if (tables + per_warp > 200 * 1024) { cap = 0; per_warp = fast_state_bytes(CP) + score_stage_bytes(0); }
-        int warps = (budget - tables) / per_warp;
-        if (warps > kScoreMaxWarps) warps = kScoreMaxWarps;
-        if (warps < 1) warps = 1;
-        a.stage_cap = cap;
-        const int smem = tables + per_warp * warps;
-        if (CP == 8) {
-            return key_is_w ? launch_score_kernel(score_fast_kernel<8, true>, a, p, warps, per_warp, smem, st)
-                            : launch_score_kernel(score_fast_kernel<8, false>, a, p, warps, per_warp, smem, st);
-        }
-        return key_is_w ? launch_score_kernel(score_fast_kernel<16, true>, a, p, warps, per_warp, smem, st)
-                        : launch_score_kernel(score_fast_kernel<16, false>, a, p, warps, per_warp, smem, st);
-    }
+    const int budget = 100 * 1024;
     const int state = score_state_bytes(p.C);
-    int per_warp = state + score_stage_bytes(cap);
-    if (per_warp > 200 * 1024) { cap = 0; per_warp = state + score_stage_bytes(0); }
+    int cap = (int)(stage_want > 2048u ? 2048u : stage_want);
+    int per_warp = state + cap * 8;
+    if (per_warp > budget) { cap = 0; per_warp = state; }
     if (per_warp > 220 * 1024) return -1;
     int warps = budget / per_warp;
     if (warps > kScoreMaxWarps) warps = kScoreMaxWarps;
     if (warps < 1) warps = 1;
     a.stage_cap = cap;
+    a.only_unstaged = only_unstaged;
     const int smem = per_warp * warps;
     return p.hell2 ? launch_score_kernel(score_kernel<true>, a, p, warps, per_warp, smem, st)
                    : launch_score_kernel(score_kernel<false>, a, p, warps, per_warp, smem, st);
+}
+
+template <int CP, bool KEY_IS_W>
+static int launch_fast(const ScoreArgs& a, const KParams& p, bool check, int warps, int per_warp, int smem,
+                       cudaStream_t st) {
+    return check ? launch_score_kernel(score_fast_kernel<CP, KEY_IS_W, true>, a, p, warps, per_warp, smem, st)
+                 : launch_score_kernel(score_fast_kernel<CP, KEY_IS_W, false>, a, p, warps, per_warp, smem, st);
+}
+
+int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsigned max_b, double mean_a, double mean_b,
+                 cudaStream_t st) {
+    if (!args.n_pairs) return 0;
+    const unsigned pad_max = ((max_a + 1) & ~1u) + ((max_b + 1) & ~1u);
+    const bool key_is_w = args.a.key_is_w != 0;
+    const bool fast = p.hell2 && p.unit_w && p.C <= 16;
+    if (!fast) return launch_generic(args, p, pad_max, 0, st);
+
+    ScoreArgs a = args;
+    const int CP = p.C <= 8 ? 8 : 16;
+    // stage: everything when the largest pair is small, else what a typical pair needs (the rest goes to the
+    // generic kernel in a second pass)
+    unsigned stage = pad_max;
+    if (stage > 1024u) {
+        stage = (unsigned)(1.5 * (mean_a + mean_b)) + 64u;
+        stage = (stage + 63u) & ~63u;
+        if (stage > 2048u) stage = 2048u;
+        if (stage > pad_max) stage = pad_max;
+    }
+    // tables: counts never exceed the environment sizes
+    unsigned need = (max_a > max_b ? max_a : max_b) + 2u;
+    bool check = false;
+    unsigned table_n = (need + 63u) & ~63u;
+    if (table_n > 1024u) { table_n = 1024u; check = true; }
+    a.table_n = (int)table_n;
+    a.stage_cap = (int)stage;
+    a.only_unstaged = 0;
+    const int tables = 2 * (int)table_n * 8;
+    const int per_warp = fast_state_bytes(CP) + (int)stage * 8;
+    const int budget = 100 * 1024;  // two CTAs per SM
+    int warps = (budget - tables) / per_warp;
+    if (warps > kScoreMaxWarps) warps = kScoreMaxWarps;
+    if (warps < 1) warps = 1;
+    const int smem = tables + per_warp * warps;
+    int n = 0;
+    if (CP == 8) n += key_is_w ? launch_fast<8, true>(a, p, check, warps, per_warp, smem, st)
+                               : launch_fast<8, false>(a, p, check, warps, per_warp, smem, st);
+    else n += key_is_w ? launch_fast<16, true>(a, p, check, warps, per_warp, smem, st)
+                       : launch_fast<16, false>(a, p, check, warps, per_warp, smem, st);
+    if (pad_max > stage) {
+        const int m = launch_generic(args, p, 0, (int)stage, st);
+        if (m < 0) return m;
+        n += m;
+    }
+    return n;
 }
 
 int launch_job_means(const double* scores, const uint64_t* job_pair_off, uint64_t n_jobs, double* means,

@@ -7,11 +7,9 @@
 
 namespace locohd {
 
-constexpr int kMaxCellsAxis = 16;
-constexpr int kMaxCells = kMaxCellsAxis * kMaxCellsAxis * kMaxCellsAxis;  // per structure
-constexpr int kCellStride = kMaxCells + 1;                                 // cell_start entries per structure
 constexpr uint8_t kUnknownCat8 = 0xFF;
 constexpr int kSqrtTableSize = 4096;
+constexpr uint64_t kCatMask = 0xFFull;  // low byte of a packed key = category
 
 // One primitive in cell-sorted order: exact coordinates for the FP64 membership test and distance.
 struct __align__(32) PrimRec {
@@ -23,9 +21,11 @@ struct __align__(32) PrimRec {
 // Per-structure cell grid (built for one threshold).
 struct __align__(16) StructMeta {
     double ox, oy, oz;   // grid origin = bounding-box minimum
-    double inv_cell;     // 1 / cell edge (cell edge >= threshold * (1 + 1e-6))
+    double inv_cell;     // 1 / cell edge (cell edge >= threshold / 2 * (1 + 1e-6))
     int nx, ny, nz;
+    int reach;           // neighbour cells to visit on each side (2 for the default half-radius cells)
     float thr2f;         // conservative squared radius for the FP32 prefilter
+    int pad[3];
 };
 
 // Kernel-visible parameter block of one LoCoHD instance (LoCoHD struct, locohd.rs:42-55).
@@ -47,6 +47,10 @@ struct KParams {
     int* err;                   // device error word (first locohd_status raised by a kernel)
 };
 
+// cells of structure s live at cell_start[cell_base(s) ...]: at most max(2 N_s, 8) cells + 1 end marker
+__host__ __device__ inline uint64_t cell_base(uint64_t prim_off_s, uint64_t s) { return 2 * prim_off_s + 9 * s; }
+__host__ __device__ inline uint64_t cell_entries(uint64_t n_prims, uint64_t n_structs) { return 2 * n_prims + 9 * n_structs; }
+
 struct StructsView {
     uint64_t n_structs;
     const uint64_t* prim_off;     // [n_structs + 1]
@@ -57,37 +61,38 @@ struct StructsView {
     float4* pf;                   // cell-sorted: (x - ox, y - oy, z - oz) as f32, w = tag bits
     PrimRec* pd;                  // cell-sorted exact records
     uint32_t* sorted_pos;         // original index -> cell-sorted position (inside the structure)
-    uint32_t* cell_start;         // [n_structs][kCellStride]
+    uint32_t* cell_start;         // [cell_entries]: first cell-sorted position of every cell
+    uint32_t* cell_fill;          // [cell_entries]: scratch cursor of the counting sort
 };
 
+// Sorted environments.  Member k of environment e is key[off[e] + k], k < count[e]; a key is the f64 bit pattern of
+// W(distance) (key_is_w) or of the distance with the low mantissa byte replaced by the member's category.
 struct EnvView {
     uint64_t n_env;
-    const uint64_t* off;    // [n_env] first member of every environment (any order, no overlap)
-    const uint32_t* count;  // [n_env] members per environment
-    const double* key;      // ascending per environment: W(distance) when key_is_w, else the distance
-    const uint8_t* cat;
+    const uint64_t* off;
+    const uint32_t* count;
+    const uint64_t* key;
     int key_is_w;
 };
 
-struct FillStats {  // written by the fill kernels, read back by the host
-    unsigned long long cursor;  // members allocated so far (== total when the launch is over)
-    unsigned int max_count;
-    unsigned int n_big;         // environments larger than the shared-memory class of the launch
-    unsigned int overflow;      // some environment did not fit below `capacity`
+struct ScanStats {  // written by the scan kernels, read back by the host
+    unsigned long long total;
+    unsigned int max_value;
     unsigned int pad;
 };
 
-struct EnvOut {
+struct EnvBuild {
     uint64_t n_env;
-    uint64_t* off;
-    uint32_t* count;
-    double* key;
-    uint8_t* cat;
-    double* dist;     // plain distances (debug/parity) or nullptr
-    uint32_t* idx;    // primitive indices (debug/parity) or nullptr
-    uint64_t capacity;
-    FillStats* stats;
+    const uint32_t* order;    // environments in cell order of their anchors
+    const uint32_t* ub;       // FP32-prefilter upper bound of every environment size
+    const uint64_t* off;      // exclusive scan of the (even-rounded) upper bounds
+    uint32_t* count;          // exact sizes (written by the fill kernel)
+    uint64_t* key;            // store: plain distances (f64 bits) until the sort kernel packs them
+    uint8_t* cat;             // categories of the unsorted members (scratch)
+    uint32_t* idx;            // primitive indices (debug/parity) or nullptr
+    double* dist;             // sorted plain distances (debug/parity) or nullptr
     int key_is_w;
+    int check_first_zero;     // rows mode: the smallest distance of a row must be 0 (locohd.rs:74-77)
 };
 
 struct ScoreArgs {
@@ -100,27 +105,33 @@ struct ScoreArgs {
     uint64_t uniform_n;            // > 0: every job has this many pairs
     const uint32_t* wf_idx;        // per pair or nullptr
     double* out;
-    int stage_cap;                 // members (A + B) staged in shared memory per warp
+    int stage_cap;                 // members (A + B) a warp can stage in shared memory
+    int only_unstaged;             // second pass: score only the pairs the fast kernel skipped
+    int table_n;                   // sqrt / rsqrt table entries staged by the fast kernel
 };
 
 // ---- launchers (all asynchronous on `st`; each returns the number of kernel launches it made) ----
 int launch_convert_categories(const uint16_t* in, uint8_t* out, uint64_t n, int C, cudaStream_t st);
 int launch_validate_xyz(const double* xyz, uint64_t n3, int* err, cudaStream_t st);
 int launch_build_cells(const StructsView& s, double threshold, cudaStream_t st);
-// sampled size probe: environment sizes of anchors 0, stride, 2*stride, ... (n_sample of them) -> count[n_sample]
-int launch_env_count_sample(const StructsView& s, const KParams& p, uint64_t n_sample, uint64_t stride,
-                            const uint32_t* anchor_struct, const uint32_t* anchor_prim, double threshold,
-                            uint32_t* count, cudaStream_t st);
-// gather + sort + store with cursor allocation; cap_class in {256, 512, 1024, 2048}
-int launch_env_fill(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
-                    const uint32_t* anchor_prim, double threshold, const EnvOut& out, int cap_class, cudaStream_t st);
-// second stage for environments larger than cap_class (after the host saw stats.n_big > 0)
-int launch_env_fill_big(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
-                        const uint32_t* anchor_prim, double threshold, const EnvOut& out, int cap_class,
-                        cudaStream_t st);
-int launch_rows_fill(const double* dmx, const uint8_t* cat, uint64_t n_rows, uint64_t row_len, const double* xyz,
-                     const KParams& p, const EnvOut& out, cudaStream_t st);
-int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_members_a, unsigned max_members_b,
+// anchors -> cell order: slot_cnt / slot_off are scratch of n_prims (+1) entries
+int launch_anchor_order(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* anchor_struct,
+                        const uint32_t* anchor_prim, uint64_t n_prims, uint32_t* slot_cnt, uint64_t* slot_off,
+                        uint64_t* scan_scratch, ScanStats* stats, uint32_t* order, cudaStream_t st);
+uint64_t scan_scratch_entries(uint64_t n);
+// exclusive scan of u32 values (optionally rounded up to even) into u64 offsets [n + 1]; stats->total / max_value
+int launch_scan(const uint32_t* values, uint64_t n, int round_even, uint64_t* off, uint64_t* scratch, ScanStats* stats,
+                cudaStream_t st);
+int launch_env_count(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* order,
+                     const uint32_t* anchor_struct, const uint32_t* anchor_prim, double threshold, uint32_t* ub,
+                     cudaStream_t st);
+int launch_env_fill(const StructsView& s, const KParams& p, const uint32_t* anchor_struct, const uint32_t* anchor_prim,
+                    double threshold, const EnvBuild& b, cudaStream_t st);
+// sorts every environment of the store in place and packs the keys; max_count bounds the environment sizes
+int launch_env_sort(const KParams& p, const EnvBuild& b, unsigned max_count, double threshold, cudaStream_t st);
+int launch_rows_copy(const double* dmx, const uint8_t* cat, uint64_t n_rows, uint64_t row_len, const double* xyz,
+                     const KParams& p, uint64_t* off, uint32_t* count, const EnvBuild& b, cudaStream_t st);
+int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsigned max_b, double mean_a, double mean_b,
                  cudaStream_t st);
 int launch_job_means(const double* scores, const uint64_t* job_pair_off, uint64_t n_jobs, double* means,
                      cudaStream_t st);
@@ -130,6 +141,5 @@ int launch_wf_points(const WfDev* wf, uint64_t n, const double* x, double* out, 
 int launch_sd_run(int kind, double q0, double q1, int C, uint64_t n, const double* p1, const double* p2, double* out,
                   cudaStream_t st);
 int launch_fp64_peak(double* scratch, int blocks, int iters, cudaStream_t st);
-int launch_fill_u64_iota_rows(uint64_t* off, uint32_t* count, uint64_t n_rows, uint64_t row_len, cudaStream_t st);
 
 }  // namespace locohd

@@ -18,6 +18,8 @@ struct WfDev {
     int n;
     int int_a;         // kumaraswamy: exponent a if it is a small non-negative integer, else -1
     int int_b;         // kumaraswamy: exponent b likewise
+    int monotone;      // the device CDF is provably non-decreasing in floating point (uniform, integer kumaraswamy)
+    int pad;
     double inv_range;  // uniform / kumaraswamy: 1 / (x_max - x_min)
     double inv_norm;   // hyper_exp: 1 / sum(a_i)
     double w_inf;      // CDF(+inf), evaluated on the host (1 except for degenerate dagum parameters)
