@@ -337,12 +337,12 @@ __global__ void anchor_slot_scatter_kernel(StructsView s, KParams p, uint64_t n_
 // K1a / K1b: one thread per anchor, anchors taken in cell order.
 //   Every lane walks the candidate cells of its own anchor (rows of 2*reach+1 cells are contiguous in the
 //   cell-sorted arrays); neighbouring lanes sit in the same or adjacent cells, so their float4 loads hit the same
-//   lines.  FILL: FP32 survivors are parked in a small per-lane list and the whole warp re-tests them together in
-//   FP64 — box test + ((dx^2 + dy^2) + dz^2) < r^2 with unfused arithmetic, the kd-tree crate's predicate and
-//   operation order; the anchor itself is always kept, others must pass the tag rule (locohd.rs:521-528).
+//   lines.  FILL: every FP32 survivor is re-tested at once in FP64 — box test + ((dx^2 + dy^2) + dz^2) < r^2 with
+//   unfused arithmetic, the kd-tree crate's predicate and operation order; the anchor itself is always kept,
+//   others must pass the tag rule (locohd.rs:521-528).  Lanes of a warp look at the same candidate at the same
+//   time, so the 32-byte exact record is one broadcast load.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTileThreads = 128;
-constexpr int kPend = 16;
 
 template <bool FILL>
 __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, KParams p, uint64_t n_env,
@@ -351,7 +351,6 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
                                                                 const uint32_t* __restrict__ anchor_prim,
                                                                 double threshold, uint32_t* __restrict__ ub,
                                                                 EnvBuild b) {
-    __shared__ uint32_t pend[FILL ? kPend : 1][kTileThreads];
     const int tid = threadIdx.x;
     const uint64_t t = (uint64_t)blockIdx.x * kTileThreads + tid;
     bool active = t < n_env;
@@ -391,34 +390,10 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
     const PrimRec* pd = s.pd + base;
     const uint64_t off = (FILL && active) ? b.off[e] : 0;
     const uint32_t cap = (FILL && active) ? b.ub[e] : 0;
-    uint32_t cnt = 0, np = 0;
-
-    auto flush = [&]() {
-        uint32_t mx = np;
-        for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(kFull, mx, o));
-        for (uint32_t k = 0; k < mx; ++k) {
-            if (k < np) {
-                const uint32_t j = pend[FILL ? k : 0][tid];
-                const PrimRec r = pd[j];
-                const bool in_box = !(r.x < q.x - threshold) && !(r.x > q.x + threshold) &&
-                                    !(r.y < q.y - threshold) && !(r.y > q.y + threshold) &&
-                                    !(r.z < q.z - threshold) && !(r.z > q.z + threshold);
-                const double ex = r.x - q.x, ey = r.y - q.y, ez = r.z - q.z;
-                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-                bool acc = in_box && (d2 < r2);
-                if (acc && j != jpos) acc = tag_rule_accepts(p, qtag, __float_as_uint(__ldg(&pf[j].w)));
-                if (acc) {
-                    if (cnt < cap) {
-                        b.key[off + cnt] = (uint64_t)__double_as_longlong(sqrt(d2));  // utils.rs:1-8
-                        b.cat[off + cnt] = (uint8_t)r.cat;
-                        if (b.idx) b.idx[off + cnt] = r.orig;
-                    }
-                    ++cnt;
-                }
-            }
-        }
-        np = 0;
-    };
+    uint32_t cnt = 0;
+    const double lox = q.x - threshold, hix = q.x + threshold;
+    const double loy = q.y - threshold, hiy = q.y + threshold;
+    const double loz = q.z - threshold, hiz = q.z + threshold;
 
     for (int dz = -reach; dz <= reach; ++dz) {
         for (int dy = -reach; dy <= reach; ++dy) {
@@ -429,25 +404,35 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
                 j = __ldg(cell_start + row + x0);
                 end = __ldg(cell_start + row + x1 + 1);
             }
-            while (__any_sync(kFull, j < end)) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (j < end) {
-                        const float4 c = __ldg(pf + j);
-                        const float dx = c.x - qf.x, dyf = c.y - qf.y, dzf = c.z - qf.z;
-                        const float d2f = dx * dx + dyf * dyf + dzf * dzf;
-                        if (d2f <= m.thr2f) {
-                            if (FILL) { pend[FILL ? np : 0][tid] = j; ++np; } else { ++cnt; }
+            for (; j < end; ++j) {
+                const float4 c = __ldg(pf + j);
+                const float dx = c.x - qf.x, dyf = c.y - qf.y, dzf = c.z - qf.z;
+                const float d2f = dx * dx + dyf * dyf + dzf * dzf;
+                if (d2f <= m.thr2f) {
+                    if (!FILL) {
+                        ++cnt;
+                    } else {
+                        const PrimRec r = pd[j];
+                        const bool in_box = !(r.x < lox) && !(r.x > hix) && !(r.y < loy) && !(r.y > hiy) &&
+                                            !(r.z < loz) && !(r.z > hiz);
+                        const double ex = r.x - q.x, ey = r.y - q.y, ez = r.z - q.z;
+                        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+                        bool acc = in_box && (d2 < r2);
+                        if (acc && j != jpos) acc = tag_rule_accepts(p, qtag, __float_as_uint(c.w));
+                        if (acc) {
+                            if (cnt < cap) {
+                                b.key[off + cnt] = (uint64_t)__double_as_longlong(sqrt(d2));  // utils.rs:1-8
+                                b.cat[off + cnt] = (uint8_t)r.cat;
+                                if (b.idx) b.idx[off + cnt] = r.orig;
+                            }
+                            ++cnt;
                         }
-                        ++j;
                     }
                 }
-                if (FILL && __any_sync(kFull, np > (uint32_t)(kPend - 4))) flush();
             }
         }
     }
     if (FILL) {
-        flush();
         if (active) {
             if (cnt > cap) raise(p.err, LOCOHD_ERR_CUDA);  // the FP32 count is an upper bound by construction
             b.count[e] = min(cnt, cap);
