@@ -401,7 +401,7 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
     }
     EnvBuild b{};
     b.n_env = n_anchors; b.order = d_order; b.ub = d_ub; b.off = e->d_off; b.count = e->d_count; b.key = e->d_key;
-    b.cat = d_cat; b.idx = e->d_idx; b.dist = e->d_dist; b.key_is_w = e->key_is_w ? 1 : 0; b.check_first_zero = 0;
+    b.cat = d_cat; b.idx = e->d_idx; b.dist = e->d_dist; b.key_is_w = e->key_is_w ? 1 : 0; b.key_is_sq = 1; b.check_first_zero = 0;
     {
         ProfScope ps(ctx, LOCOHD_PROF_FILL);
         ctx->launches += launch_env_fill(sv, ctx->kp, d_anchor_struct, d_anchor_prim, threshold, b, ctx->stream);
@@ -801,7 +801,7 @@ static int rows_envset(locohd_ctx* ctx, uint64_t n_rows, uint64_t row_len, const
         return bail(st);
     EnvBuild b{};
     b.n_env = n_rows; b.off = e->d_off; b.count = e->d_count; b.key = e->d_key; b.cat = d_cat; b.idx = e->d_idx;
-    b.dist = e->d_dist; b.key_is_w = e->key_is_w ? 1 : 0; b.check_first_zero = 1;
+    b.dist = e->d_dist; b.key_is_w = e->key_is_w ? 1 : 0; b.key_is_sq = 0; b.check_first_zero = 1;
     {
         ProfScope ps(ctx, LOCOHD_PROF_OTHER);
         ctx->launches += launch_rows_copy(dmx ? in.ptr : nullptr, d_cat8, n_rows, row_len, xyz ? in.ptr : nullptr,

@@ -394,6 +394,11 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
     const double lox = q.x - threshold, hix = q.x + threshold;
     const double loy = q.y - threshold, hiy = q.y + threshold;
     const double loz = q.z - threshold, hiz = q.z + threshold;
+    // Below r2_safe the box test cannot fail: |dx| < r - margin with margin >= the rounding error of q + r
+    // (4 ulp of the larger of |q| and r).  Only the thin shell above it pays for the six extra compares.
+    const double qmax = fmax(fmax(fabs(q.x), fabs(q.y)), fmax(fabs(q.z), threshold));
+    const double r_safe = threshold - 8.9e-16 * (qmax + threshold);
+    const double r2_safe = (r_safe > 0.0 && isfinite(r_safe)) ? r_safe * r_safe * (1.0 - 1e-15) : (isinf(threshold) ? r2 : 0.0);
 
     for (int dz = -reach; dz <= reach; ++dz) {
         for (int dy = -reach; dy <= reach; ++dy) {
@@ -413,15 +418,18 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
                         ++cnt;
                     } else {
                         const PrimRec r = pd[j];
-                        const bool in_box = !(r.x < lox) && !(r.x > hix) && !(r.y < loy) && !(r.y > hiy) &&
-                                            !(r.z < loz) && !(r.z > hiz);
                         const double ex = r.x - q.x, ey = r.y - q.y, ez = r.z - q.z;
                         const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-                        bool acc = in_box && (d2 < r2);
+                        bool acc = d2 < r2;
+                        if (acc && !(d2 < r2_safe)) {
+                            // within rounding distance of the sphere: the crate's per-axis box test can still reject
+                            acc = !(r.x < lox) && !(r.x > hix) && !(r.y < loy) && !(r.y > hiy) && !(r.z < loz) &&
+                                  !(r.z > hiz);
+                        }
                         if (acc && j != jpos) acc = tag_rule_accepts(p, qtag, __float_as_uint(c.w));
                         if (acc) {
                             if (cnt < cap) {
-                                b.key[off + cnt] = (uint64_t)__double_as_longlong(sqrt(d2));  // utils.rs:1-8
+                                b.key[off + cnt] = (uint64_t)__double_as_longlong(d2);  // sqrt in the sort kernel
                                 b.cat[off + cnt] = (uint8_t)r.cat;
                                 if (b.idx) b.idx[off + cnt] = r.orig;
                             }
@@ -511,9 +519,10 @@ __global__ void __launch_bounds__(kSortWarps * 32) env_sort_kernel(KParams p, En
     for (int q = lane; q < NB; q += 32) bend[q] = 0;
     __syncwarp();
     // ---- bucket = NB * (d * scale)^2: members of a spherical environment grow like d^2 per unit distance
+    //      (keys that are already squared distances come with scale = 1 / r^2 and are used linearly)
     for (uint32_t i = lane; i < M; i += 32) {
         const float x = (float)(key[i] * scale);       // monotone in the key; NaN only for inf * 0
-        const float f = x * fabsf(x) * (float)NB;
+        const float f = (b.key_is_sq ? x : x * fabsf(x)) * (float)NB;
         int q = (int)fminf(f, (float)(NB - 1));        // fminf(NaN, y) = y: infinities land in the last bucket
         q = max(q, 0);
         bkt[i] = (uint16_t)q;
@@ -574,7 +583,7 @@ __global__ void __launch_bounds__(kSortWarps * 32) env_sort_kernel(KParams p, En
         uint64_t packed = 0;
         if (pos < M) {
             const uint32_t en = perm[pos];
-            const double d = key[en];
+            const double d = b.key_is_sq ? sqrt(key[en]) : key[en];   // utils.rs:1-8
             const double w = b.key_is_w ? ((d < 0.0) ? 0.0 : wf_cdf(wf, d)) : d;
             packed = pack_key(w, scat[en]);
             if (b.dist) b.dist[off + pos] = d;
@@ -608,7 +617,10 @@ __global__ void __launch_bounds__(kBigThreads) env_sort_big_kernel(KParams p, En
     uint8_t* c = b.cat + off;
     uint32_t* ix = b.idx ? b.idx + off : nullptr;
     bool bad = false;
-    for (uint32_t i = threadIdx.x; i < M; i += kBigThreads) bad |= isnan(d[i]);
+    for (uint32_t i = threadIdx.x; i < M; i += kBigThreads) {
+        if (b.key_is_sq) d[i] = sqrt(d[i]);
+        bad |= isnan(d[i]);
+    }
     if (__syncthreads_or(bad)) { if (threadIdx.x == 0) raise(p.err, LOCOHD_ERR_NAN); return; }
     uint32_t n2 = 1;
     while (n2 < M) n2 <<= 1;
@@ -702,7 +714,7 @@ constexpr int kScoreMaxWarps = 8;
 constexpr uint64_t kWMask = ~kCatMask;
 
 __host__ __device__ inline int score_state_bytes(int C) { return ((2 * C * 32 * 8 + 2 * C * 32 * 4) + 15) & ~15; }
-__host__ __device__ inline int fast_state_bytes(int CP) { return 2 * CP * 32 * 8 + CP * 32 * 4; }
+__host__ __device__ inline int fast_state_bytes(int CP) { return CP * 32 * 4; }
 
 struct PairEnvs {
     bool ok;
@@ -936,9 +948,7 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
     if (wib >= warps_per_block) return;
     const int C = P.C;
     unsigned char* mine = smem_raw + (size_t)2 * table_n * 8 + (size_t)wib * per_warp_bytes;
-    double2* val2 = reinterpret_cast<double2*>(mine);                        // [2][CP/2][32]
-    double* valf = reinterpret_cast<double*>(mine);
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(mine + 2 * CP * 32 * 8);     // [CP][32]: A count | B count << 16
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(mine);                       // [CP][32]: A count | B count << 16
     uint64_t* stage = reinterpret_cast<uint64_t*>(mine + fast_state_bytes(CP));
     auto sqrt_of = [&](uint32_t k) -> double {
         if (CHECK && k >= (uint32_t)table_n) return sqrt((double)k);
@@ -995,6 +1005,7 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
         }
         if (__any_sync(kFull, unknown)) { raise(P.err, LOCOHD_ERR_UNKNOWN_CATEGORY); continue; }  // pmf.rs:38-42
         uint32_t totA = 0, totB = 0;
+        double sa[CP], sb[CP];   // sqrt(count) per category, in registers (every access below is unrolled)
 #pragma unroll
         for (int r = 0; r < CP; ++r) {
             const uint32_t v = cnt[r * 32 + lane];
@@ -1010,8 +1021,8 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
             cnt[r * 32 + lane] = ex;
             const uint32_t ka = ex & 0xffffu, kb = ex >> 16;
             totA += ka; totB += kb;
-            valf[((r >> 1) * 32 + lane) * 2 + (r & 1)] = sqrt_of(ka);
-            valf[((CP / 2 + (r >> 1)) * 32 + lane) * 2 + (r & 1)] = sqrt_of(kb);
+            sa[r] = sqrt_of(ka);
+            sb[r] = sqrt_of(kb);
         }
         double rA = rsqrt_of(totA), rB = rsqrt_of(totB);
 
@@ -1019,12 +1030,9 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
             // difference form of the Hellinger distance; products rounded before the subtraction (see score_kernel)
             double acc = 0.0;
 #pragma unroll
-            for (int q = 0; q < CP / 2; ++q) {
-                const double2 va = val2[q * 32 + lane], vb = val2[(CP / 2 + q) * 32 + lane];
-                const double u0 = __dmul_rn(va.x, rA) - __dmul_rn(vb.x, rB);
-                const double u1 = __dmul_rn(va.y, rA) - __dmul_rn(vb.y, rB);
-                acc = fma(u0, u0, acc);
-                acc = fma(u1, u1, acc);
+            for (int r = 0; r < CP; ++r) {
+                const double u = __dmul_rn(sa[r], rA) - __dmul_rn(sb[r], rB);
+                acc = fma(u, u, acc);
             }
             return sqrt(0.5 * acc);
         };
@@ -1049,7 +1057,13 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
             const uint32_t word = cnt[c * 32 + lane] + (takeA ? 1u : 0x10000u);
             cnt[c * 32 + lane] = word;
             const uint32_t k = takeA ? (word & 0xffffu) : (word >> 16);
-            valf[(((takeA ? 0 : CP / 2) + (c >> 1)) * 32 + lane) * 2 + (c & 1)] = sqrt_of(k);
+            const double sk = sqrt_of(k);
+#pragma unroll
+            for (int r = 0; r < CP; ++r) {   // predicated register update: one of the 2*CP values changes
+                const bool hit = c == (uint32_t)r;
+                sa[r] = (hit && takeA) ? sk : sa[r];
+                sb[r] = (hit && !takeA) ? sk : sb[r];
+            }
             if (takeA) {
                 ++totA; rA = rsqrt_of(totA);
                 ++i;
@@ -1291,7 +1305,9 @@ static int launch_env_sort_t(const KParams& p, const EnvBuild& b, unsigned max_c
 int launch_env_sort(const KParams& p, const EnvBuild& b, unsigned max_count, double threshold, cudaStream_t st) {
     if (!b.n_env) return 0;
     // gather mode: distances are below the threshold; rows mode (threshold <= 0): scale from the data
-    const double scale = (threshold > 0.0 && std::isfinite(threshold)) ? (1.0 - 1e-9) / threshold : 0.0;
+    double scale = 0.0;
+    if (threshold > 0.0 && std::isfinite(threshold * threshold))
+        scale = b.key_is_sq ? (1.0 - 1e-9) / (threshold * threshold) : (1.0 - 1e-9) / threshold;
     return b.idx ? launch_env_sort_t<true>(p, b, max_count, scale, st) : launch_env_sort_t<false>(p, b, max_count, scale, st);
 }
 
@@ -1382,7 +1398,7 @@ int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsign
     a.only_unstaged = 0;
     const int tables = 2 * (int)table_n * 8;
     const int per_warp = fast_state_bytes(CP) + (int)stage * 8;
-    const int budget = 100 * 1024;  // two CTAs per SM
+    const int budget = 72 * 1024;  // three CTAs per SM
     int warps = (budget - tables) / per_warp;
     if (warps > kScoreMaxWarps) warps = kScoreMaxWarps;
     if (warps < 1) warps = 1;

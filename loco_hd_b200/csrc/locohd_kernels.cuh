@@ -92,6 +92,7 @@ struct EnvBuild {
     uint32_t* idx;            // primitive indices (debug/parity) or nullptr
     double* dist;             // sorted plain distances (debug/parity) or nullptr
     int key_is_w;
+    int key_is_sq;            // unsorted keys are squared distances (gather) rather than distances (rows)
     int check_first_zero;     // rows mode: the smallest distance of a row must be 0 (locohd.rs:74-77)
 };
 

@@ -27,7 +27,19 @@ struct WfDev {
 };
 
 __device__ __forceinline__ double powi_small(double x, int e) {
-    // e in [0, 64): square-and-multiply; a handful of roundings (<= 1e-15 relative).
+    // e in [0, 64]: a handful of roundings (<= 1e-15 relative).  Straight-line code for the common small exponents
+    // (the exponent is uniform over a launch), square-and-multiply otherwise.
+    switch (e) {
+        case 0: return 1.0;
+        case 1: return x;
+        case 2: return x * x;
+        case 3: return x * x * x;
+        case 4: { const double x2 = x * x; return x2 * x2; }
+        case 5: { const double x2 = x * x; return x2 * x2 * x; }
+        case 6: { const double x2 = x * x; return x2 * x2 * x2; }
+        case 8: { const double x2 = x * x, x4 = x2 * x2; return x4 * x4; }
+        default: break;
+    }
     double r = 1.0;
     double b = x;
     while (e) {
