@@ -1,0 +1,123 @@
+"""Batches of structure pairs / trajectory frames / ensemble members over the GPUs of one box.
+
+The scoring path has no exchange step (anchor pairs are independent): every rank owns one GPU,
+scores its share of the jobs, and the per-rank score slabs are put together on the host.  This module holds the
+host-side logic — dealing jobs to ranks, running a rank's share through the C ABI, assembling the results — and
+nothing else; `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is only used to assemble results when the
+caller asks for them on every rank.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+JOB_DTYPE = np.dtype([("a_first", "<u8"), ("b_first", "<u8"), ("n", "<u8")])
+
+
+def deal_jobs(job_sizes: Sequence[int], world: int) -> List[np.ndarray]:
+    """Deal jobs to `world` ranks so that the anchor-pair totals are balanced (longest job first onto the least
+    loaded rank; ties broken by rank, then job id, so every rank computes the same assignment)."""
+    sizes = np.asarray(job_sizes, dtype=np.int64)
+    order = np.lexsort((np.arange(len(sizes)), -sizes))
+    load = np.zeros(world, dtype=np.int64)
+    owner = np.empty(len(sizes), dtype=np.int64)
+    for j in order:
+        r = int(np.argmin(load))
+        owner[j] = r
+        load[r] += sizes[j]
+    return [np.flatnonzero(owner == r) for r in range(world)]
+
+
+def all_pairs(n: int) -> np.ndarray:
+    """(i, j) with i < j, the all-vs-all job list of an ensemble of n structures (compare_ensembles.py:250-296)."""
+    i, j = np.triu_indices(n, k=1)
+    return np.stack([i, j], axis=1)
+
+
+def assemble(per_rank_ids: Sequence[np.ndarray], per_rank_values: Sequence[np.ndarray], n_jobs: int) -> np.ndarray:
+    """Per-rank (job ids, values) -> one array indexed by job id."""
+    out = np.full(n_jobs, np.nan, dtype=np.float64)
+    for ids, vals in zip(per_rank_ids, per_rank_values):
+        out[np.asarray(ids, dtype=np.int64)] = np.asarray(vals, dtype=np.float64)
+    return out
+
+
+def gather_job_values(my_ids: np.ndarray, my_values: np.ndarray, n_jobs: int) -> np.ndarray:
+    """All ranks get the values of all jobs.  Works with any initialised torch.distributed backend."""
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return assemble([my_ids], [my_values], n_jobs)
+    gathered: List[Optional[Tuple[np.ndarray, np.ndarray]]] = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, (np.asarray(my_ids), np.asarray(my_values)))
+    return assemble([g[0] for g in gathered], [g[1] for g in gathered], n_jobs)
+
+
+def run_sharded(job_sizes: Sequence[int], scorer: Callable[[np.ndarray], np.ndarray], rank: int, world: int,
+                gather: bool = True) -> np.ndarray:
+    """Score this rank's share with `scorer(job_ids) -> one value per job` and (optionally) gather everything."""
+    mine = deal_jobs(job_sizes, world)[rank]
+    values = np.asarray(scorer(mine), dtype=np.float64) if len(mine) else np.zeros(0)
+    if not gather:
+        return assemble([mine], [values], len(job_sizes))
+    return gather_job_values(mine, values, len(job_sizes))
+
+
+@dataclass
+class ResidentEnsemble:
+    """An ensemble resident on one GPU: structures uploaded once, one environment per (structure, anchor)."""
+
+    ctx: object
+    structs: object
+    env: object
+    anchors_per_structure: int
+
+    @classmethod
+    def build(cls, ctx, clouds, anchors: np.ndarray, threshold: float) -> "ResidentEnsemble":
+        """clouds: objects with .xyz [n,3] f64, .cat u16, .tag u32 (same topology); anchors: primitive indices used in
+        every structure."""
+        offs = np.cumsum([0] + [len(c.cat) for c in clouds]).astype(np.uint64)
+        st = ctx.structs_create(offs, np.concatenate([c.xyz for c in clouds]), np.concatenate([c.cat for c in clouds]),
+                                np.concatenate([c.tag for c in clouds]))
+        anchors = np.asarray(anchors, dtype=np.uint32)
+        a_struct = np.repeat(np.arange(len(clouds), dtype=np.uint32), len(anchors))
+        env = ctx.envset_build(st, np.tile(anchors, len(clouds)), threshold, anchor_struct=a_struct)
+        return cls(ctx, st, env, len(anchors))
+
+    def job_table(self, pairs: np.ndarray) -> np.ndarray:
+        n = self.anchors_per_structure
+        jobs = np.empty(len(pairs), dtype=JOB_DTYPE)
+        jobs["a_first"] = np.asarray(pairs)[:, 0].astype(np.uint64) * n
+        jobs["b_first"] = np.asarray(pairs)[:, 1].astype(np.uint64) * n
+        jobs["n"] = n
+        return jobs
+
+    def pair_means(self, pairs: np.ndarray, chunk: int = 4096) -> np.ndarray:
+        """Mean LoCoHD of every structure pair (the `lchd_dmx` entries of compare_ensembles.py:293-299), reduced on
+        the device so that only one number per pair crosses the bus."""
+        out = np.empty(len(pairs), dtype=np.float64)
+        for lo in range(0, len(pairs), chunk):
+            jobs = self.job_table(pairs[lo:lo + chunk])
+            _, means = self.ctx.score_jobs(self.env, self.env, jobs, want_scores=False, want_means=True)
+            out[lo:lo + chunk] = means
+        return out
+
+    def close(self):
+        self.env.close()
+        self.structs.close()
+
+
+def ensemble_all_vs_all(ctx, clouds, anchors, threshold: float, rank: int = 0, world: int = 1,
+                        gather: bool = True) -> np.ndarray:
+    """All-vs-all mean LoCoHD matrix entries (i < j, order of `all_pairs`) of an ensemble, sharded over `world`
+    ranks: every rank keeps the whole ensemble resident (1000 x 5000 primitives = 145 MB) and scores its share of
+    the structure pairs."""
+    pairs = all_pairs(len(clouds))
+    ens = ResidentEnsemble.build(ctx, clouds, anchors, threshold)
+    try:
+        sizes = np.full(len(pairs), len(anchors))
+        return run_sharded(sizes, lambda ids: ens.pair_means(pairs[ids]), rank, world, gather)
+    finally:
+        ens.close()
