@@ -154,6 +154,14 @@ def oracle_params(oracle, wl):
     return oracle.Params(wl.C, [(wl.wf[0], list(wl.wf[1]))], tag_rule=wl.rule)
 
 
+def host_threads():
+    """Host threads the CPU arm may use (torchrun exports OMP_NUM_THREADS=1: the oracle gets the count explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def oracle_run_jobs(oracle, op, wl, job_ids, n_threads=0):
     """The CPU restatement on a set of jobs; returns (anchor pairs, seconds, walk steps, env members)."""
     pairs, steps, members = 0, 0, 0
@@ -188,12 +196,12 @@ def run_reference(args, rank, world):
     wl = make_workload(args.workload, 0, world, args)
     op = oracle_params(oracle, wl)
     ids = sample_jobs(wl, args.ref_pairs)
-    cores = oracle.max_threads()
+    cores = host_threads()
     for _ in range(args.warmup):
-        oracle_run_jobs(oracle, op, wl, ids[:1])
+        oracle_run_jobs(oracle, op, wl, ids[:1], n_threads=cores)
     t, pairs = 0.0, 0
     for _ in range(args.steps):
-        p, dt, _, _ = oracle_run_jobs(oracle, op, wl, ids)
+        p, dt, _, _ = oracle_run_jobs(oracle, op, wl, ids, n_threads=cores)
         t += dt
         pairs += p
     value = pairs / t
@@ -371,15 +379,16 @@ def run_gpu(args, rank, local_rank, world):
         oracle.build()
         op = oracle_params(oracle, wl)
         ids = sample_jobs(wl, args.ref_pairs)
-        oracle_run_jobs(oracle, op, wl, ids[:1])
-        p, dt, steps, members = oracle_run_jobs(oracle, op, wl, ids)
+        cores = host_threads()
+        oracle_run_jobs(oracle, op, wl, ids[:1], n_threads=cores)
+        p, dt, steps, members = oracle_run_jobs(oracle, op, wl, ids, n_threads=cores)
         ids1 = sample_jobs(wl, max(1, args.ref_pairs // 16))
         p1, dt1, _, _ = oracle_run_jobs(oracle, op, wl, ids1, n_threads=1)
         # the sample doubles as a parity spot check of this very run
         a, b, anchors = wl.job_arrays(0)
         ref = oracle.from_primitives(op, a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, wl.threshold)
         n0 = int(wl.jobs["n"][0])
-        cpu = {"value": p / dt, "unit": "anchor-pairs/s", "cores": oracle.max_threads(), "kind": "port",
+        cpu = {"value": p / dt, "unit": "anchor-pairs/s", "cores": cores, "kind": "port",
                "sample": f"first {len(ids)} structure pair(s) of the step = {p} anchor pairs, {dt:.2f} s",
                "single_thread_value": p1 / dt1,
                "walk_steps_per_pair": steps / p, "env_members_per_pair": members / p,
