@@ -133,18 +133,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([v.strip() for v in line.split(",")])
+            self.rows.append((time.perf_counter(), [v.strip() for v in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples taken inside [t_begin, t_end] (the timed region).  The sampler is started before
+        the warm-up so that nvidia-smi's own start-up does not fall into the timed region."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         self.thread.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = [r for ts, r in self.rows if (t_begin is None or ts >= t_begin) and (t_end is None or ts <= t_end + 0.1)]
+        if not rows:
+            rows = [r for _, r in self.rows[-3:]]
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
+        reasons = sorted({n for r in rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -266,13 +271,14 @@ def run_gpu(args, rank, local_rank, world):
         ctx.score_jobs(env, env, wl.jobs, out=d_out.data_ptr())
         env.close()
 
+    clocks = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step_resident()
     ctx.synchronize()
     ctx.profile_read()
     barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank)
+    t_begin = time.perf_counter()
     ctx.profile_enable(True)
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -281,12 +287,13 @@ def run_gpu(args, rank, local_rank, world):
         step_resident()
     e1.record(stream)
     torch.cuda.synchronize()
+    t_end = time.perf_counter()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count - launches0
     prof = ctx.profile_read()
     ctx.profile_enable(False)
-    clock_info = clocks.stop()
+    clock_info = clocks.stop(t_begin, t_end)
     total_pairs = sum_over_ranks(float(wl.n_pairs))
     value = total_pairs * args.steps / (ms_total * 1e-3)
 

@@ -929,30 +929,50 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
 }
 
 // Fast kernel: Hellinger-2, unit category weights, C <= CP (8 or 16), both environments staged in shared memory.
-// Per-lane state lives in shared memory as double2 pairs read with LDS.128 at compile-time offsets, the (A, B)
-// counts of a category share one 32-bit word, sqrt / rsqrt tables sit in shared memory, and with KEY_IS_W the
-// environments already hold W(distance).  Pairs that do not fit the stage are left to score_kernel.
+//
+// With unit weights the compositions are count_r / n, so
+//     H^2 = 1/2 sum_r (sqrt(a_r / nA) - sqrt(b_r / nB))^2 = 1 - D / sqrt(nA nB),   D = sum_r sqrt(a_r) sqrt(b_r),
+// and one event changes a single term of D: D += (sqrt(k + 1) - sqrt(k)) * sqrt(other count of that category).
+// Each lane therefore keeps (D, nA, nB, #categories whose two counts differ) in registers, the counts of a category
+// share one 32-bit shared-memory word, and sqrt / delta-sqrt / rsqrt come from shared-memory tables.
+// The expanded form loses digits when H^2 is tiny, so
+//   * identical counts give H = 0 exactly (as upstream, and as the difference form does),
+//   * H^2 < kSmallH2 (only reachable for environments of thousands of members, or proportional compositions) is
+//     recomputed in the difference form sum_r (sqrt(a_r) rA - sqrt(b_r) rB)^2 from the counts,
+//   * D is rebuilt from the counts every kRefresh events, so rounding cannot drift.
+// Error of the fast branch: |dH| <= ~5e-16 / (2 * sqrt(kSmallH2)) = 2.5e-12 (bar: 1e-9 on the score).
+// With KEY_IS_W the environments already hold W(distance).  Pairs that do not fit the stage are left to score_kernel.
+constexpr double kSmallH2 = 1e-8;
+constexpr int kRefresh = 64;
+
 template <int CP, bool KEY_IS_W, bool CHECK>
 __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreArgs a, KParams P, int warps_per_block,
                                                                          int per_warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int table_n = a.table_n;
-    double* s_sqrt = reinterpret_cast<double*>(smem_raw);
-    double* s_rsqrt = s_sqrt + table_n;
+    double* s_sqrt = reinterpret_cast<double*>(smem_raw);   // sqrt(k)
+    double* s_dsq = s_sqrt + table_n;                       // sqrt(k + 1) - sqrt(k)   (exact: Sterbenz)
+    double* s_rsqrt = s_dsq + table_n;                      // 1 / sqrt(k)
     for (int k = threadIdx.x; k < table_n; k += blockDim.x) {
-        s_sqrt[k] = P.sqrt_tbl[k];
+        const double s0 = P.sqrt_tbl[k], s1 = P.sqrt_tbl[k + 1];
+        s_sqrt[k] = s0;
+        s_dsq[k] = s1 - s0;
         s_rsqrt[k] = P.rsqrt_tbl[k];
     }
     __syncthreads();
     if (wib >= warps_per_block) return;
     const int C = P.C;
-    unsigned char* mine = smem_raw + (size_t)2 * table_n * 8 + (size_t)wib * per_warp_bytes;
+    unsigned char* mine = smem_raw + (size_t)3 * table_n * 8 + (size_t)wib * per_warp_bytes;
     uint32_t* cnt = reinterpret_cast<uint32_t*>(mine);                       // [CP][32]: A count | B count << 16
     uint64_t* stage = reinterpret_cast<uint64_t*>(mine + fast_state_bytes(CP));
     auto sqrt_of = [&](uint32_t k) -> double {
         if (CHECK && k >= (uint32_t)table_n) return sqrt((double)k);
         return s_sqrt[k];
+    };
+    auto dsq_of = [&](uint32_t k) -> double {   // sqrt(k + 1) - sqrt(k)
+        if (CHECK && k >= (uint32_t)table_n) return sqrt((double)k + 1.0) - sqrt((double)k);
+        return s_dsq[k];
     };
     auto rsqrt_of = [&](uint32_t k) -> double {
         if (CHECK && k >= (uint32_t)table_n) return 1.0 / sqrt((double)k);
@@ -1004,8 +1024,6 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
             if (c < (uint32_t)C) cnt[c * 32 + lane] += 0x10000u; else unknown = true;
         }
         if (__any_sync(kFull, unknown)) { raise(P.err, LOCOHD_ERR_UNKNOWN_CATEGORY); continue; }  // pmf.rs:38-42
-        uint32_t totA = 0, totB = 0;
-        double sa[CP], sb[CP];   // sqrt(count) per category, in registers (every access below is unrolled)
 #pragma unroll
         for (int r = 0; r < CP; ++r) {
             const uint32_t v = cnt[r * 32 + lane];
@@ -1019,23 +1037,42 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
             if (r == (int)catA0) ex += 1u;          // anchors (locohd.rs:82-84)
             if (r == (int)catB0) ex += 0x10000u;
             cnt[r * 32 + lane] = ex;
-            const uint32_t ka = ex & 0xffffu, kb = ex >> 16;
-            totA += ka; totB += kb;
-            sa[r] = sqrt_of(ka);
-            sb[r] = sqrt_of(kb);
         }
-        double rA = rsqrt_of(totA), rB = rsqrt_of(totB);
 
-        auto stat_dist = [&]() -> double {
-            // difference form of the Hellinger distance; products rounded before the subtraction (see score_kernel)
+        uint32_t totA = 0, totB = 0;
+        int mism = 0;
+        double D = 0.0, rA = 0.0, rB = 0.0;
+        // (re)build D, the totals and the mismatch count from the counts
+        auto rebuild = [&]() {
+            totA = 0; totB = 0; mism = 0; D = 0.0;
+#pragma unroll
+            for (int r = 0; r < CP; ++r) {
+                const uint32_t word = cnt[r * 32 + lane];
+                const uint32_t ka = word & 0xffffu, kb = word >> 16;
+                totA += ka; totB += kb;
+                mism += (ka != kb) ? 1 : 0;
+                D = fma(sqrt_of(ka), sqrt_of(kb), D);
+            }
+            rA = rsqrt_of(totA); rB = rsqrt_of(totB);
+        };
+        // difference form from the counts (small H^2 only)
+        auto exact_h2 = [&]() -> double {
             double acc = 0.0;
 #pragma unroll
             for (int r = 0; r < CP; ++r) {
-                const double u = __dmul_rn(sa[r], rA) - __dmul_rn(sb[r], rB);
+                const uint32_t word = cnt[r * 32 + lane];
+                const double u = __dmul_rn(sqrt_of(word & 0xffffu), rA) - __dmul_rn(sqrt_of(word >> 16), rB);
                 acc = fma(u, u, acc);
             }
-            return sqrt(0.5 * acc);
+            return 0.5 * acc;
         };
+        auto stat_dist = [&]() -> double {
+            if (mism == 0) return 0.0;                       // identical counts: exactly 0
+            double h2 = fma(-__dmul_rn(rA, rB), D, 1.0);
+            if (h2 < kSmallH2) h2 = exact_h2();
+            return sqrt(h2);
+        };
+        rebuild();
 
         const WfDev& wf = P.wfs[(!KEY_IS_W && a.wf_idx) ? a.wf_idx[pair] : 0];
         auto weight = [&](uint64_t k) -> double { return KEY_IS_W ? key_value(k) : wf_cdf(wf, key_value(k)); };
@@ -1047,6 +1084,7 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
         double acc = 0.0;
 
         uint64_t ra = (i < i1) ? kA[i] : 0, rb = (j < j1) ? kB[j] : 0;
+        int since_refresh = 0;
         while (i < i1 || j < j1) {
             const bool takeA = (i < i1) && (!(j < j1) || (ra & kWMask) <= (rb & kWMask));
             const uint64_t raw = takeA ? ra : rb;
@@ -1054,16 +1092,12 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
             const double w = weight(raw);
             acc = fma(w - wprev, h, acc);
             wprev = w;
-            const uint32_t word = cnt[c * 32 + lane] + (takeA ? 1u : 0x10000u);
-            cnt[c * 32 + lane] = word;
-            const uint32_t k = takeA ? (word & 0xffffu) : (word >> 16);
-            const double sk = sqrt_of(k);
-#pragma unroll
-            for (int r = 0; r < CP; ++r) {   // predicated register update: one of the 2*CP values changes
-                const bool hit = c == (uint32_t)r;
-                sa[r] = (hit && takeA) ? sk : sa[r];
-                sb[r] = (hit && !takeA) ? sk : sb[r];
-            }
+            const uint32_t word = cnt[c * 32 + lane];
+            const uint32_t ka = word & 0xffffu, kb = word >> 16;
+            const uint32_t mine_k = takeA ? ka : kb, other_k = takeA ? kb : ka;
+            cnt[c * 32 + lane] = word + (takeA ? 1u : 0x10000u);
+            mism += (mine_k == other_k ? 1 : 0) - (mine_k + 1u == other_k ? 1 : 0);
+            D = fma(dsq_of(mine_k), sqrt_of(other_k), D);
             if (takeA) {
                 ++totA; rA = rsqrt_of(totA);
                 ++i;
@@ -1073,6 +1107,7 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
                 ++j;
                 if (j < j1) rb = kB[j];
             }
+            if (++since_refresh == kRefresh) { since_refresh = 0; rebuild(); }
             h = stat_dist();
         }
         if (lane == 31) acc = fma(wf.w_inf - wprev, h, acc);
@@ -1396,7 +1431,7 @@ int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsign
     a.table_n = (int)table_n;
     a.stage_cap = (int)stage;
     a.only_unstaged = 0;
-    const int tables = 2 * (int)table_n * 8;
+    const int tables = 3 * (int)table_n * 8;
     const int per_warp = fast_state_bytes(CP) + (int)stage * 8;
     const int budget = 72 * 1024;  // three CTAs per SM
     int warps = (budget - tables) / per_warp;
