@@ -356,20 +356,36 @@ def run_gpu(args, rank, local_rank, world):
     fp64_peak = ctx.measure_fp64_tflops()
     kernels = {g: {"ms_per_step": ms / args.steps, "share": ms / max(sum(v[0] for v in prof.values()), 1e-9)}
                for g, (ms, n) in prof.items() if n}
-    # K1 (upper-bound count + exact gather + sort) is one algorithmic unit in SURVEY.md 8(d): 10 flops per member
-    k1 = sum(kernels[g]["ms_per_step"] for g in ("count", "fill", "sort") if g in kernels)
-    k2 = kernels.get("score", {}).get("ms_per_step", 0.0)
-    if k2 >= k1:
-        dominant, dom_flops, dom_ms = "score_fast_kernel / score_kernel (K2 merge walk)", f_walk, k2
-    else:
-        dominant, dom_flops, dom_ms = "env_tile_kernel + env_sort_kernel (K1 gather + sort)", f_gather, k1
+    # Algorithmic flops per kernel: walk E * (10 C + 4 + F_wf) -> K2; of the 10 flops per
+    # environment member 9 (3 sub, 3 mul, 2 add, 1 compare) belong to the exact gather K1b and 1 (sqrt) to the sort
+    # K1c; the FP32 upper-bound pass K1a does no algorithmic FP64 work (its 7 FP32 flops per candidate are overhead).
+    alg = {"score": ("score_fast_kernel / score_kernel (K2 merge walk)", f_walk),
+           "fill": ("env_tile_kernel<true> (K1b exact gather)", 0.9 * f_gather),
+           "sort": ("env_sort_kernel (K1c sort + CDF + packing)", 0.1 * f_gather),
+           "count": ("env_tile_kernel<false> (K1a FP32 upper-bound sizes)", 0.0)}
+    traffic = {}
+    try:
+        tr = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+        if tr.get("workload") == wl.name and tr.get("anchor_pairs_per_step") == wl.n_pairs:
+            traffic = tr.get("dram_bytes_per_launch", {})
+    except (OSError, ValueError):
+        pass
+    per_kernel = {}
+    for g, (name, flops) in alg.items():
+        if g in kernels and kernels[g]["ms_per_step"] > 0:
+            ach = flops / (kernels[g]["ms_per_step"] * 1e-3) / 1e12
+            per_kernel[g] = {"kernel": name, "launch_ms": kernels[g]["ms_per_step"], "alg_flops_per_launch": flops,
+                             "achieved_tflops": ach, "frac_of_fp64_peak": ach / fp64_peak, "traffic": traffic.get(g)}
+    dom = max(per_kernel, key=lambda g: per_kernel[g]["launch_ms"])
+    dominant, dom_flops, dom_ms = per_kernel[dom]["kernel"], per_kernel[dom]["alg_flops_per_launch"], per_kernel[dom]["launch_ms"]
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     step_ms = ms_total / args.steps
     roofline = {
         "kernel": dominant,
         "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
         "peak_source": "FP64 FMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 entry)",
-        "traffic": None, "alg_flops_per_launch": dom_flops, "launch_ms": dom_ms,
+        "traffic": traffic.get(dom), "alg_flops_per_launch": dom_flops, "launch_ms": dom_ms,
+        "note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch from profiles/ (ncu --set full)",
     }
     roofline_hbm = {"bound": "hbm", "achieved": alg_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
@@ -416,7 +432,7 @@ def run_gpu(args, rank, local_rank, world):
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_step": roofline_step,
-        "kernels": kernels,
+        "kernels": kernels, "kernel_rooflines": per_kernel,
         "env_size_mean": float(sizes.mean()), "env_size_max": int(sizes.max()),
         "cpu_baseline": cpu,
     }
