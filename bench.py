@@ -116,42 +116,74 @@ def make_workload(name, rank, world, args):
 
 # ---------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (in-process, ~20 Hz).  A looping
+    `nvidia-smi -lms` next to the benchmark perturbs short kernels on these hosts, so it is only the fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, device):
-        self.rows, self.proc = [], None
+        self.rows, self.stop_flag, self.nvml, self.proc = [], False, None, None
+        self.period = float(os.environ.get("LOCOHD_BENCH_CLOCK_PERIOD", "0.2"))
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(device)], stdout=subprocess.PIPE, text=True,
-                                         stderr=subprocess.DEVNULL)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [v.strip() for v in line.split(",")]))
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = device
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[device])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+        self.thread = threading.Thread(target=self._poll if self.nvml else self._smi, args=(device,), daemon=True)
+        self.thread.start()
+
+    def _poll(self, device):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.perf_counter(), mhz, self.max_mhz, mask))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def _smi(self, device):
+        fields = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={fields}", "--format=csv,noheader,nounits", "-i",
+                                      str(device)], capture_output=True, text=True, timeout=5).stdout.strip()
+                v = [x.strip() for x in out.split(",")]
+                mask = sum(bit for bit, flag in zip((0x8, 0x40, 0x20, 0x4), v[2:6]) if flag == "Active")
+                self.rows.append((time.perf_counter(), float(v[0]), float(v[1]), mask))
+            except Exception:
+                pass
+            time.sleep(1.0)
 
     def stop(self, t_begin=None, t_end=None):
-        """Summary of the samples taken inside [t_begin, t_end] (the timed region).  The sampler is started before
-        the warm-up so that nvidia-smi's own start-up does not fall into the timed region."""
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.thread.join(timeout=2)
-        rows = [r for ts, r in self.rows if (t_begin is None or ts >= t_begin) and (t_end is None or ts <= t_end + 0.1)]
+        """Summary of the samples taken inside [t_begin, t_end] (the timed region)."""
+        self.stop_flag = True
+        self.thread.join(timeout=3)
+        rows = [r for r in self.rows if (t_begin is None or r[0] >= t_begin) and (t_end is None or r[0] <= t_end)]
         if not rows:
-            rows = [r for _, r in self.rows[-3:]]
-        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+            rows = self.rows[-3:]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "samples": 0}
+        mask = 0
+        for r in rows:
+            mask |= r[3]
+        reasons = sorted(name for bit, name in self.REASONS.items() if mask & bit)
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": max(r[2] for r in rows),
+                "reasons": reasons, "samples": len(rows), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------- reference arm

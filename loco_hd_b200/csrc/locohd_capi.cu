@@ -11,6 +11,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "locohd_kernels.cuh"
@@ -39,6 +40,11 @@ struct locohd_ctx {
     double* d_rsqrt_tbl = nullptr;
     int* d_err = nullptr;
     ScanStats* d_scan = nullptr;   // two slots: [0] anchor order, [1] environment sizes
+    // Large device buffers (environment stores, scratch) are recycled per context: the stream-ordered pool of the
+    // driver splits and re-merges multi-GB blocks unpredictably, which shows up as 30-60 ms stalls per call.
+    std::mutex cache_mu;
+    std::unordered_map<void*, size_t> big_live;           // big blocks handed out
+    std::vector<std::pair<size_t, void*>> big_free;       // big blocks ready for reuse (same stream: ordered)
     // per-kernel-group event timing
     bool prof_on = false;
     struct ProfRec { int group; cudaEvent_t a, b; };
@@ -152,19 +158,69 @@ const char* status_text(int code) {
     }
 }
 
-// Device allocations are stream-ordered on the context stream.
+// Device allocations are stream-ordered on the context stream; blocks of kBigBlock bytes and more are recycled
+// through the context's cache (best fit with at most 25 % slack).
+constexpr size_t kBigBlock = 16u << 20;
+constexpr size_t kBigCacheEntries = 32;
+
+int dev_alloc_bytes(locohd_ctx* ctx, void** out, size_t bytes) {
+    *out = nullptr;
+    if (bytes == 0) bytes = 1;
+    if (bytes >= kBigBlock) {
+        std::lock_guard<std::mutex> g(ctx->cache_mu);
+        int best = -1;
+        for (int i = 0; i < (int)ctx->big_free.size(); ++i) {
+            const size_t sz = ctx->big_free[i].first;
+            if (sz >= bytes && sz - bytes <= bytes / 4 && (best < 0 || sz < ctx->big_free[best].first)) best = i;
+        }
+        if (best >= 0) {
+            *out = ctx->big_free[best].second;
+            ctx->big_live[*out] = ctx->big_free[best].first;
+            ctx->big_free.erase(ctx->big_free.begin() + best);
+            return 0;
+        }
+    }
+    void* p = nullptr;
+    CU(ctx, cudaMallocAsync(&p, bytes, ctx->stream));
+    if (bytes >= kBigBlock) {
+        std::lock_guard<std::mutex> g(ctx->cache_mu);
+        ctx->big_live[p] = bytes;
+    }
+    *out = p;
+    return 0;
+}
+
+void dev_free_bytes(locohd_ctx* ctx, void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> g(ctx->cache_mu);
+        auto it = ctx->big_live.find(p);
+        if (it != ctx->big_live.end()) {
+            const size_t sz = it->second;
+            ctx->big_live.erase(it);
+            if (ctx->big_free.size() >= kBigCacheEntries) {   // drop the smallest cached block
+                size_t k = 0;
+                for (size_t i = 1; i < ctx->big_free.size(); ++i) if (ctx->big_free[i].first < ctx->big_free[k].first) k = i;
+                cudaFreeAsync(ctx->big_free[k].second, ctx->stream);
+                ctx->big_free.erase(ctx->big_free.begin() + k);
+            }
+            ctx->big_free.emplace_back(sz, p);
+            return;
+        }
+    }
+    cudaFreeAsync(p, ctx->stream);
+}
+
 template <class T>
 int dev_alloc(locohd_ctx* ctx, T** out, uint64_t n) {
-    *out = nullptr;
-    if (n == 0) n = 1;
     void* p = nullptr;
-    CU(ctx, cudaMallocAsync(&p, n * sizeof(T), ctx->stream));
+    const int st = dev_alloc_bytes(ctx, &p, (size_t)n * sizeof(T));
     *out = static_cast<T*>(p);
-    return 0;
+    return st;
 }
 template <class T>
 void dev_free(locohd_ctx* ctx, T*& p) {
-    if (p) cudaFreeAsync((void*)p, ctx->stream);
+    dev_free_bytes(ctx, (void*)p);
     p = nullptr;
 }
 
@@ -181,7 +237,7 @@ struct InBuf {
     locohd_ctx* ctx = nullptr;
     const T* ptr = nullptr;
     T* owned = nullptr;
-    ~InBuf() { if (owned) cudaFreeAsync(owned, ctx->stream); }
+    ~InBuf() { if (owned) dev_free_bytes(ctx, owned); }
     int load(locohd_ctx* c, const T* src, uint64_t n) {
         ctx = c;
         if (!src || n == 0) { ptr = nullptr; return 0; }
@@ -201,7 +257,7 @@ struct OutBuf {
     T* owned = nullptr;
     T* user = nullptr;
     uint64_t n = 0;
-    ~OutBuf() { if (owned) cudaFreeAsync(owned, ctx->stream); }
+    ~OutBuf() { if (owned) dev_free_bytes(ctx, owned); }
     int prepare(locohd_ctx* c, T* dst, uint64_t count) {
         ctx = c; user = dst; n = count;
         if (!dst) { ptr = nullptr; return 0; }
@@ -524,6 +580,9 @@ int locohd_ctx_create(int device, locohd_ctx** out) {
 void locohd_ctx_destroy(locohd_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& blk : ctx->big_free) cudaFreeAsync(blk.second, ctx->stream);
+    ctx->big_free.clear();
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_cat_w); cudaFree(ctx->d_cat_sw); cudaFree(ctx->d_wfs); cudaFree(ctx->d_tag_pairs);
     cudaFree(ctx->d_sqrt_tbl); cudaFree(ctx->d_rsqrt_tbl); cudaFree(ctx->d_err); cudaFree(ctx->d_scan);
