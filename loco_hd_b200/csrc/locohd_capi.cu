@@ -3,9 +3,11 @@
 // ordering and the launch sequence K0 -> K1 -> scan -> K1' -> K2.  No CPU fallback exists: every entry point
 // needs a CUDA device.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -35,11 +37,14 @@ struct locohd_ctx {
     double* d_cat_w = nullptr;
     double* d_cat_sw = nullptr;
     WfDev* d_wfs = nullptr;
+    WfDev h_wf0{};                 // host copy of weight function 0 (selects kernel specialisations)
     uint64_t* d_tag_pairs = nullptr;
     double* d_sqrt_tbl = nullptr;
     double* d_rsqrt_tbl = nullptr;
     int* d_err = nullptr;
     ScanStats* d_scan = nullptr;   // two slots: [0] anchor order, [1] environment sizes
+    FusedStats* d_fstats = nullptr;  // fused gather: store cursor, sample sum, largest environment, overflow word
+    int legacy_gather = 0;         // LOCOHD_LEGACY_GATHER=1: always use the multi-kernel gather (A/B runs)
     // Large device buffers (environment stores, scratch) are recycled per context: the stream-ordered pool of the
     // driver splits and re-merges multi-GB blocks unpredictably, which shows up as 30-60 ms stalls per call.
     std::mutex cache_mu;
@@ -52,6 +57,18 @@ struct locohd_ctx {
 };
 
 namespace {
+// LOCOHD_TRACE=1: host wall-clock of the phases of an environment build on stderr (development aid)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(false) { const char* v = std::getenv("LOCOHD_TRACE"); on = v && v[0] && v[0] != '0'; t0 = std::chrono::steady_clock::now(); }
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[locohd trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 // Brackets the launches issued in its scope with a pair of events when profiling is enabled.
 struct ProfScope {
     locohd_ctx* ctx;
@@ -80,6 +97,7 @@ struct locohd_structs {
     StructMeta* d_meta = nullptr;
     float4* d_pf = nullptr;
     PrimRec* d_pd = nullptr;
+    uint32_t* d_ptag = nullptr;
     uint32_t* d_sorted_pos = nullptr;
     uint32_t* d_cell_start = nullptr;
     uint32_t* d_cell_fill = nullptr;
@@ -88,7 +106,7 @@ struct locohd_structs {
     StructsView view() const {
         StructsView v;
         v.n_structs = n_structs; v.prim_off = d_prim_off; v.xyz = d_xyz; v.cat = d_cat; v.tag = d_tag;
-        v.meta = d_meta; v.pf = d_pf; v.pd = d_pd; v.sorted_pos = d_sorted_pos; v.cell_start = d_cell_start;
+        v.meta = d_meta; v.pf = d_pf; v.pd = d_pd; v.ptag = d_ptag; v.sorted_pos = d_sorted_pos; v.cell_start = d_cell_start;
         v.cell_fill = d_cell_fill;
         return v;
     }
@@ -406,6 +424,7 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
     if (!(threshold > 0.0))  // NaN included: nothing passes `d2 < r*r`, the reference then panics on dists[0]
         return fail(ctx, LOCOHD_ERR_EMPTY_ENV, "threshold_distance must be positive (got %g): every environment would be empty", threshold);
     if (n_anchors > 0xFFFFFFF0ull) return fail(ctx, LOCOHD_ERR_UNSUPPORTED, "more than 2^32 anchors in one call");
+    Trace tr;
     TRY_ST(ensure_cells(s, threshold));
     locohd_envset* e = new locohd_envset();
     e->ctx = ctx;
@@ -437,6 +456,67 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
         ProfScope ps(ctx, LOCOHD_PROF_OTHER);
         ctx->launches += launch_anchor_order(sv, ctx->kp, n_anchors, d_anchor_struct, d_anchor_prim, n_prims, d_slot_cnt,
                                              d_slot_off, d_scratch, ctx->d_scan, d_order, ctx->stream);
+    }
+    tr.mark("cells + order launched");
+    // ---- fused path: sample the sizes (every anchor for small calls), reserve the store, one kernel does the rest
+    if (!ctx->legacy_gather) {
+        const uint32_t stride = n_anchors <= 65536 ? 1u : 16u;
+        cudaMemsetAsync(ctx->d_fstats, 0, sizeof(FusedStats), ctx->stream);
+        {
+            ProfScope ps(ctx, LOCOHD_PROF_COUNT);
+            ctx->launches += launch_env_sample(sv, ctx->kp, n_anchors, d_order, d_anchor_struct, d_anchor_prim, threshold,
+                                               stride, &ctx->d_fstats->sample, ctx->stream);
+        }
+        FusedStats fs{};
+        if (cudaMemcpyAsync(&fs, ctx->d_fstats, sizeof fs, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            return bail(fail(ctx, LOCOHD_ERR_CUDA, "copy of the gather statistics failed"));
+        if ((st = sync_and_check(ctx))) return bail(st);
+        tr.mark("sample + sync");
+        const unsigned grid = fused_grid(ctx->kp, &ctx->h_wf0, e->key_is_w ? 1 : 0, keep_indices != 0, n_anchors);
+        // sampled sizes are FP32 upper bounds; even-rounding adds at most one entry per environment, every warp
+        // can leave most of a chunk unused at every refill and at the end
+        double est = (double)fs.sample * (double)stride;
+        if (stride > 1) est = est * 1.03 + 65536.0;
+        const double waste = 1.0 + (double)kFusedCap / (double)kFusedChunk;
+        uint64_t capacity = (uint64_t)((est + (double)n_anchors) * waste) + (uint64_t)grid * kFusedWarps * kFusedChunk + 2 * kFusedChunk;
+        // The sample differs a little from call to call (cell order depends on atomics): round the size up to 4
+        // significant bits so that repeated calls ask the block cache for the same size (a fresh multi-GB
+        // cudaMallocAsync costs 0.5-2 s).
+        for (uint64_t step = 1ull << 62; step >= 32; step >>= 1)
+            if (capacity & step) { step >>= 4; capacity = (capacity + step - 1) & ~(step - 1); break; }
+        tr.mark("grid + capacity");
+        if (tr.on) std::fprintf(stderr, "[locohd trace] capacity %llu entries, grid %u, cached blocks %zu\n",
+                                (unsigned long long)capacity, grid, ctx->big_free.size());
+        if ((st = dev_alloc(ctx, &e->d_key, capacity))) return bail(st);
+        if (keep_indices) {
+            if ((st = dev_alloc(ctx, &e->d_idx, capacity)) || (st = dev_alloc(ctx, &e->d_dist, capacity))) return bail(st);
+        }
+        tr.mark("store allocation");
+        EnvBuild b{};
+        b.n_env = n_anchors; b.order = d_order; b.ub = nullptr; b.off = nullptr; b.off_out = e->d_off; b.count = e->d_count;
+        b.key = e->d_key; b.cat = nullptr; b.idx = e->d_idx; b.dist = e->d_dist; b.key_is_w = e->key_is_w ? 1 : 0;
+        b.key_is_sq = 1; b.check_first_zero = 0;
+        {
+            ProfScope ps(ctx, LOCOHD_PROF_FILL);
+            ctx->launches += launch_env_fused(sv, ctx->kp, &ctx->h_wf0, d_anchor_struct, d_anchor_prim, threshold, b,
+                                              ctx->d_fstats, capacity, grid, ctx->stream);
+        }
+        cudaError_t ce = cudaGetLastError();
+        if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
+        if (cudaMemcpyAsync(&fs, ctx->d_fstats, sizeof fs, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            return bail(fail(ctx, LOCOHD_ERR_CUDA, "copy of the gather statistics failed"));
+        if ((st = sync_and_check(ctx))) return bail(st);
+        tr.mark("fused kernel + sync");
+        if (!fs.overflow) {
+            e->capacity = capacity;
+            e->total = fs.cursor < capacity ? fs.cursor : capacity;
+            e->max_count = fs.max_count;
+            release();
+            *out = e;
+            return 0;
+        }
+        // some environment did not fit the fused kernel: rebuild everything with the exact multi-kernel path
+        dev_free(ctx, e->d_key); dev_free(ctx, e->d_idx); dev_free(ctx, e->d_dist);
     }
     {
         ProfScope ps(ctx, LOCOHD_PROF_COUNT);
@@ -564,6 +644,11 @@ int locohd_ctx_create(int device, locohd_ctx** out) {
     if ((ce = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMemset(ctx->d_err, 0, sizeof(int))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMalloc(&ctx->d_scan, 2 * sizeof(ScanStats))) != cudaSuccess) return bail(ce);
+    if ((ce = cudaMalloc(&ctx->d_fstats, sizeof(FusedStats))) != cudaSuccess) return bail(ce);
+    {
+        const char* lg = std::getenv("LOCOHD_LEGACY_GATHER");
+        ctx->legacy_gather = (lg && lg[0] && lg[0] != '0') ? 1 : 0;
+    }
     if ((ce = cudaMalloc(&ctx->d_sqrt_tbl, kSqrtTableSize * sizeof(double))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMalloc(&ctx->d_rsqrt_tbl, kSqrtTableSize * sizeof(double))) != cudaSuccess) return bail(ce);
     std::vector<double> t(kSqrtTableSize), r(kSqrtTableSize);
@@ -586,6 +671,7 @@ void locohd_ctx_destroy(locohd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_cat_w); cudaFree(ctx->d_cat_sw); cudaFree(ctx->d_wfs); cudaFree(ctx->d_tag_pairs);
     cudaFree(ctx->d_sqrt_tbl); cudaFree(ctx->d_rsqrt_tbl); cudaFree(ctx->d_err); cudaFree(ctx->d_scan);
+    cudaFree(ctx->d_fstats);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -707,6 +793,7 @@ int locohd_ctx_set_params(locohd_ctx* ctx, const locohd_params* params) {
     CU(ctx, cudaMemcpy(ctx->d_cat_w, w.data(), C * sizeof(double), cudaMemcpyHostToDevice));
     CU(ctx, cudaMemcpy(ctx->d_cat_sw, sw.data(), C * sizeof(double), cudaMemcpyHostToDevice));
     CU(ctx, cudaMemcpy(ctx->d_wfs, wfs.data(), wfs.size() * sizeof(WfDev), cudaMemcpyHostToDevice));
+    ctx->h_wf0 = wfs[0];
     if (!pairs.empty()) {
         CU(ctx, cudaMalloc(&ctx->d_tag_pairs, pairs.size() * sizeof(uint64_t)));
         CU(ctx, cudaMemcpy(ctx->d_tag_pairs, pairs.data(), pairs.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
@@ -767,7 +854,8 @@ int locohd_structs_create(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* p
     if ((st = dev_alloc(ctx, &s->d_prim_off, n_structs + 1)) || (st = dev_alloc(ctx, &s->d_xyz, 3 * n)) ||
         (st = dev_alloc(ctx, &s->d_cat, n)) || (st = dev_alloc(ctx, &s->d_tag, n)) ||
         (st = dev_alloc(ctx, &s->d_meta, n_structs)) || (st = dev_alloc(ctx, &s->d_pf, n)) ||
-        (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_sorted_pos, n)) ||
+        (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_ptag, n)) ||
+        (st = dev_alloc(ctx, &s->d_sorted_pos, n)) ||
         (st = dev_alloc(ctx, &s->d_cell_start, cell_entries(n, n_structs))) ||
         (st = dev_alloc(ctx, &s->d_cell_fill, cell_entries(n, n_structs))))
         return bail(st);
@@ -793,7 +881,8 @@ void locohd_structs_destroy(locohd_structs* s) {
     locohd_ctx* ctx = s->ctx;
     DeviceGuard g(ctx->device);
     dev_free(ctx, s->d_prim_off); dev_free(ctx, s->d_xyz); dev_free(ctx, s->d_cat); dev_free(ctx, s->d_tag);
-    dev_free(ctx, s->d_meta); dev_free(ctx, s->d_pf); dev_free(ctx, s->d_pd); dev_free(ctx, s->d_sorted_pos);
+    dev_free(ctx, s->d_meta); dev_free(ctx, s->d_pf); dev_free(ctx, s->d_pd); dev_free(ctx, s->d_ptag);
+    dev_free(ctx, s->d_sorted_pos);
     dev_free(ctx, s->d_cell_start); dev_free(ctx, s->d_cell_fill);
     delete s;
 }
@@ -1091,7 +1180,8 @@ int locohd_from_primitives(locohd_ctx* ctx, uint64_t n_a, const double* xyz_a, c
     if ((st = dev_alloc(ctx, &s->d_prim_off, 3)) || (st = dev_alloc(ctx, &s->d_xyz, 3 * n)) ||
         (st = dev_alloc(ctx, &s->d_cat, n)) || (st = dev_alloc(ctx, &s->d_tag, n)) ||
         (st = dev_alloc(ctx, &s->d_meta, 2)) || (st = dev_alloc(ctx, &s->d_pf, n)) ||
-        (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_sorted_pos, n)) ||
+        (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_ptag, n)) ||
+        (st = dev_alloc(ctx, &s->d_sorted_pos, n)) ||
         (st = dev_alloc(ctx, &s->d_cell_start, cell_entries(n, 2))) ||
         (st = dev_alloc(ctx, &s->d_cell_fill, cell_entries(n, 2))))
         return cleanup(st);

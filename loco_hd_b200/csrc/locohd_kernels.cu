@@ -21,6 +21,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 namespace locohd {
 
@@ -204,7 +205,10 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
         if ((long long)m.nx * m.ny * m.nz > max_cells) { inv_cell = 0.0; m.nx = m.ny = m.nz = 1; }
         m.ox = lo[0]; m.oy = lo[1]; m.oz = lo[2];
         m.inv_cell = inv_cell;
-        const double span = threshold * inv_cell * (1.0 + 1e-6);  // radius in cells
+        // radius in cells.  A member lies less than `span` cells from its anchor along every axis, the anchor sits
+        // at a fractional position < 1 inside its own cell, so the cell index differs by at most floor(span) + 1;
+        // the default edge (r / 2 * (1 + 1e-6)) gives span = 1.999998 -> reach 2 (5 x 5 rows of 5 cells).
+        const double span = threshold * inv_cell * (1.0 + 1e-9);   // 1e-9: rounding of the product near an integer
         m.reach = (inv_cell > 0.0 && isfinite(span)) ? (int)fmin(span, 2.0e6) + 1 : 0;
         if (inv_cell == 0.0) m.reach = 0;
         // FP32 prefilter: relative coordinates are rounded to f32 (error <= emax * 2^-24 each); the bound below
@@ -215,7 +219,21 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
         float tf = (t2 < 3.0e38) ? (float)t2 : INFINITY;
         if (isfinite(tf)) tf = nextafterf(tf, INFINITY);
         m.thr2f = tf;
-        m.pad[0] = m.pad[1] = m.pad[2] = 0;
+        // Row pruning of the fused gather works on the f32 relative coordinates.  A cell edge evaluated in f32
+        // ((float)index * cellf) and an f32 coordinate are each within 2.5e-7 * (emax + cell + r) =: D of the exact
+        // values, so a row that holds a member has a y-z gap below r + 2 D, and the x half-width
+        // sqrt((r + 2 D)^2 - gap^2) covers the member ("row pruning").
+        if (inv_cell > 0.0 && isfinite(threshold) && isfinite(emax)) {
+            const double cell = 1.0 / inv_cell;
+            const double D = 2.5e-7 * (emax + cell + threshold) * 1.001;
+            const double pr = (threshold + 2.0 * D) * (1.0 + 1e-5);
+            m.cellf = (float)cell;
+            m.inv_cellf = (float)inv_cell;
+            m.prune_r = (pr < 1.0e18) ? nextafterf((float)pr, INFINITY) : 0.f;
+            if (!(m.prune_r > 0.f) || !isfinite(m.cellf) || !isfinite(m.inv_cellf)) { m.cellf = 0.f; m.prune_r = 0.f; }
+        } else {
+            m.cellf = 0.f; m.inv_cellf = 0.f; m.prune_r = 0.f;
+        }
         sm_meta = m;
         s.meta[sid] = m;
         sh_carry = 0;
@@ -266,6 +284,7 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
         r.orig = i;
         r.cat = s.cat[base + i];
         s.pd[base + pos] = r;
+        s.ptag[base + pos] = s.tag[base + i];
         s.pf[base + pos] = make_float4((float)(x - m.ox), (float)(y - m.oy), (float)(z - m.oz),
                                        __uint_as_float(s.tag[base + i]));
         s.sorted_pos[base + i] = pos;
@@ -350,15 +369,18 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
                                                                 const uint32_t* __restrict__ anchor_struct,
                                                                 const uint32_t* __restrict__ anchor_prim,
                                                                 double threshold, uint32_t* __restrict__ ub,
-                                                                EnvBuild b) {
+                                                                EnvBuild b, uint32_t stride,
+                                                                unsigned long long* sample_sum) {
+    // stride > 1 (count mode only): every stride-th anchor is visited and the sizes are summed into *sample_sum
     const int tid = threadIdx.x;
-    const uint64_t t = (uint64_t)blockIdx.x * kTileThreads + tid;
+    const uint64_t t = ((uint64_t)blockIdx.x * kTileThreads + tid) * stride;
     bool active = t < n_env;
     const uint64_t e = active ? order[t] : 0;
     uint64_t base = 0;
     uint32_t jpos = 0;
     StructMeta m;
     m.nx = m.ny = m.nz = 1; m.reach = 0; m.inv_cell = 0.0; m.ox = m.oy = m.oz = 0.0; m.thr2f = 0.f;
+    m.cellf = m.prune_r = m.inv_cellf = 0.f;
     const uint32_t* cell_start = s.cell_start;
     if (active) {
         const uint64_t sid = anchor_struct ? anchor_struct[e] : 0;
@@ -445,11 +467,442 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
             if (cnt > cap) raise(p.err, LOCOHD_ERR_CUDA);  // the FP32 count is an upper bound by construction
             b.count[e] = min(cnt, cap);
         }
+    } else if (sample_sum) {
+        unsigned v = active ? cnt : 0u;
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if ((tid & 31) == 0 && v) atomicAdd(sample_sum, (unsigned long long)v);
     } else if (active) {
         ub[e] = cnt;
     } else if (t < n_env) {
         ub[e] = 0;
     }
+}
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// f64 bits of W (or of the distance) with the low mantissa byte replaced by the category
+__device__ __forceinline__ uint64_t pack_key(double w, uint32_t cat) {
+    w = w + 0.0;                 // -0.0 -> +0.0
+    w = fmax(w, 0.0);            // a CDF that rounds to a tiny negative value must not set the sign bit
+    return ((uint64_t)__double_as_longlong(w) & ~kCatMask) | (uint64_t)(cat & 0xFFu);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 (fused): one persistent WARP per anchor does the whole of env_from_idx (locohd.rs:514-542) in one pass:
+//   rows      lane r < 25 owns one of the (2 reach + 1)^2 <= 25 candidate rows of the anchor (reach <= 2 always:
+//             cells are never smaller than r / 2): rows farther than r in the y-z plane are dropped, the x range of
+//             the others is cut to sqrt(r^2 - gap^2), in f32 with conservative margins (build_cells_kernel)
+//   gather    lanes over the flat concatenation of the rows (coalesced 32-byte records, the next round is loaded
+//             while the current one is tested); the row of a flat index comes from one REDUX.OR of the row-start
+//             bits + popc, no search loop.  Exact membership: the kd-tree crate's predicate in FP64 with unfused
+//             arithmetic (as env_tile_kernel<true>) + tag rule; members are ballot-compacted into shared memory:
+//             squared distance, category and a 32-bit sort key = 23-bit fixed-point squared distance << 9 | slot.
+//             (No FP32 prefilter here: with a warp per anchor every lane tests a different candidate, the FP64
+//             instructions are issued once per round either way.)
+//   sort      warp bitonic network on the 32-bit keys in registers (4, 8 or 16 per lane; min/max and shuffles, no
+//             shared-memory atomics; stages run as loops to keep the code small), then neighbours with equal
+//             fixed-point distance are checked against the exact values (rare serial repair)
+//   store     sqrt (utils.rs:1-8), CDF (specialised by WFK), key packing; coalesced stores into a chunk of the store
+//             the warp reserved with one atomicAdd per kFusedChunk entries.
+// Environments that do not fit (more than kFusedCap members, store exhausted) raise the overflow word: the host
+// then rebuilds the call with the exact multi-kernel path.
+// ------------------------------------------------------------------------------------------------
+template <bool DEBUG>
+struct FusedLayout {
+    static constexpr int kD2Off = 0;                                    // f64 [CAP] exact squared distances
+    static constexpr int kKeyOff = kD2Off + 8 * kFusedCap;              // u32 [CAP] sort keys
+    static constexpr int kRowOff = kKeyOff + 4 * kFusedCap;             // i32 [32] row delta (start - flat prefix)
+    static constexpr int kCatOff = kRowOff + 4 * 32;                    // u8 [CAP]
+    static constexpr int kIdxOff = kCatOff + kFusedCap;                 // u32 [CAP] (DEBUG)
+    static constexpr int kBytes = (kIdxOff + (DEBUG ? 4 * kFusedCap : 0) + 15) & ~15;
+};
+
+// ascending compare-exchange of two registers of one lane
+__device__ __forceinline__ void cex(uint32_t& a, uint32_t& c) {
+    const uint32_t lo = min(a, c), hi = max(a, c);
+    a = lo;
+    c = hi;
+}
+
+// Ascending bitonic sort of 32 * PER distinct keys, element g = lane * PER + r, in the formulation whose first stage
+// of every merge compares g with g ^ (size - 1) (mirror) and the others g with g ^ stride: every compare-exchange
+// puts the smaller key at the lower index, so in-lane stages are plain min / max pairs and a cross-lane exchange is
+// SHFL + ISETP.XOR + SEL (keep mine iff (mine < other) != I-am-the-upper-lane).  Merges that span lanes run as
+// (not unrolled) loops to keep the code small.
+template <int PER>
+__device__ __forceinline__ void warp_bitonic(uint32_t (&k)[PER], int lane) {
+    // merges inside a lane: static network
+#pragma unroll
+    for (int size = 2; size <= PER; size <<= 1) {
+#pragma unroll
+        for (int r = 0; r < PER; ++r)
+            if ((r & (size >> 1)) == 0) cex(k[r], k[r ^ (size - 1)]);
+#pragma unroll
+        for (int stride = size >> 2; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int r = 0; r < PER; ++r)
+                if ((r & stride) == 0) cex(k[r], k[r | stride]);
+        }
+    }
+    // merges across lanes: lsz = lanes per merged run
+#pragma unroll 1
+    for (int lsz = 2; lsz <= 32; lsz <<= 1) {
+        {   // mirror stage: element r of this lane meets element PER - 1 - r of lane ^ (lsz - 1)
+            const bool upper = (lane & (lsz >> 1)) != 0;
+            uint32_t x[PER];
+#pragma unroll
+            for (int r = 0; r < PER; ++r) x[r] = __shfl_xor_sync(kFull, k[PER - 1 - r], lsz - 1);
+#pragma unroll
+            for (int r = 0; r < PER; ++r) k[r] = ((k[r] < x[r]) != upper) ? k[r] : x[r];
+        }
+#pragma unroll 1
+        for (int lm = lsz >> 2; lm > 0; lm >>= 1) {
+            const bool upper = (lane & lm) != 0;
+#pragma unroll
+            for (int r = 0; r < PER; ++r) {
+                const uint32_t x = __shfl_xor_sync(kFull, k[r], lm);
+                k[r] = ((k[r] < x) != upper) ? k[r] : x;
+            }
+        }
+#pragma unroll
+        for (int stride = PER >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int r = 0; r < PER; ++r)
+                if ((r & stride) == 0) cex(k[r], k[r | stride]);
+        }
+    }
+}
+
+template <int PER>
+__device__ __noinline__ void fused_sort(uint32_t* key32, uint32_t M, int lane) {
+    uint32_t k[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const uint32_t g = (uint32_t)(lane * PER + r);
+        k[r] = (g < M) ? key32[g] : 0xFFFFFFFFu;
+    }
+    __syncwarp();
+    warp_bitonic<PER>(k, lane);
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        const uint32_t g = (uint32_t)(lane * PER + r);
+        if (g < M) key32[g] = k[r];
+    }
+    __syncwarp();
+}
+
+// serial repair of groups with equal fixed-point distance (order by exact squared distance, category, slot)
+__device__ __noinline__ void fused_repair(uint32_t* key32, const double* d2s, const uint8_t* cats, uint32_t M) {
+    for (uint32_t g = 1; g < M; ++g) {
+        const uint32_t kg = key32[g];
+        const uint32_t sg = kg & 511u;
+        const double dg = d2s[sg];
+        const uint32_t cg = cats[sg];
+        uint32_t u = g;
+        while (u > 0) {
+            const uint32_t kf = key32[u - 1];
+            if ((kf >> 9) != (kg >> 9)) break;
+            const uint32_t sf = kf & 511u;
+            const double df = d2s[sf];
+            const uint32_t cf = cats[sf];
+            if (df < dg || (df == dg && (cf < cg || (cf == cg && sf < sg)))) break;
+            key32[u] = kf;
+            --u;
+        }
+        key32[u] = kg;
+    }
+}
+
+// WFK: 0 uniform, 1 kumaraswamy with small integer exponents, 2 anything else (wf_cdf, or plain distances)
+template <int WFK>
+__device__ __forceinline__ double fused_weight(const WfDev& wf, double d, int key_is_w) {
+    if (WFK == 0) {
+        const double z = (d - wf.p[0]) * wf.inv_range;
+        return (d < wf.p[0]) ? 0.0 : ((d > wf.p[1]) ? 1.0 : z);
+    } else if (WFK == 1) {
+        const double z = (d - wf.p[0]) * wf.inv_range;
+        const double u = 1.0 - powi_small(z, wf.int_a);
+        const double v = 1.0 - powi_small(u, wf.int_b);
+        return (d < wf.p[0]) ? 0.0 : ((d > wf.p[1]) ? 1.0 : v);
+    } else {
+        return key_is_w ? wf_cdf(wf, d) : d;
+    }
+}
+
+// Distance from the exact squared distance.  Parity dumps (EXACT) take the IEEE square root; otherwise the value only
+// feeds W(d) / the packed key, and MUFU.RSQ (f32 seed) + two coupled Newton steps in FP64 (~1e-16 relative, a third of
+// the instructions) is used inside the f32 exponent range.
+template <bool EXACT>
+__device__ __forceinline__ double fused_distance(double d2) {
+    if (EXACT) return sqrt(d2);
+    const float f = (float)d2;
+    if (!(f > 1e-30f && f < 1e30f)) return sqrt(d2);
+    const double g = (double)rsqrt_approx(f);
+    double sq = d2 * g, hh = 0.5 * g;
+    double r = fma(-sq, hh, 0.5);
+    sq = fma(sq, r, sq); hh = fma(hh, r, hh);
+    r = fma(-sq, hh, 0.5);
+    return fma(sq, r, sq);
+}
+
+template <int WFK, bool DEBUG>
+__global__ void __launch_bounds__(kFusedWarps * 32) env_fused_kernel(StructsView s, KParams p, uint64_t n_env,
+                                                                     const uint32_t* __restrict__ order,
+                                                                     const uint32_t* __restrict__ anchor_struct,
+                                                                     const uint32_t* __restrict__ anchor_prim,
+                                                                     double threshold, EnvBuild b, FusedStats* stats,
+                                                                     uint64_t capacity) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using L = FusedLayout<DEBUG>;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char* smem = smem_raw + (size_t)wib * L::kBytes;
+    double* d2s = reinterpret_cast<double*>(smem + L::kD2Off);
+    uint32_t* key32 = reinterpret_cast<uint32_t*>(smem + L::kKeyOff);
+    int* row_delta = reinterpret_cast<int*>(smem + L::kRowOff);
+    uint8_t* cats = smem + L::kCatOff;
+    uint32_t* sidx = reinterpret_cast<uint32_t*>(smem + L::kIdxOff);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned le_mask = lt_mask | (1u << lane);
+
+    const double r2 = __dmul_rn(threshold, threshold);
+    const bool r2_finite = isfinite(r2);
+    const double qscale = r2_finite ? 8388592.0 / r2 : 0.0;   // (2^23 - 16) / r^2: d2 < r2 -> key < 2^23 - 15
+    const bool simple_rule = p.tpr_kind == LOCOHD_TPR_WITHOUT_LIST;
+    const bool accept_same = p.tpr_accept_same != 0;
+    const WfDev& wf = p.wfs[0];
+    const bool fix_monotone = (WFK == 2) && b.key_is_w && !wf.monotone;
+    uint64_t chunk_pos = 0, chunk_end = 0;   // warp-uniform: the reserved part of the store
+    unsigned max_m = 0;
+
+    // every CTA takes a contiguous block of the cell-ordered anchors: consecutive rounds read overlapping
+    // candidate rows (L1 hits)
+    uint64_t per_block = (n_env + gridDim.x - 1) / gridDim.x;
+    per_block = (per_block + kFusedWarps - 1) / kFusedWarps * kFusedWarps;
+    const uint64_t t_end = min(n_env, (uint64_t)(blockIdx.x + 1) * per_block);
+#pragma unroll 1
+    for (uint64_t t = (uint64_t)blockIdx.x * per_block + wib; t < t_end; t += kFusedWarps) {
+        __syncwarp();
+        const uint64_t e = order[t];
+        const uint64_t sid = anchor_struct ? anchor_struct[e] : 0;
+        const uint32_t prim = anchor_prim[e];
+        if (sid >= s.n_structs || prim >= s.prim_off[sid + 1] - s.prim_off[sid]) {   // locohd.rs:521 panics
+            if (lane == 0) { raise(p.err, LOCOHD_ERR_INDEX); b.count[e] = 0; b.off_out[e] = 0; }
+            continue;
+        }
+        const uint64_t base = s.prim_off[sid];
+        const uint32_t jpos = s.sorted_pos[base + prim];
+        const StructMeta m = s.meta[sid];
+        const uint32_t* cell_start = s.cell_start + cell_base(base, sid);
+        const PrimRec* pd = s.pd + base;
+        const PrimRec q = pd[jpos];
+        const float4 qf = __ldg(s.pf + base + jpos);
+        const uint32_t qtag = __float_as_uint(qf.w);
+        if (m.reach > 2) {   // cannot happen (cells are never smaller than r / 2); leave it to the multi-kernel path
+            if (lane == 0) { atomicOr(&stats->overflow, 2u); b.count[e] = 0; b.off_out[e] = 0; }
+            continue;
+        }
+
+        // ---- candidate rows: lane r < W * W owns row (dy, dz)
+        uint32_t my_len = 0, my_pre = 0;
+        {
+            const int W = 2 * m.reach + 1;
+            const int cx = cell_coord(q.x - m.ox, m.inv_cell, m.nx);
+            const int cy = cell_coord(q.y - m.oy, m.inv_cell, m.ny);
+            const int cz = cell_coord(q.z - m.oz, m.inv_cell, m.nz);
+            uint32_t start = 0;
+            if (lane < W * W) {
+                const int dzi = (lane * 13) >> 6;   // lane / 5 for lane < 25
+                const int dz5 = (W == 5) ? dzi : ((W == 3) ? (lane * 11) >> 5 : 0);   // lane / W
+                const int dyi = lane - dz5 * W - m.reach, dzz = dz5 - m.reach;
+                const int yy = cy + dyi, zz = cz + dzz;
+                if (yy >= 0 && yy < m.ny && zz >= 0 && zz < m.nz) {
+                    int x0 = max(cx - m.reach, 0), x1 = min(cx + m.reach, m.nx - 1);
+                    bool keep = true;
+                    if (m.prune_r > 0.f) {
+                        float gy = 0.f, gz = 0.f;
+                        if (dyi > 0) gy = (float)yy * m.cellf - qf.y;
+                        else if (dyi < 0) gy = qf.y - (float)(yy + 1) * m.cellf;
+                        if (dzz > 0) gz = (float)zz * m.cellf - qf.z;
+                        else if (dzz < 0) gz = qf.z - (float)(zz + 1) * m.cellf;
+                        gy = fmaxf(gy, 0.f); gz = fmaxf(gz, 0.f);
+                        const float h2 = m.prune_r * m.prune_r - (gy * gy + gz * gz);
+                        if (h2 < 0.f) keep = false;
+                        else {
+                            const float hx = sqrtf(h2) * 1.00001f;
+                            const float lo = (qf.x - hx) * m.inv_cellf - 2e-3f, hi = (qf.x + hx) * m.inv_cellf + 2e-3f;
+                            x0 = max(x0, (int)floorf(fmaxf(lo, 0.f)));
+                            x1 = min(x1, (int)fminf(hi, 2.0e6f));
+                        }
+                    }
+                    if (keep && x0 <= x1) {
+                        const int row = (zz * m.ny + yy) * m.nx;
+                        start = __ldg(cell_start + row + x0);
+                        my_len = __ldg(cell_start + row + x1 + 1) - start;
+                    }
+                }
+            }
+            uint32_t incl = my_len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += v;
+            }
+            my_pre = incl - my_len;
+            const unsigned nonempty = __ballot_sync(kFull, my_len > 0);
+            if (my_len > 0) row_delta[__popc(nonempty & lt_mask)] = (int)start - (int)my_pre;
+        }
+        const uint32_t T = __shfl_sync(kFull, my_pre + my_len, 31);
+        __syncwarp();
+
+        // ---- candidates: lanes over the flat concatenation of the rows; exact membership with the kd-tree crate's
+        //      predicate (unfused FP64, as env_tile_kernel<true>) + tag rule; members ballot-compacted.
+        //      The record of the next round is requested before the current one is tested.
+        const double qmax = fmax(fmax(fabs(q.x), fabs(q.y)), fmax(fabs(q.z), threshold));
+        const double r_safe = threshold - 8.9e-16 * (qmax + threshold);
+        const double r2_safe = (r_safe > 0.0 && isfinite(r_safe)) ? r_safe * r_safe * (1.0 - 1e-15) : (isinf(threshold) ? r2 : 0.0);
+        uint32_t M = 0;
+        {
+            int row_base = -1;   // compacted row of the last candidate of the previous round
+            // flat index -> cell-sorted position; one REDUX.OR of the row-start bits, no search
+            auto locate = [&](uint32_t i0) -> uint32_t {
+                const uint32_t dpos = my_pre - i0;   // does my row start inside this round?
+                const unsigned bit = (my_len > 0 && dpos < 32u) ? (1u << dpos) : 0u;
+                const unsigned starts = __reduce_or_sync(kFull, bit);
+                const int row = row_base + __popc(starts & le_mask);
+                row_base += __popc(starts);
+                const uint32_t i = i0 + lane;
+                return (i < T) ? (uint32_t)((int)i + row_delta[row]) : 0xFFFFFFFFu;
+            };
+            // one round: 32 candidates, one per lane
+            auto test = [&](uint32_t j, const PrimRec& r, uint32_t rtag) {
+                bool acc = false;
+                double d2 = 0.0;
+                if (j != 0xFFFFFFFFu) {
+                    const double ex = r.x - q.x, ey = r.y - q.y, ez = r.z - q.z;
+                    d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+                    acc = d2 < r2;
+                    if (acc && !(d2 < r2_safe)) {
+                        // within rounding distance of the sphere: the crate's per-axis box test can still reject
+                        acc = !(r.x < q.x - threshold) && !(r.x > q.x + threshold) && !(r.y < q.y - threshold) &&
+                              !(r.y > q.y + threshold) && !(r.z < q.z - threshold) && !(r.z > q.z + threshold);
+                    }
+                    if (simple_rule) acc = acc && (((rtag == qtag) == accept_same) || j == jpos);
+                    else if (acc && j != jpos) acc = tag_rule_accepts(p, qtag, rtag);
+                }
+                const unsigned mask = __ballot_sync(kFull, acc);
+                if (acc) {
+                    const uint32_t slot = M + __popc(mask & lt_mask);
+                    if (slot < (uint32_t)kFusedCap) {
+                        d2s[slot] = d2;
+                        cats[slot] = (uint8_t)r.cat;
+                        key32[slot] = ((uint32_t)(d2 * qscale) << 9) | slot;
+                        if (DEBUG) sidx[slot] = r.orig;
+                    }
+                }
+                M += __popc(mask);
+            };
+            // two rounds per iteration: both records are requested before either is tested
+#pragma unroll 1
+            for (uint32_t i0 = 0; i0 < T; i0 += 64) {
+                const uint32_t j0 = locate(i0);
+                const uint32_t j1 = (i0 + 32 < T) ? locate(i0 + 32) : 0xFFFFFFFFu;
+                PrimRec r0, r1;
+                uint32_t t0 = 0, t1 = 0;
+                r0.x = r0.y = r0.z = 0.0; r0.orig = 0; r0.cat = 0;
+                r1 = r0;
+                if (j0 != 0xFFFFFFFFu) { r0 = pd[j0]; t0 = __ldg(s.ptag + base + j0); }
+                if (j1 != 0xFFFFFFFFu) { r1 = pd[j1]; t1 = __ldg(s.ptag + base + j1); }
+                test(j0, r0, t0);
+                if (i0 + 32 < T) test(j1, r1, t1);
+            }
+        }
+        __syncwarp();
+        if (M > (uint32_t)kFusedCap) {
+            if (lane == 0) { atomicOr(&stats->overflow, 8u); b.count[e] = 0; b.off_out[e] = 0; }
+            continue;
+        }
+        if (M == 0) {   // cannot happen for r > 0 (the anchor is a member); keep the store consistent anyway
+            if (lane == 0) { b.count[e] = 0; b.off_out[e] = 0; }
+            continue;
+        }
+        if (!r2_finite) {   // infinite radius: fixed-point scale from the data
+            double dmax = 0.0;
+            for (uint32_t g = lane; g < M; g += 32) { const double v = d2s[g]; if (isfinite(v)) dmax = fmax(dmax, v); }
+            for (int o = 16; o; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
+            const double sc = dmax > 0.0 ? 8388592.0 / dmax : 0.0;
+            for (uint32_t g = lane; g < M; g += 32) {
+                const double v = d2s[g];
+                const uint32_t qv = isfinite(v) ? (uint32_t)(v * sc) : 8388600u;
+                key32[g] = (qv << 9) | g;
+            }
+            __syncwarp();
+        }
+
+        // ---- sort
+        if (M <= 128) fused_sort<4>(key32, M, lane);
+        else if (M <= 256) fused_sort<8>(key32, M, lane);
+        else fused_sort<16>(key32, M, lane);
+        {   // equal fixed-point distances: order by the exact (distance, category)
+            bool viol = false;
+            for (uint32_t g = lane; g + 1 < M; g += 32) {
+                const uint32_t ka = key32[g], kb = key32[g + 1];
+                if ((ka >> 9) == (kb >> 9)) {
+                    const uint32_t sa = ka & 511u, sb = kb & 511u;
+                    const double da = d2s[sa], db = d2s[sb];
+                    viol |= (da > db) || (da == db && cats[sa] > cats[sb]);
+                }
+            }
+            if (__any_sync(kFull, viol)) {
+                if (lane == 0) fused_repair(key32, d2s, cats, M);
+                __syncwarp();
+            }
+        }
+
+        // ---- reserve the store range
+        const uint32_t Mpad = (M + 1u) & ~1u;
+        if (chunk_pos + Mpad > chunk_end) {
+            unsigned long long got = 0;
+            if (lane == 0) got = atomicAdd(&stats->cursor, (unsigned long long)kFusedChunk);
+            got = __shfl_sync(kFull, got, 0);
+            chunk_pos = got; chunk_end = got + kFusedChunk;
+        }
+        if (chunk_end > capacity) {
+            if (lane == 0) { atomicOr(&stats->overflow, 1u); b.count[e] = 0; b.off_out[e] = 0; }
+            continue;
+        }
+        const uint64_t off = chunk_pos;
+        chunk_pos += Mpad;
+        max_m = max(max_m, M);
+
+        // ---- sqrt, CDF, packing, coalesced store
+        uint64_t carry = 0;
+        for (uint32_t g0 = 0; g0 < Mpad; g0 += 32) {
+            const uint32_t g = g0 + lane;
+            uint64_t packed = 0;
+            if (g < M) {
+                const uint32_t slot = key32[g] & 511u;
+                const double d = fused_distance<DEBUG>(d2s[slot]);   // utils.rs:1-8
+                packed = pack_key(fused_weight<WFK>(wf, d, b.key_is_w), cats[slot]);
+                if (DEBUG) { b.dist[off + g] = d; b.idx[off + g] = sidx[slot]; }
+            }
+            if (fix_monotone) {
+                uint64_t wbits = packed & ~kCatMask;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint64_t v = __shfl_up_sync(kFull, wbits, o);
+                    if (lane >= o) wbits = max(wbits, v);
+                }
+                wbits = max(wbits, carry);
+                carry = __shfl_sync(kFull, wbits, 31);
+                if (g < M) packed = wbits | (packed & kCatMask);
+            }
+            if (g < Mpad) b.key[off + g] = packed;
+        }
+        if (lane == 0) { b.off_out[e] = off; b.count[e] = M; }
+    }
+    if (lane == 0 && max_m) atomicMax(&stats->max_count, max_m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -472,12 +925,6 @@ struct SortLayout {
     static constexpr int kCatOff = kPermOff + 2 * CAP;          // u8 [CAP]
     static constexpr int kBytes = (kCatOff + CAP + 15) & ~15;
 };
-
-__device__ __forceinline__ uint64_t pack_key(double w, uint32_t cat) {
-    w = w + 0.0;                 // -0.0 -> +0.0
-    w = fmax(w, 0.0);            // a CDF that rounds to a tiny negative value must not set the sign bit
-    return ((uint64_t)__double_as_longlong(w) & ~kCatMask) | (uint64_t)(cat & 0xFFu);
-}
 
 template <int CAP, bool DEBUG>
 __global__ void __launch_bounds__(kSortWarps * 32) env_sort_kernel(KParams p, EnvBuild b, uint32_t min_m,
@@ -945,6 +1392,16 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
 constexpr double kSmallH2 = 1e-8;
 constexpr int kRefresh = 64;
 
+// sqrt of a double in [1e-8, ~1]: MUFU.RSQ (f32) seed + one coupled Newton step in FP64, relative error
+// 1.5 * 2^-44 = 8.5e-14.  Used for H itself (nothing amplifies the error; bar 1e-9 on the score); IEEE sqrt costs
+// ~30 instructions per event, this one 7.
+__device__ __forceinline__ double sqrt_unit(double v) {
+    const double g = (double)rsqrt_approx((float)v);
+    const double s0 = v * g;
+    const double r = fma(-s0, 0.5 * g, 0.5);
+    return fma(s0, r, s0);
+}
+
 template <int CP, bool KEY_IS_W, bool CHECK>
 __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreArgs a, KParams P, int warps_per_block,
                                                                          int per_warp_bytes) {
@@ -1068,9 +1525,9 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
         };
         auto stat_dist = [&]() -> double {
             if (mism == 0) return 0.0;                       // identical counts: exactly 0
-            double h2 = fma(-__dmul_rn(rA, rB), D, 1.0);
-            if (h2 < kSmallH2) h2 = exact_h2();
-            return sqrt(h2);
+            const double h2 = fma(-__dmul_rn(rA, rB), D, 1.0);
+            if (h2 < kSmallH2) return sqrt(exact_h2());
+            return sqrt_unit(h2);
         };
         rebuild();
 
@@ -1302,8 +1759,77 @@ int launch_env_count(const StructsView& s, const KParams& p, uint64_t n_env, con
                      cudaStream_t st) {
     if (!n_env) return 0;
     EnvBuild none{};
-    env_tile_kernel<false><<<blocks_for(n_env, kTileThreads), kTileThreads, 0, st>>>(s, p, n_env, order, anchor_struct,
-                                                                                    anchor_prim, threshold, ub, none);
+    env_tile_kernel<false><<<blocks_for(n_env, kTileThreads), kTileThreads, 0, st>>>(
+        s, p, n_env, order, anchor_struct, anchor_prim, threshold, ub, none, 1u, nullptr);
+    return 1;
+}
+
+int launch_env_sample(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* order,
+                      const uint32_t* anchor_struct, const uint32_t* anchor_prim, double threshold, uint32_t stride,
+                      unsigned long long* sum, cudaStream_t st) {
+    if (!n_env) return 0;
+    EnvBuild none{};
+    const uint64_t n_vis = (n_env + stride - 1) / stride;
+    env_tile_kernel<false><<<blocks_for(n_vis, kTileThreads), kTileThreads, 0, st>>>(
+        s, p, n_env, order, anchor_struct, anchor_prim, threshold, nullptr, none, stride, sum);
+    return 1;
+}
+
+// WFK of a parameter block: 0 uniform, 1 integer-exponent kumaraswamy, 2 generic / plain distances
+static int fused_wfk(const KParams& p, const WfDev* host_wf, int key_is_w) {
+    (void)p;
+    if (!key_is_w || !host_wf) return 2;
+    if (host_wf->kind == LOCOHD_WF_UNIFORM) return 0;
+    if (host_wf->kind == LOCOHD_WF_KUMARASWAMY && host_wf->int_a >= 0 && host_wf->int_b >= 0) return 1;
+    return 2;
+}
+
+template <int WFK, bool DEBUG>
+static unsigned fused_grid_t(uint64_t n_env) {
+    const int smem = FusedLayout<DEBUG>::kBytes * kFusedWarps;
+    cudaFuncSetAttribute(env_fused_kernel<WFK, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_fused_kernel<WFK, DEBUG>, kFusedWarps * 32, smem);
+    if (occ < 1) occ = 1;
+    const uint64_t need = (n_env + kFusedWarps - 1) / kFusedWarps;
+    const uint64_t cap = (uint64_t)sms * occ;
+    return (unsigned)(need < cap ? need : cap);
+}
+
+template <int WFK, bool DEBUG>
+static void fused_launch_t(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
+                           const uint32_t* anchor_prim, double threshold, const EnvBuild& b, FusedStats* stats,
+                           uint64_t capacity, unsigned grid, cudaStream_t st) {
+    const int smem = FusedLayout<DEBUG>::kBytes * kFusedWarps;
+    env_fused_kernel<WFK, DEBUG><<<grid, kFusedWarps * 32, smem, st>>>(s, p, b.n_env, b.order, anchor_struct,
+                                                                       anchor_prim, threshold, b, stats, capacity);
+}
+
+unsigned fused_grid(const KParams& p, const WfDev* host_wf, int key_is_w, bool debug, uint64_t n_env) {
+    switch (fused_wfk(p, host_wf, key_is_w) * 2 + (debug ? 1 : 0)) {
+        case 0: return fused_grid_t<0, false>(n_env);
+        case 1: return fused_grid_t<0, true>(n_env);
+        case 2: return fused_grid_t<1, false>(n_env);
+        case 3: return fused_grid_t<1, true>(n_env);
+        case 4: return fused_grid_t<2, false>(n_env);
+        default: return fused_grid_t<2, true>(n_env);
+    }
+}
+
+int launch_env_fused(const StructsView& s, const KParams& p, const WfDev* host_wf, const uint32_t* anchor_struct,
+                     const uint32_t* anchor_prim, double threshold, const EnvBuild& b, FusedStats* stats,
+                     uint64_t capacity, unsigned grid, cudaStream_t st) {
+    if (!b.n_env) return 0;
+    switch (fused_wfk(p, host_wf, b.key_is_w) * 2 + (b.idx ? 1 : 0)) {
+        case 0: fused_launch_t<0, false>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
+        case 1: fused_launch_t<0, true>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
+        case 2: fused_launch_t<1, false>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
+        case 3: fused_launch_t<1, true>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
+        case 4: fused_launch_t<2, false>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
+        default: fused_launch_t<2, true>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
+    }
     return 1;
 }
 
@@ -1311,7 +1837,7 @@ int launch_env_fill(const StructsView& s, const KParams& p, const uint32_t* anch
                     double threshold, const EnvBuild& b, cudaStream_t st) {
     if (!b.n_env) return 0;
     env_tile_kernel<true><<<blocks_for(b.n_env, kTileThreads), kTileThreads, 0, st>>>(
-        s, p, b.n_env, b.order, anchor_struct, anchor_prim, threshold, nullptr, b);
+        s, p, b.n_env, b.order, anchor_struct, anchor_prim, threshold, nullptr, b, 1u, nullptr);
     return 1;
 }
 
@@ -1423,6 +1949,7 @@ int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsign
         if (stage > 2048u) stage = 2048u;
         if (stage > pad_max) stage = pad_max;
     }
+    int n = 0;
     // tables: counts never exceed the environment sizes
     unsigned need = (max_a > max_b ? max_a : max_b) + 2u;
     bool check = false;
@@ -1438,7 +1965,6 @@ int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsign
     if (warps > kScoreMaxWarps) warps = kScoreMaxWarps;
     if (warps < 1) warps = 1;
     const int smem = tables + per_warp * warps;
-    int n = 0;
     if (CP == 8) n += key_is_w ? launch_fast<8, true>(a, p, check, warps, per_warp, smem, st)
                                : launch_fast<8, false>(a, p, check, warps, per_warp, smem, st);
     else n += key_is_w ? launch_fast<16, true>(a, p, check, warps, per_warp, smem, st)

@@ -25,7 +25,9 @@ struct __align__(16) StructMeta {
     int nx, ny, nz;
     int reach;           // neighbour cells to visit on each side (2 for the default half-radius cells)
     float thr2f;         // conservative squared radius for the FP32 prefilter
-    int pad[3];
+    float cellf;         // cell edge as f32 (0: a single cell, no row pruning)
+    float prune_r;       // row pruning (fused gather): conservative radius in the f32 relative coordinates
+    float inv_cellf;     // 1 / cell edge as f32
 };
 
 // Kernel-visible parameter block of one LoCoHD instance (LoCoHD struct, locohd.rs:42-55).
@@ -60,6 +62,7 @@ struct StructsView {
     StructMeta* meta;             // [n_structs]
     float4* pf;                   // cell-sorted: (x - ox, y - oy, z - oz) as f32, w = tag bits
     PrimRec* pd;                  // cell-sorted exact records
+    uint32_t* ptag;               // cell-sorted tag ids (fused gather)
     uint32_t* sorted_pos;         // original index -> cell-sorted position (inside the structure)
     uint32_t* cell_start;         // [cell_entries]: first cell-sorted position of every cell
     uint32_t* cell_fill;          // [cell_entries]: scratch cursor of the counting sort
@@ -81,11 +84,24 @@ struct ScanStats {  // written by the scan kernels, read back by the host
     unsigned int pad;
 };
 
+// fused gather (env_fused_kernel)
+constexpr int kFusedWarps = 4;      // warps per CTA, one anchor per warp at a time
+constexpr int kFusedCap = 512;      // members per environment
+constexpr int kFusedChunk = 2048;   // store entries a warp reserves with one atomicAdd
+
+struct FusedStats {  // written by env_fused_kernel, read back by the host
+    unsigned long long cursor;     // store entries handed out (multiple of kFusedChunk)
+    unsigned long long sample;     // sum of the sampled upper-bound sizes (env_tile_kernel<false> with a stride)
+    unsigned int max_count;        // largest environment
+    unsigned int overflow;         // != 0: some environment did not fit -> rebuild with the multi-kernel path
+};
+
 struct EnvBuild {
     uint64_t n_env;
     const uint32_t* order;    // environments in cell order of their anchors
     const uint32_t* ub;       // FP32-prefilter upper bound of every environment size
     const uint64_t* off;      // exclusive scan of the (even-rounded) upper bounds
+    uint64_t* off_out;        // fused gather: store offset of every environment (written by the kernel)
     uint32_t* count;          // exact sizes (written by the fill kernel)
     uint64_t* key;            // store: plain distances (f64 bits) until the sort kernel packs them
     uint8_t* cat;             // categories of the unsorted members (scratch)
@@ -126,6 +142,17 @@ int launch_scan(const uint32_t* values, uint64_t n, int round_even, uint64_t* of
 int launch_env_count(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* order,
                      const uint32_t* anchor_struct, const uint32_t* anchor_prim, double threshold, uint32_t* ub,
                      cudaStream_t st);
+// sum of the upper-bound sizes of every stride-th anchor (in cell order) -> *sum
+int launch_env_sample(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* order,
+                      const uint32_t* anchor_struct, const uint32_t* anchor_prim, double threshold, uint32_t stride,
+                      unsigned long long* sum, cudaStream_t st);
+// fused gather + sort + pack: grid from fused_grid(); the store needs room for the members plus one kFusedChunk per
+// warp of the grid
+// host_wf: host copy of weight function 0 (selects the CDF specialisation)
+unsigned fused_grid(const KParams& p, const WfDev* host_wf, int key_is_w, bool debug, uint64_t n_env);
+int launch_env_fused(const StructsView& s, const KParams& p, const WfDev* host_wf, const uint32_t* anchor_struct,
+                     const uint32_t* anchor_prim, double threshold, const EnvBuild& b, FusedStats* stats,
+                     uint64_t capacity, unsigned grid, cudaStream_t st);
 int launch_env_fill(const StructsView& s, const KParams& p, const uint32_t* anchor_struct, const uint32_t* anchor_prim,
                     double threshold, const EnvBuild& b, cudaStream_t st);
 // sorts every environment of the store in place and packs the keys; max_count bounds the environment sizes

@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 from loco_hd_b200 import synth
-from helpers import SCORE_TOL, assert_scores_close, check_from_primitives, random_cloud, set_both
+from helpers import (SCORE_TOL, assert_scores_close, canonical_env, check_from_primitives, random_cloud,
+                     set_both)
 
 pytestmark = pytest.mark.gpu
 
@@ -376,3 +377,50 @@ def test_symmetry_and_permutation_invariance(gpu_ctx, oracle_mod):
     s_p = gpu_ctx.from_primitives(a.xyz[perm], a.cat[perm], a.tag[perm], b.xyz, b.cat, b.tag, anchors_p, 10.0)
     assert np.abs(s_ab - s_p).max() <= 1e-12
     assert s_ab.min() >= 0.0 and s_ab.max() <= 1.0
+
+
+# ------------------------------------------------------------------------------- fused gather vs multi-kernel gather
+def _dump_env(ctx, S, anchors, thr):
+    st = ctx.structure(*S)
+    env = ctx.envset_build(st, anchors, thr, keep_indices=True)
+    out = env.dump()
+    env.close()
+    st.close()
+    return out
+
+
+@pytest.mark.parametrize("case", ["protein10", "cloud50", "sparse_anchors", "inf_small", "f32"])
+def test_fused_gather_matches_multi_kernel_gather(oracle_mod, case, monkeypatch):
+    """env_fused_kernel (one warp per anchor: gather + exact test + register sort + packing) and the multi-kernel
+    path (count / scan / fill / bucket sort) must produce the same environments: sizes, categories, distances and
+    - up to the order inside groups of equal (distance, category) - primitive indices."""
+    from loco_hd_b200 import _capi
+    rng = np.random.default_rng(77)
+    if case == "protein10":
+        a = synth.gen(31, 400, 8, 7)
+        S, anchors, thr, C = (a.xyz, a.cat, a.tag), np.arange(a.n, dtype=np.uint32), 10.0, 7
+    elif case == "cloud50":
+        S, anchors, thr, C = random_cloud(rng, 300, 5, n_tags=40), np.arange(300, dtype=np.uint32), 50.0, 5
+    elif case == "sparse_anchors":
+        a = synth.gen(33, 300, 9, 8)
+        S, anchors, thr, C = (a.xyz, a.cat, a.tag), np.arange(0, a.n, 9, dtype=np.uint32)[::-1].copy(), 7.5, 8
+    elif case == "inf_small":
+        S, anchors, thr, C = random_cloud(rng, 200, 4), np.arange(0, 200, 3, dtype=np.uint32), float("inf"), 4
+    else:
+        a = synth.gen(35, 250, 8, 7, f32_exact=True)
+        S, anchors, thr, C = (a.xyz, a.cat, a.tag), np.arange(a.n, dtype=np.uint32), 10.0, 7
+    outs = []
+    for legacy in ("0", "1"):
+        monkeypatch.setenv("LOCOHD_LEGACY_GATHER", legacy)
+        ctx = _capi.Context(0)
+        ctx.set_params(C, [("kumaraswamy", (3.0, 10.0, 2.0, 5.0))], tag_rule={"accept_same": False})
+        outs.append(_dump_env(ctx, S, anchors, thr))
+        ctx.close()
+    (off0, d0, c0, i0), (off1, d1, c1, i1) = outs
+    assert np.array_equal(off0, off1)
+    assert np.array_equal(d0, d1), "sorted distances differ"
+    assert np.array_equal(c0, c1), "categories differ"
+    for p in range(len(anchors)):
+        a0, _ = canonical_env(i0[off0[p]:off0[p + 1]], d0[off0[p]:off0[p + 1]])
+        a1, _ = canonical_env(i1[off1[p]:off1[p + 1]], d1[off1[p]:off1[p + 1]])
+        assert np.array_equal(a0, a1), f"members differ for anchor {p}"
