@@ -388,13 +388,20 @@ def run_gpu(args, rank, local_rank, world):
     fp64_peak = ctx.measure_fp64_tflops()
     kernels = {g: {"ms_per_step": ms / args.steps, "share": ms / max(sum(v[0] for v in prof.values()), 1e-9)}
                for g, (ms, n) in prof.items() if n}
-    # Algorithmic flops per kernel: walk E * (10 C + 4 + F_wf) -> K2; of the 10 flops per
-    # environment member 9 (3 sub, 3 mul, 2 add, 1 compare) belong to the exact gather K1b and 1 (sqrt) to the sort
-    # K1c; the FP32 upper-bound pass K1a does no algorithmic FP64 work (its 7 FP32 flops per candidate are overhead).
-    alg = {"score": ("score_fast_kernel / score_kernel (K2 merge walk)", f_walk),
-           "fill": ("env_tile_kernel<true> (K1b exact gather)", 0.9 * f_gather),
-           "sort": ("env_sort_kernel (K1c sort + CDF + packing)", 0.1 * f_gather),
-           "count": ("env_tile_kernel<false> (K1a FP32 upper-bound sizes)", 0.0)}
+    # Algorithmic flops per kernel: walk E * (10 C + 4 + F_wf) -> K2; the 10 flops per environment
+    # member (3 sub, 3 mul, 2 add, 1 compare, 1 sqrt) all belong to the fused gather K1; the sampled upper-bound
+    # pass does no algorithmic FP64 work.  With LOCOHD_LEGACY_GATHER=1 the multi-kernel path runs instead (9 of the
+    # 10 in the exact fill K1b, the sqrt in the sort K1c).
+    if "sort" in kernels:
+        alg = {"score": ("score_fast_kernel / score_kernel (K2 merge walk)", f_walk),
+               "fill": ("env_tile_kernel<true> (K1b exact gather, multi-kernel path)", 0.9 * f_gather),
+               "sort": ("env_sort_kernel (K1c sort + CDF + packing, multi-kernel path)", 0.1 * f_gather),
+               "count": ("env_tile_kernel<false> (K1a FP32 upper-bound sizes)", 0.0)}
+    else:
+        alg = {"score": ("score_fast_kernel / score_kernel (K2 merge walk)", f_walk),
+               "fill": ("env_fused_kernel (K1: row pruning, exact FP64 gather, register bitonic sort, CDF, packing)",
+                        f_gather),
+               "count": ("env_tile_kernel<false> with stride 16 (store sizing sample)", 0.0)}
     traffic = {}
     try:
         tr = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
@@ -457,7 +464,7 @@ def run_gpu(args, rank, local_rank, world):
         "config": {"workload": wl.desc, "anchor_pairs_per_gpu_per_step": wl.n_pairs,
                    "environments_per_gpu_per_step": n_env,
                    "l2": f"inputs larger than L2 each step: {wl.h2d_bytes / 1e6:.0f} MB of structures/anchors + "
-                         f"{9 * float(sizes.sum()) / 1e6:.0f} MB environment store streamed per step"},
+                         f"{8 * float(sizes.sum()) / 1e6:.0f} MB environment store written and read per step"},
         "e2e": {"value": e2e_value, "unit": "anchor-pairs/s", "h2d_bytes_per_step": int(wl.h2d_bytes),
                 "d2h_bytes_per_step": int(8 * wl.n_pairs), "steps": e2e_steps,
                 "scores_identical_to_resident_run": e2e_ok},

@@ -193,24 +193,30 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
         double inv_cell = 2.0 / (threshold * (1.0 + 1e-6));
         if (!(inv_cell > 0.0) || !isfinite(inv_cell)) inv_cell = 0.0;  // infinite radius: a single cell
         StructMeta m;
+        int xf = 4;   // x refinement: x cells of r / 8 as long as the grid stays within its bounds
         for (int it = 0; it < 200; ++it) {
-            m.nx = (int)fmin(ext[0] * inv_cell, 1.0e6) + 1;
+            m.nx = (int)fmin(ext[0] * inv_cell * xf, 1.0e6) + 1;
             m.ny = (int)fmin(ext[1] * inv_cell, 1.0e6) + 1;
             m.nz = (int)fmin(ext[2] * inv_cell, 1.0e6) + 1;
             if ((long long)m.nx * m.ny * m.nz <= max_cells && m.nx <= kMaxCellsAxis && m.ny <= kMaxCellsAxis &&
                 m.nz <= kMaxCellsAxis)
                 break;
-            inv_cell *= 0.8;
+            if (xf > 1) xf >>= 1; else inv_cell *= 0.8;
         }
-        if ((long long)m.nx * m.ny * m.nz > max_cells) { inv_cell = 0.0; m.nx = m.ny = m.nz = 1; }
+        if ((long long)m.nx * m.ny * m.nz > max_cells) { inv_cell = 0.0; xf = 1; m.nx = m.ny = m.nz = 1; }
+        const double inv_cell_x = inv_cell * xf;
         m.ox = lo[0]; m.oy = lo[1]; m.oz = lo[2];
         m.inv_cell = inv_cell;
+        m.inv_cell_x = inv_cell_x;
         // radius in cells.  A member lies less than `span` cells from its anchor along every axis, the anchor sits
         // at a fractional position < 1 inside its own cell, so the cell index differs by at most floor(span) + 1;
         // the default edge (r / 2 * (1 + 1e-6)) gives span = 1.999998 -> reach 2 (5 x 5 rows of 5 cells).
         const double span = threshold * inv_cell * (1.0 + 1e-9);   // 1e-9: rounding of the product near an integer
         m.reach = (inv_cell > 0.0 && isfinite(span)) ? (int)fmin(span, 2.0e6) + 1 : 0;
         if (inv_cell == 0.0) m.reach = 0;
+        const double span_x = threshold * inv_cell_x * (1.0 + 1e-9);
+        m.reach_x = (inv_cell_x > 0.0 && isfinite(span_x)) ? (int)fmin(span_x, 2.0e6) + 1 : 0;
+        m.pad[0] = m.pad[1] = m.pad[2] = 0;
         // FP32 prefilter: relative coordinates are rounded to f32 (error <= emax * 2^-24 each); the bound below
         // is generous (see DESIGN.md "prefilter margin").
         const double delta = 4.0 * emax * 5.9604644775390625e-8;
@@ -228,11 +234,11 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
             const double D = 2.5e-7 * (emax + cell + threshold) * 1.001;
             const double pr = (threshold + 2.0 * D) * (1.0 + 1e-5);
             m.cellf = (float)cell;
-            m.inv_cellf = (float)inv_cell;
+            m.inv_cellxf = (float)inv_cell_x;
             m.prune_r = (pr < 1.0e18) ? nextafterf((float)pr, INFINITY) : 0.f;
-            if (!(m.prune_r > 0.f) || !isfinite(m.cellf) || !isfinite(m.inv_cellf)) { m.cellf = 0.f; m.prune_r = 0.f; }
+            if (!(m.prune_r > 0.f) || !isfinite(m.cellf) || !isfinite(m.inv_cellxf)) { m.cellf = 0.f; m.prune_r = 0.f; }
         } else {
-            m.cellf = 0.f; m.inv_cellf = 0.f; m.prune_r = 0.f;
+            m.cellf = 0.f; m.inv_cellxf = 0.f; m.prune_r = 0.f;
         }
         sm_meta = m;
         s.meta[sid] = m;
@@ -247,7 +253,7 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
     // ---- histogram (global atomics: the grid can be larger than shared memory)
     for (uint32_t i = tid; i < n; i += kCellThreads) {
         const double x = xyz[3 * (uint64_t)i], y = xyz[3 * (uint64_t)i + 1], z = xyz[3 * (uint64_t)i + 2];
-        const int cx = cell_coord(x - m.ox, m.inv_cell, m.nx);
+        const int cx = cell_coord(x - m.ox, m.inv_cell_x, m.nx);
         const int cy = cell_coord(y - m.oy, m.inv_cell, m.ny);
         const int cz = cell_coord(z - m.oz, m.inv_cell, m.nz);
         atomicAdd(&cell_start[(cz * m.ny + cy) * m.nx + cx], 1u);
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
     // ---- scatter into cell order
     for (uint32_t i = tid; i < n; i += kCellThreads) {
         const double x = xyz[3 * (uint64_t)i], y = xyz[3 * (uint64_t)i + 1], z = xyz[3 * (uint64_t)i + 2];
-        const int cx = cell_coord(x - m.ox, m.inv_cell, m.nx);
+        const int cx = cell_coord(x - m.ox, m.inv_cell_x, m.nx);
         const int cy = cell_coord(y - m.oy, m.inv_cell, m.ny);
         const int cz = cell_coord(z - m.oz, m.inv_cell, m.nz);
         const uint32_t pos = atomicAdd(&cell_fill[(cz * m.ny + cy) * m.nx + cx], 1u);
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
     uint32_t jpos = 0;
     StructMeta m;
     m.nx = m.ny = m.nz = 1; m.reach = 0; m.inv_cell = 0.0; m.ox = m.oy = m.oz = 0.0; m.thr2f = 0.f;
-    m.cellf = m.prune_r = m.inv_cellf = 0.f;
+    m.cellf = m.prune_r = m.inv_cellxf = 0.f; m.inv_cell_x = 0.0; m.reach_x = 0;
     const uint32_t* cell_start = s.cell_start;
     if (active) {
         const uint64_t sid = anchor_struct ? anchor_struct[e] : 0;
@@ -401,10 +407,10 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
     if (active) { q = s.pd[base + jpos]; qf = s.pf[base + jpos]; }
     const uint32_t qtag = __float_as_uint(qf.w);
     const double r2 = __dmul_rn(threshold, threshold);
-    const int cx = cell_coord(q.x - m.ox, m.inv_cell, m.nx);
+    const int cx = cell_coord(q.x - m.ox, m.inv_cell_x, m.nx);
     const int cy = cell_coord(q.y - m.oy, m.inv_cell, m.ny);
     const int cz = cell_coord(q.z - m.oz, m.inv_cell, m.nz);
-    const int x0 = max(cx - m.reach, 0), x1 = min(cx + m.reach, m.nx - 1);
+    const int x0 = max(cx - m.reach_x, 0), x1 = min(cx + m.reach_x, m.nx - 1);
     int reach = active ? m.reach : 0;
     for (int o = 16; o; o >>= 1) reach = max(reach, __shfl_xor_sync(kFull, reach, o));   // warp-uniform loop bounds
 
@@ -649,7 +655,7 @@ __device__ __forceinline__ double fused_distance(double d2) {
 }
 
 template <int WFK, bool DEBUG>
-__global__ void __launch_bounds__(kFusedWarps * 32) env_fused_kernel(StructsView s, KParams p, uint64_t n_env,
+__global__ void __launch_bounds__(kFusedWarps * 32, 8) env_fused_kernel(StructsView s, KParams p, uint64_t n_env,
                                                                      const uint32_t* __restrict__ order,
                                                                      const uint32_t* __restrict__ anchor_struct,
                                                                      const uint32_t* __restrict__ anchor_prim,
@@ -709,7 +715,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32) env_fused_kernel(StructsView
         uint32_t my_len = 0, my_pre = 0;
         {
             const int W = 2 * m.reach + 1;
-            const int cx = cell_coord(q.x - m.ox, m.inv_cell, m.nx);
+            const int cx = cell_coord(q.x - m.ox, m.inv_cell_x, m.nx);
             const int cy = cell_coord(q.y - m.oy, m.inv_cell, m.ny);
             const int cz = cell_coord(q.z - m.oz, m.inv_cell, m.nz);
             uint32_t start = 0;
@@ -719,7 +725,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32) env_fused_kernel(StructsView
                 const int dyi = lane - dz5 * W - m.reach, dzz = dz5 - m.reach;
                 const int yy = cy + dyi, zz = cz + dzz;
                 if (yy >= 0 && yy < m.ny && zz >= 0 && zz < m.nz) {
-                    int x0 = max(cx - m.reach, 0), x1 = min(cx + m.reach, m.nx - 1);
+                    int x0 = max(cx - m.reach_x, 0), x1 = min(cx + m.reach_x, m.nx - 1);
                     bool keep = true;
                     if (m.prune_r > 0.f) {
                         float gy = 0.f, gz = 0.f;
@@ -732,7 +738,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32) env_fused_kernel(StructsView
                         if (h2 < 0.f) keep = false;
                         else {
                             const float hx = sqrtf(h2) * 1.00001f;
-                            const float lo = (qf.x - hx) * m.inv_cellf - 2e-3f, hi = (qf.x + hx) * m.inv_cellf + 2e-3f;
+                            const float lo = (qf.x - hx) * m.inv_cellxf - 2e-3f, hi = (qf.x + hx) * m.inv_cellxf + 2e-3f;
                             x0 = max(x0, (int)floorf(fmaxf(lo, 0.f)));
                             x1 = min(x1, (int)fminf(hi, 2.0e6f));
                         }

@@ -21,13 +21,17 @@ struct __align__(32) PrimRec {
 // Per-structure cell grid (built for one threshold).
 struct __align__(16) StructMeta {
     double ox, oy, oz;   // grid origin = bounding-box minimum
-    double inv_cell;     // 1 / cell edge (cell edge >= threshold / 2 * (1 + 1e-6))
+    double inv_cell;     // 1 / cell edge along y and z (cell edge >= threshold / 2 * (1 + 1e-6))
     int nx, ny, nz;
-    int reach;           // neighbour cells to visit on each side (2 for the default half-radius cells)
+    int reach;           // neighbour cells to visit on each side along y and z (at most 2)
     float thr2f;         // conservative squared radius for the FP32 prefilter
     float cellf;         // cell edge as f32 (0: a single cell, no row pruning)
     float prune_r;       // row pruning (fused gather): conservative radius in the f32 relative coordinates
-    float inv_cellf;     // 1 / cell edge as f32
+    float inv_cellxf;    // 1 / x cell edge as f32
+    double inv_cell_x;   // 1 / x cell edge: cells are up to 4 times finer along x (the fastest axis), which costs no
+                         // extra rows and lets the gather cut every row close to the sphere
+    int reach_x;         // neighbour cells along x
+    int pad[3];
 };
 
 // Kernel-visible parameter block of one LoCoHD instance (LoCoHD struct, locohd.rs:42-55).
