@@ -622,17 +622,23 @@ __device__ __noinline__ void fused_repair(uint32_t* key32, const double* d2s, co
     }
 }
 
-// WFK: 0 uniform, 1 kumaraswamy with small integer exponents, 2 anything else (wf_cdf, or plain distances)
+// WFK: 0 uniform, 1 kumaraswamy with small integer exponents, 2 anything else (wf_cdf, or plain distances).
+// The parameters of variants 0 and 1 are read once per kernel into registers (FusedWf): left in global memory the
+// compiler reloads them in every round of the store loop (they may alias the stores) and the loop waits on them.
+struct FusedWf {
+    double p0, p1, inv_range;
+    int int_a, int_b;
+};
 template <int WFK>
-__device__ __forceinline__ double fused_weight(const WfDev& wf, double d, int key_is_w) {
+__device__ __forceinline__ double fused_weight(const WfDev& wf, const FusedWf& f, double d, int key_is_w) {
     if (WFK == 0) {
-        const double z = (d - wf.p[0]) * wf.inv_range;
-        return (d < wf.p[0]) ? 0.0 : ((d > wf.p[1]) ? 1.0 : z);
+        const double z = (d - f.p0) * f.inv_range;
+        return (d < f.p0) ? 0.0 : ((d > f.p1) ? 1.0 : z);
     } else if (WFK == 1) {
-        const double z = (d - wf.p[0]) * wf.inv_range;
-        const double u = 1.0 - powi_small(z, wf.int_a);
-        const double v = 1.0 - powi_small(u, wf.int_b);
-        return (d < wf.p[0]) ? 0.0 : ((d > wf.p[1]) ? 1.0 : v);
+        const double z = (d - f.p0) * f.inv_range;
+        const double u = 1.0 - powi_small(z, f.int_a);
+        const double v = 1.0 - powi_small(u, f.int_b);
+        return (d < f.p0) ? 0.0 : ((d > f.p1) ? 1.0 : v);
     } else {
         return key_is_w ? wf_cdf(wf, d) : d;
     }
@@ -679,7 +685,10 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 8) env_fused_kernel(StructsV
     const bool simple_rule = p.tpr_kind == LOCOHD_TPR_WITHOUT_LIST;
     const bool accept_same = p.tpr_accept_same != 0;
     const WfDev& wf = p.wfs[0];
+    FusedWf fwf;
+    fwf.p0 = wf.p[0]; fwf.p1 = wf.p[1]; fwf.inv_range = wf.inv_range; fwf.int_a = wf.int_a; fwf.int_b = wf.int_b;
     const bool fix_monotone = (WFK == 2) && b.key_is_w && !wf.monotone;
+    const int key_is_w = b.key_is_w;
     uint64_t chunk_pos = 0, chunk_end = 0;   // warp-uniform: the reserved part of the store
     unsigned max_m = 0;
 
@@ -891,7 +900,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 8) env_fused_kernel(StructsV
             if (g < M) {
                 const uint32_t slot = key32[g] & 511u;
                 const double d = fused_distance<DEBUG>(d2s[slot]);   // utils.rs:1-8
-                packed = pack_key(fused_weight<WFK>(wf, d, b.key_is_w), cats[slot]);
+                packed = pack_key(fused_weight<WFK>(wf, fwf, d, key_is_w), cats[slot]);
                 if (DEBUG) { b.dist[off + g] = d; b.idx[off + g] = sidx[slot]; }
             }
             if (fix_monotone) {
@@ -1799,6 +1808,7 @@ static unsigned fused_grid_t(uint64_t n_env) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_fused_kernel<WFK, DEBUG>, kFusedWarps * 32, smem);
     if (occ < 1) occ = 1;
+    if (const char* v = std::getenv("LOCOHD_FUSED_CTAS")) { const int c = std::atoi(v); if (c >= 1 && c < occ) occ = c; }
     const uint64_t need = (n_env + kFusedWarps - 1) / kFusedWarps;
     const uint64_t cap = (uint64_t)sms * occ;
     return (unsigned)(need < cap ? need : cap);

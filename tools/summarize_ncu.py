@@ -35,15 +35,15 @@ units = rows[1]
 ki = hdr.index("Kernel Name")
 kernels = rows[2:]
 out = [f"# {tag} — ncu `--set full --clock-control none` on B200 ({note})", "",
-       "Command: `ncu --set full --clock-control none --import-source on -k regex:\"env_tile_kernel|env_sort_kernel|"
-       "score_fast_kernel\" -s 15 -c 5 python bench.py --steps 1 --warmup 3 --no-cpu-baseline`",
+       "Command: `ncu --set full --clock-control none --import-source on -k regex:\"env_fused|score_fast|env_tile|"
+       "build_cells\" -s 8 -c 4 python bench.py --steps 1 --warmup 3 --no-cpu-baseline`",
        "(default workload: 256 structure pairs of config-2 shape = 5.12 M environments, 2.56 M anchor pairs per launch)", ""]
 names = [short(r[ki]) for r in kernels]
 out.append("| metric | " + " | ".join(names) + " |")
 out.append("|---|" + "---|" * len(names))
 traffic = {}
-group = {"env_tile_kernel<0>": "count", "env_tile_kernel<1>": "fill", "env_sort_kernel<256, 0>": "sort",
-         "score_fast_kernel": "score"}
+group = {"env_tile_kernel<0>": "count", "env_tile_kernel<1>": "fill", "env_fused_kernel": "fill",
+         "env_sort_kernel<256, 0>": "sort", "score_fast_kernel": "score", "build_cells_kernel": "cells"}
 for m, label in metrics:
     if m not in hdr:
         continue
@@ -55,7 +55,8 @@ for r, n in zip(kernels, names):
     b = float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
     for k, g in group.items():
         if n.startswith(k) or k in n:
-            traffic[g] = traffic.get(g, 0.0) + b
+            traffic.setdefault(g, b)   # one launch per group (the capture holds one step)
+            break
 lf = ROOT / "gpurun_out" / f"{tag}_launches.csv"
 if lf.exists():
     lr = [r for r in csv.reader(open(lf)) if len(r) > 10]
@@ -70,8 +71,9 @@ if lf.exists():
         agg[short(r[k2])][0] += 1
         agg[short(r[k2])][1] += v
     tot = sum(v[1] for k, v in agg.items() if "fp64_peak" not in k)
-    out += ["", "Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, 5 steps incl. warm-up + the "
-            "e2e passes; cold-cache serialised times — compare shares):", "",
+    out += ["", "Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 ... bench.py --steps 2 "
+            "--warmup 3 --no-cpu-baseline`: warm-up, timed, work-count and e2e passes; cold-cache serialised times — "
+            "compare shares):", "",
             "| kernel | launches | total ms | share |", "|---|---|---|---|"]
     for n, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
         if "fp64_peak" in n:
