@@ -10,7 +10,9 @@ contacts only, every primitive an anchor; `--pairs` structure pairs per GPU per 
 
     value  whole-job throughput with the structures already resident in HBM (CUDA events on the library stream)
     e2e    same metric through the C-ABI call sequence with HOST (pinned) buffers: H2D of the structures and
-           anchors and D2H of the scores inside the timed region (wall clock between synchronisations)
+           anchors and D2H of the scores inside the timed region (wall clock between synchronisations); measured
+           with one host thread (steps back to back) and with two host threads / contexts (the copies of one step
+           overlap the kernels of the other); `e2e.value` is the better of the two, both are in the line
 
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/, all host threads; the Rust crate
 cannot be built in this image) on a bounded sample of the same workload.
@@ -123,7 +125,7 @@ class ClockSampler:
 
     def __init__(self, device):
         self.rows, self.stop_flag, self.nvml, self.proc = [], False, None, None
-        self.period = float(os.environ.get("LOCOHD_BENCH_CLOCK_PERIOD", "0.2"))
+        self.period = float(os.environ.get("LOCOHD_BENCH_CLOCK_PERIOD", "0.05"))
         try:
             import pynvml
 
@@ -352,14 +354,14 @@ def run_gpu(args, rank, local_rank, world):
     h_ap = ctx.pinned_array(wl.anchor_prim.shape, np.uint32); h_ap[...] = wl.anchor_prim
     h_out = ctx.pinned_array((wl.n_pairs,), np.float64)
 
-    def step_e2e():
-        st = ctx.structs_create(h_off, h_xyz, h_cat, h_tag)
-        env = ctx.envset_build(st, h_ap, wl.threshold, anchor_struct=h_as)
-        ctx.score_jobs(env, env, wl.jobs, out=h_out)
+    def step_e2e(c=ctx, out=h_out):
+        st = c.structs_create(h_off, h_xyz, h_cat, h_tag)
+        env = c.envset_build(st, h_ap, wl.threshold, anchor_struct=h_as)
+        c.score_jobs(env, env, wl.jobs, out=out)
         env.close()
         st.close()
 
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 6)) // 2 * 2
     for _ in range(2):
         step_e2e()
     ctx.synchronize()
@@ -368,9 +370,41 @@ def run_gpu(args, rank, local_rank, world):
     for _ in range(e2e_steps):
         step_e2e()
     ctx.synchronize()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = total_pairs * e2e_steps / t_e2e
+    t_serial = max_over_ranks(time.perf_counter() - t0)
+    e2e_serial = total_pairs * e2e_steps / t_serial
     e2e_ok = bool(np.array_equal(h_out, check_scores))
+
+    # The same calls from two host threads, each with its own context (= stream) and output buffer: the H2D copies
+    # of one step overlap the kernels of the other.  Every step still uploads its inputs from pinned host memory
+    # and reads its scores back inside the timed region.
+    ctx2 = _capi.Context(local_rank)
+    ctx2.set_params(wl.C, [wl.wf], tag_rule=wl.rule)
+    h_out2 = ctx2.pinned_array((wl.n_pairs,), np.float64)
+    lanes = [(ctx, h_out), (ctx2, h_out2)]
+
+    def worker(c, out, n):
+        torch.cuda.set_device(local_rank)
+        for _ in range(n):
+            step_e2e(c, out)
+        c.synchronize()
+
+    def run_pipelined(n_each):
+        ths = [threading.Thread(target=worker, args=(c, o, n_each)) for c, o in lanes]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
+    run_pipelined(1)
+    barrier()
+    t0 = time.perf_counter()
+    run_pipelined(e2e_steps // 2)
+    t_pipe = max_over_ranks(time.perf_counter() - t0)
+    e2e_pipe = total_pairs * e2e_steps / t_pipe
+    e2e_ok = e2e_ok and bool(np.array_equal(h_out2, check_scores))
+    ctx2.close()
+    e2e_value, e2e_mode = (e2e_pipe, "two host threads / contexts, copies of one step overlap kernels of the other") \
+        if e2e_pipe > e2e_serial else (e2e_serial, "one host thread, steps back to back")
 
     if rank != 0:
         ctx.close()
@@ -466,7 +500,8 @@ def run_gpu(args, rank, local_rank, world):
                    "l2": f"inputs larger than L2 each step: {wl.h2d_bytes / 1e6:.0f} MB of structures/anchors + "
                          f"{8 * float(sizes.sum()) / 1e6:.0f} MB environment store written and read per step"},
         "e2e": {"value": e2e_value, "unit": "anchor-pairs/s", "h2d_bytes_per_step": int(wl.h2d_bytes),
-                "d2h_bytes_per_step": int(8 * wl.n_pairs), "steps": e2e_steps,
+                "d2h_bytes_per_step": int(8 * wl.n_pairs), "steps": e2e_steps, "mode": e2e_mode,
+                "one_thread_value": e2e_serial, "two_thread_value": e2e_pipe,
                 "scores_identical_to_resident_run": e2e_ok},
         "gpu_launches": int(launches),
         "clocks": clock_info,
