@@ -1570,14 +1570,20 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreAr
             cnt[c * 32 + lane] = word + (takeA ? 1u : 0x10000u);
             mism += (mine_k == other_k ? 1 : 0) - (mine_k + 1u == other_k ? 1 : 0);
             D = fma(dsq_of(mine_k), sqrt_of(other_k), D);
-            if (takeA) {
-                ++totA; rA = rsqrt_of(totA);
-                ++i;
-                if (i < i1) ra = kA[i];
-            } else {
-                ++totB; rB = rsqrt_of(totB);
-                ++j;
-                if (j < j1) rb = kB[j];
+            {   // one table read and one key read per event, whichever side moved (two predicated reads of each
+                // kind cost twice the shared-memory wavefronts: ncu, profiles/r1t)
+                totA += takeA ? 1u : 0u;
+                totB += takeA ? 0u : 1u;
+                const double rnew = rsqrt_of(takeA ? totA : totB);
+                rA = takeA ? rnew : rA;
+                rB = takeA ? rB : rnew;
+                i += takeA ? 1u : 0u;
+                j += takeA ? 0u : 1u;
+                const bool more = takeA ? (i < i1) : (j < j1);
+                const uint64_t* src = takeA ? (kA + i) : (kB + j);
+                const uint64_t nxt = more ? *src : 0ull;
+                ra = takeA ? nxt : ra;
+                rb = takeA ? rb : nxt;
             }
             if (++since_refresh == kRefresh) { since_refresh = 0; rebuild(); }
             h = stat_dist();
