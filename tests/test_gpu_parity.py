@@ -424,3 +424,58 @@ def test_fused_gather_matches_multi_kernel_gather(oracle_mod, case, monkeypatch)
         a0, _ = canonical_env(i0[off0[p]:off0[p + 1]], d0[off0[p]:off0[p + 1]])
         a1, _ = canonical_env(i1[off1[p]:off1[p + 1]], d1[off1[p]:off1[p + 1]])
         assert np.array_equal(a0, a1), f"members differ for anchor {p}"
+
+
+# ------------------------------------------------------------------------------- fused gather: geometry corner cases
+def test_members_exactly_on_the_sphere_are_excluded(gpu_ctx, oracle_mod):
+    """Integer lattice, threshold exactly 5: primitives at distance exactly 5 (3-4-5 and axis neighbours) sit on the
+    strict `d2 < r2` boundary and on cell / row-pruning boundaries at the same time."""
+    g = np.arange(-6, 7, dtype=np.float64)
+    xyz = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
+    rng = np.random.default_rng(12)
+    cat = rng.integers(0, 5, size=len(xyz)).astype(np.uint16)
+    tag = np.arange(len(xyz), dtype=np.uint32)
+    centre = int(np.flatnonzero((xyz == 0).all(axis=1))[0])
+    anchors = [(centre, centre)] + [(int(i), int(i)) for i in rng.choice(len(xyz), 40, replace=False)]
+    op = set_both(gpu_ctx, oracle_mod, 5, [("uniform", (1.0, 5.0))], tag_rule={"accept_same": False})
+    _, ref = check_from_primitives(gpu_ctx, oracle_mod, op, (xyz, cat, tag), (xyz, cat, tag), anchors, 5.0)
+    # the centre sees every lattice point with x^2 + y^2 + z^2 < 25 (itself included)
+    assert ref["env_sizes"][0, 0] == int(((xyz ** 2).sum(axis=1) < 25).sum())
+
+
+@pytest.mark.parametrize("shape", ["line", "plane", "point", "two_clusters", "f32_far"])
+def test_degenerate_structures(gpu_ctx, oracle_mod, shape):
+    """Flat, linear, single-point and widely separated structures: grids with one cell along some axes, enlarged
+    cells, empty rows; every primitive an anchor, neighbour lists compared with the oracle."""
+    rng = np.random.default_rng(13)
+    n = 160
+    if shape == "line":
+        xyz = np.zeros((n, 3)); xyz[:, 0] = np.sort(rng.uniform(0, 300, n))
+    elif shape == "plane":
+        xyz = np.zeros((n, 3)); xyz[:, 1:] = rng.uniform(0, 40, (n, 2)); xyz[:, 0] = 7.25
+    elif shape == "point":
+        xyz = np.tile(np.array([[1.5, -2.5, 3.0]]), (n, 1))
+    elif shape == "two_clusters":
+        xyz = rng.normal(0, 4, (n, 3)); xyz[n // 2:] += np.array([5000.0, -3000.0, 800.0])
+    else:
+        xyz = (rng.uniform(-30, 30, (n, 3)) + np.array([9.0e4, 9.0e4, -9.0e4])).astype(np.float32).astype(np.float64)
+    cat = rng.integers(0, 4, size=n).astype(np.uint16)
+    tag = (np.arange(n) // 4).astype(np.uint32)
+    anchors = [(i, (i * 3) % n) for i in range(n)]
+    op = set_both(gpu_ctx, oracle_mod, 4, [("dagum", (3.0, 6.0, 2.0))], tag_rule={"accept_same": False})
+    check_from_primitives(gpu_ctx, oracle_mod, op, (xyz, cat, tag), (xyz[::-1].copy(), cat, tag), anchors, 10.0)
+
+
+def test_one_oversized_environment_falls_back(gpu_ctx, oracle_mod):
+    """One dense blob (> 512 members around its anchors) next to an ordinary structure: the fused gather reports the
+    overflow and the whole call is rebuilt by the multi-kernel path - same results as the oracle."""
+    rng = np.random.default_rng(14)
+    blob = rng.normal(0, 2.0, (700, 3))
+    rest = rng.uniform(-40, 40, (600, 3)) + np.array([80.0, 0, 0])
+    xyz = np.concatenate([blob, rest])
+    cat = rng.integers(0, 6, size=len(xyz)).astype(np.uint16)
+    tag = rng.integers(0, 200, size=len(xyz)).astype(np.uint32)
+    anchors = [(i, i) for i in range(0, len(xyz), 13)]
+    op = set_both(gpu_ctx, oracle_mod, 6, [("kumaraswamy", (3.0, 10.0, 2.0, 5.0))], tag_rule={"accept_same": False})
+    _, ref = check_from_primitives(gpu_ctx, oracle_mod, op, (xyz, cat, tag), (xyz, cat, tag), anchors, 10.0)
+    assert ref["env_sizes"].max() > 512
