@@ -1,22 +1,27 @@
 // locohd_kernels.cu — hand-written sm_100a kernels of the LoCoHD per-anchor scoring path.
 //
 // Pipeline (all FP64 where the reference is FP64; no tensor cores: there is no dense contraction):
-//   K0   build_cells_kernel     one CTA per structure: bounding box, half-radius cell grid, counting sort of the
-//                               primitives into cell order (replaces KdTree::build_by_ordered_float, locohd.rs:504-510)
-//   Ka   anchor_slot_* kernels  put the requested anchors into cell order, so that the 32 lanes of a warp work on
-//                               neighbouring anchors and read the same candidate cells
-//   K1a  env_tile_kernel<false> one THREAD per anchor: FP32 prefilter over the candidate cells, counts the
-//                               survivors (upper bound of the environment size) -> scan -> store offsets
-//   K1b  env_tile_kernel<true>  same traversal; survivors are re-tested in FP64 with the kd-tree predicate, the tag
-//                               rule is applied and (distance, category) is written unsorted into the store
-//                               (kdtree.within_radius + filter + euclidean_distance, locohd.rs:521-538)
-//   K1c  env_sort_kernel<CAP>   one warp per environment: bucket sort by distance in shared memory, CDF evaluation,
-//                               packed keys written back in place (utils::sort_together, utils.rs:25-39)
+//   K0   build_cells_kernel     one CTA per structure: bounding box, cell grid (edge r / 2 along y and z, r / 8 along
+//                               x), counting sort of the primitives into cell order
+//                               (replaces KdTree::build_by_ordered_float, locohd.rs:504-510)
+//   Ka   anchor_slot_* kernels  put the requested anchors into cell order: neighbouring anchors are processed
+//                               together and read the same candidate rows
+//   K1   env_fused_kernel       one persistent WARP per anchor: row pruning, exact FP64 gather with the kd-tree
+//                               predicate + tag rule, register bitonic sort, sqrt, CDF, key packing, store
+//                               (kdtree.within_radius + filter + euclidean_distance + sort_together,
+//                               locohd.rs:514-542, utils.rs:1-39); env_tile_kernel<false> on a 1/16 sample sizes
+//                               the store beforehand
 //   K2   score_fast_kernel /    one warp per anchor pair: merge-path split of the two sorted environments over the
 //        score_kernel           32 lanes, per-lane category counts by warp prefix sums, per-lane walk that
 //                               accumulates dW * H (stat_dist_integral, locohd.rs:61-226, as a flat prefix scan)
-// plus the small kernels around them (scans, rows of from_dmxs/from_coords, the exact-order sequential walk of
-// from_anchors, leaf-math probes).
+//   fallback gather (environments the fused kernel cannot take, rows of from_dmxs / from_coords):
+//   K1a  env_tile_kernel<false> one THREAD per anchor: FP32 prefilter over the candidate cells, counts the
+//                               survivors (upper bound of the environment size) -> scan -> store offsets
+//   K1b  env_tile_kernel<true>  same traversal; survivors are re-tested in FP64, (distance, category) is written
+//                               unsorted into the store
+//   K1c  env_sort_kernel<CAP>   one warp per environment: bucket sort by distance in shared memory, CDF, packing
+// plus the small kernels around them (scans, row copies, the exact-order sequential walk of from_anchors,
+// leaf-math probes).
 #include "locohd_kernels.cuh"
 
 #include <cfloat>
@@ -651,7 +656,7 @@ template <bool EXACT>
 __device__ __forceinline__ double fused_distance(double d2) {
     if (EXACT) return sqrt(d2);
     const float f = (float)d2;
-    if (!(f > 1e-30f && f < 1e30f)) return sqrt(d2);
+    if (!(f > 1e-30f && f < 1e30f)) return d2 == 0.0 ? 0.0 : sqrt(d2);   // 0: the anchor, once per environment
     const double g = (double)rsqrt_approx(f);
     double sq = d2 * g, hh = 0.5 * g;
     double r = fma(-sq, hh, 0.5);
