@@ -460,23 +460,29 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
     tr.mark("cells + order launched");
     // ---- fused path: sample the sizes (every anchor for small calls), reserve the store, one kernel does the rest
     if (!ctx->legacy_gather) {
-        const uint32_t stride = n_anchors <= 65536 ? 1u : 16u;
+        // Store sizing.  Small calls (one structure pair is the typical call of the reference API) take the bound
+        // kFusedCap per environment and skip the sizing pass and its synchronisation; large batches sample the FP32
+        // upper-bound sizes of every 16th anchor.
+        const bool sized_by_bound = n_anchors <= 32768;
+        const uint32_t stride = 16u;
         cudaMemsetAsync(ctx->d_fstats, 0, sizeof(FusedStats), ctx->stream);
-        {
-            ProfScope ps(ctx, LOCOHD_PROF_COUNT);
-            ctx->launches += launch_env_sample(sv, ctx->kp, n_anchors, d_order, d_anchor_struct, d_anchor_prim, threshold,
-                                               stride, &ctx->d_fstats->sample, ctx->stream);
-        }
         FusedStats fs{};
-        if (cudaMemcpyAsync(&fs, ctx->d_fstats, sizeof fs, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-            return bail(fail(ctx, LOCOHD_ERR_CUDA, "copy of the gather statistics failed"));
-        if ((st = sync_and_check(ctx))) return bail(st);
-        tr.mark("sample + sync");
+        if (!sized_by_bound) {
+            {
+                ProfScope ps(ctx, LOCOHD_PROF_COUNT);
+                ctx->launches += launch_env_sample(sv, ctx->kp, n_anchors, d_order, d_anchor_struct, d_anchor_prim,
+                                                   threshold, stride, &ctx->d_fstats->sample, ctx->stream);
+            }
+            if (cudaMemcpyAsync(&fs, ctx->d_fstats, sizeof fs, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+                return bail(fail(ctx, LOCOHD_ERR_CUDA, "copy of the gather statistics failed"));
+            if ((st = sync_and_check(ctx))) return bail(st);
+            tr.mark("sample + sync");
+        }
         const unsigned grid = fused_grid(ctx->kp, &ctx->h_wf0, e->key_is_w ? 1 : 0, keep_indices != 0, n_anchors);
         // sampled sizes are FP32 upper bounds; even-rounding adds at most one entry per environment, every warp
         // can leave most of a chunk unused at every refill and at the end
-        double est = (double)fs.sample * (double)stride;
-        if (stride > 1) est = est * 1.03 + 65536.0;
+        const double est = sized_by_bound ? (double)n_anchors * (double)kFusedCap
+                                          : (double)fs.sample * (double)stride * 1.03 + 65536.0;
         const double waste = 1.0 + (double)kFusedCap / (double)kFusedChunk;
         uint64_t capacity = (uint64_t)((est + (double)n_anchors) * waste) + (uint64_t)grid * kFusedWarps * kFusedChunk + 2 * kFusedChunk;
         // The sample differs a little from call to call (cell order depends on atomics): round the size up to 4
