@@ -554,11 +554,19 @@ struct LoCoHD {
         Flat f;
         const py::ssize_t hint = py::len_hint(prims);
         if (hint > 0) { f.xyz.reserve(3 * hint); f.cat.reserve(hint); f.tag.reserve(hint); }
+        // consecutive primitives usually share their tag (one tag per residue) and often their type: compare with
+        // the previous strings before hashing
+        const std::string* last_tag = nullptr;
+        const std::string* last_type = nullptr;
+        uint32_t last_tag_id = 0;
+        uint16_t last_cat = 0;
         for (auto item : prims) {
             const PrimitiveAtom& p = item.cast<const PrimitiveAtom&>();
             f.xyz.push_back(p.coordinates[0]); f.xyz.push_back(p.coordinates[1]); f.xyz.push_back(p.coordinates[2]);
-            f.cat.push_back(cat_id(p.primitive_type));
-            f.tag.push_back(intern_tag(p.tag));
+            if (!last_type || *last_type != p.primitive_type) { last_cat = cat_id(p.primitive_type); last_type = &p.primitive_type; }
+            if (!last_tag || *last_tag != p.tag) { last_tag_id = intern_tag(p.tag); last_tag = &p.tag; }
+            f.cat.push_back(last_cat);
+            f.tag.push_back(last_tag_id);
         }
         return f;
     }
@@ -573,12 +581,26 @@ struct LoCoHD {
         bool with_keys = true, first = true;
         size_t n_pairs = 0;
         for (auto item : anchor_pairs) {
+            long long i, j;
+            if (PyTuple_CheckExact(item.ptr()) && PyTuple_GET_SIZE(item.ptr()) == 2 && (first || !with_keys) &&
+                PyLong_CheckExact(PyTuple_GET_ITEM(item.ptr(), 0)) && PyLong_CheckExact(PyTuple_GET_ITEM(item.ptr(), 1))) {
+                // fast path: a plain (int, int) tuple
+                if (first) { with_keys = false; first = false; }
+                i = PyLong_AsLongLong(PyTuple_GET_ITEM(item.ptr(), 0));
+                j = PyLong_AsLongLong(PyTuple_GET_ITEM(item.ptr(), 1));
+                if ((i == -1 || j == -1) && PyErr_Occurred()) throw py::error_already_set();
+                if (i < 0 || j < 0) throw py::value_error("anchor indices must be non-negative");
+                if (i > 0xFFFFFFFELL || j > 0xFFFFFFFELL) throw py::value_error("anchor index out of range");
+                anchors.push_back((uint32_t)i); anchors.push_back((uint32_t)j);
+                ++n_pairs;
+                continue;
+            }
             py::sequence t = py::reinterpret_borrow<py::sequence>(item);
             if (!PySequence_Check(item.ptr()) || py::isinstance<py::str>(item)) throw py::type_error("anchor_pairs must contain (int, int) or (int, int, str) tuples");
             const size_t len = t.size();
             if (first) { with_keys = (len == 3); first = false; }
             if (len != (with_keys ? 3u : 2u)) throw py::type_error("anchor_pairs must contain (int, int) or (int, int, str) tuples");
-            const long long i = t[0].cast<long long>(), j = t[1].cast<long long>();
+            i = t[0].cast<long long>(); j = t[1].cast<long long>();
             if (i < 0 || j < 0) throw py::value_error("anchor indices must be non-negative");
             if (i > 0xFFFFFFFELL || j > 0xFFFFFFFELL) throw py::value_error("anchor index out of range");
             anchors.push_back((uint32_t)i); anchors.push_back((uint32_t)j);
