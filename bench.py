@@ -288,6 +288,9 @@ def run_gpu(args, rank, local_rank, world):
         return float(t.item())
 
     wl = make_workload(args.workload, rank, world, args)
+    if args.threshold:   # exploration only: the BASELINE configurations use 10 A
+        wl.threshold = float(args.threshold)
+        wl.desc += f" [threshold overridden: {wl.threshold:g}]"
     ctx = _capi.Context(local_rank)
     ctx.set_params(wl.C, [wl.wf], tag_rule=wl.rule)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
@@ -529,6 +532,7 @@ def main():
     ap.add_argument("--ensemble", type=int, default=96, help="cfg5: ensemble size (all-vs-all, jobs dealt over GPUs)")
     ap.add_argument("--ref-pairs", type=int, default=160000, help="anchor pairs per CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--threshold", type=float, default=0.0, help="override the 10 A threshold (exploration only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -45,6 +45,7 @@ struct locohd_ctx {
     ScanStats* d_scan = nullptr;   // two slots: [0] anchor order, [1] environment sizes
     FusedStats* d_fstats = nullptr;  // fused gather: store cursor, sample sum, largest environment, overflow word
     int legacy_gather = 0;         // LOCOHD_LEGACY_GATHER=1: always use the multi-kernel gather (A/B runs)
+    int fused_cap_hint = kFusedCap;  // members per environment the fused gather starts with (512 or 1024)
     // Large device buffers (environment stores, scratch) are recycled per context: the stream-ordered pool of the
     // driver splits and re-merges multi-GB blocks unpredictably, which shows up as 30-60 ms stalls per call.
     std::mutex cache_mu;
@@ -478,51 +479,61 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
             if ((st = sync_and_check(ctx))) return bail(st);
             tr.mark("sample + sync");
         }
-        const unsigned grid = fused_grid(ctx->kp, &ctx->h_wf0, e->key_is_w ? 1 : 0, keep_indices != 0, n_anchors);
-        // sampled sizes are FP32 upper bounds; even-rounding adds at most one entry per environment, every warp
-        // can leave most of a chunk unused at every refill and at the end
-        const double est = sized_by_bound ? (double)n_anchors * (double)kFusedCap
-                                          : (double)fs.sample * (double)stride * 1.03 + 65536.0;
-        const double waste = 1.0 + (double)kFusedCap / (double)kFusedChunk;
-        uint64_t capacity = (uint64_t)((est + (double)n_anchors) * waste) + (uint64_t)grid * kFusedWarps * kFusedChunk + 2 * kFusedChunk;
-        // The sample differs a little from call to call (cell order depends on atomics): round the size up to 4
-        // significant bits so that repeated calls ask the block cache for the same size (a fresh multi-GB
-        // cudaMallocAsync costs 0.5-2 s).
-        for (uint64_t step = 1ull << 62; step >= 32; step >>= 1)
-            if (capacity & step) { step >>= 4; capacity = (capacity + step - 1) & ~(step - 1); break; }
-        tr.mark("grid + capacity");
-        if (tr.on) std::fprintf(stderr, "[locohd trace] capacity %llu entries, grid %u, cached blocks %zu\n",
-                                (unsigned long long)capacity, grid, ctx->big_free.size());
-        if ((st = dev_alloc(ctx, &e->d_key, capacity))) return bail(st);
-        if (keep_indices) {
-            if ((st = dev_alloc(ctx, &e->d_idx, capacity)) || (st = dev_alloc(ctx, &e->d_dist, capacity))) return bail(st);
-        }
-        tr.mark("store allocation");
-        EnvBuild b{};
-        b.n_env = n_anchors; b.order = d_order; b.ub = nullptr; b.off = nullptr; b.off_out = e->d_off; b.count = e->d_count;
-        b.key = e->d_key; b.cat = nullptr; b.idx = e->d_idx; b.dist = e->d_dist; b.key_is_w = e->key_is_w ? 1 : 0;
-        b.key_is_sq = 1; b.check_first_zero = 0;
-        {
-            ProfScope ps(ctx, LOCOHD_PROF_FILL);
-            ctx->launches += launch_env_fused(sv, ctx->kp, &ctx->h_wf0, d_anchor_struct, d_anchor_prim, threshold, b,
-                                              ctx->d_fstats, capacity, grid, ctx->stream);
-        }
-        cudaError_t ce = cudaGetLastError();
-        if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
-        if (cudaMemcpyAsync(&fs, ctx->d_fstats, sizeof fs, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-            return bail(fail(ctx, LOCOHD_ERR_CUDA, "copy of the gather statistics failed"));
-        if ((st = sync_and_check(ctx))) return bail(st);
-        tr.mark("fused kernel + sync");
-        if (!fs.overflow) {
-            e->capacity = capacity;
-            e->total = fs.cursor < capacity ? fs.cursor : capacity;
-            e->max_count = fs.max_count;
-            release();
-            *out = e;
-            return 0;
+        // Members per environment the kernel is instantiated for: 512, and 1024 once a call has reported larger
+        // environments (the hint stays with the context until a 1024 run sees only small ones again).
+        for (int cap = ctx->fused_cap_hint; cap <= kFusedCapBig; cap *= 2) {
+            const unsigned grid = fused_grid(ctx->kp, &ctx->h_wf0, e->key_is_w ? 1 : 0, keep_indices != 0, cap, n_anchors);
+            // sampled sizes are FP32 upper bounds; even-rounding adds at most one entry per environment, every warp
+            // can leave most of a chunk unused at every refill and at the end
+            const double est = sized_by_bound ? (double)n_anchors * (double)cap
+                                              : (double)fs.sample * (double)stride * 1.03 + 65536.0;
+            const double waste = 1.0 + (double)cap / (double)kFusedChunk;
+            uint64_t capacity = (uint64_t)((est + (double)n_anchors) * waste) + (uint64_t)grid * kFusedWarps * kFusedChunk + 2 * kFusedChunk;
+            // The sample differs a little from call to call (cell order depends on atomics): round the size up to 4
+            // significant bits so that repeated calls ask the block cache for the same size (a fresh multi-GB
+            // cudaMallocAsync costs 0.5-2 s).
+            for (uint64_t step = 1ull << 62; step >= 32; step >>= 1)
+                if (capacity & step) { step >>= 4; capacity = (capacity + step - 1) & ~(step - 1); break; }
+            tr.mark("grid + capacity");
+            if (tr.on) std::fprintf(stderr, "[locohd trace] cap %d, capacity %llu entries, grid %u, cached blocks %zu\n", cap,
+                                    (unsigned long long)capacity, grid, ctx->big_free.size());
+            if ((st = dev_alloc(ctx, &e->d_key, capacity))) return bail(st);
+            if (keep_indices) {
+                if ((st = dev_alloc(ctx, &e->d_idx, capacity)) || (st = dev_alloc(ctx, &e->d_dist, capacity))) return bail(st);
+            }
+            tr.mark("store allocation");
+            EnvBuild b{};
+            b.n_env = n_anchors; b.order = d_order; b.ub = nullptr; b.off = nullptr; b.off_out = e->d_off; b.count = e->d_count;
+            b.key = e->d_key; b.cat = nullptr; b.idx = e->d_idx; b.dist = e->d_dist; b.key_is_w = e->key_is_w ? 1 : 0;
+            b.key_is_sq = 1; b.check_first_zero = 0;
+            cudaMemsetAsync(&ctx->d_fstats->cursor, 0, sizeof(unsigned long long), ctx->stream);
+            cudaMemsetAsync(&ctx->d_fstats->max_count, 0, 2 * sizeof(unsigned int), ctx->stream);
+            {
+                ProfScope ps(ctx, LOCOHD_PROF_FILL);
+                ctx->launches += launch_env_fused(sv, ctx->kp, &ctx->h_wf0, d_anchor_struct, d_anchor_prim, threshold, b, cap,
+                                                  ctx->d_fstats, capacity, grid, ctx->stream);
+            }
+            cudaError_t ce = cudaGetLastError();
+            if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
+            FusedStats fr{};
+            if (cudaMemcpyAsync(&fr, ctx->d_fstats, sizeof fr, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+                return bail(fail(ctx, LOCOHD_ERR_CUDA, "copy of the gather statistics failed"));
+            if ((st = sync_and_check(ctx))) return bail(st);
+            tr.mark("fused kernel + sync");
+            if (!fr.overflow) {
+                if (cap == kFusedCapBig && fr.max_count <= (unsigned)(kFusedCap * 3 / 4)) ctx->fused_cap_hint = kFusedCap;
+                e->capacity = capacity;
+                e->total = fr.cursor < capacity ? fr.cursor : capacity;
+                e->max_count = fr.max_count;
+                release();
+                *out = e;
+                return 0;
+            }
+            dev_free(ctx, e->d_key); dev_free(ctx, e->d_idx); dev_free(ctx, e->d_dist);
+            if (fr.overflow != 8u) break;          // not (only) "more members than cap": the larger kernel will not help
+            ctx->fused_cap_hint = kFusedCapBig;     // environments beyond 512 members: go on with the 1024 instantiation
         }
         // some environment did not fit the fused kernel: rebuild everything with the exact multi-kernel path
-        dev_free(ctx, e->d_key); dev_free(ctx, e->d_idx); dev_free(ctx, e->d_dist);
     }
     {
         ProfScope ps(ctx, LOCOHD_PROF_COUNT);

@@ -518,17 +518,25 @@ __device__ __forceinline__ uint64_t pack_key(double w, uint32_t cat) {
 //             fixed-point distance are checked against the exact values (rare serial repair)
 //   store     sqrt (utils.rs:1-8), CDF (specialised by WFK), key packing; coalesced stores into a chunk of the store
 //             the warp reserved with one atomicAdd per kFusedChunk entries.
-// Environments that do not fit (more than kFusedCap members, store exhausted) raise the overflow word: the host
-// then rebuilds the call with the exact multi-kernel path.
+// CAP (512 or 1024) bounds the members of an environment.  Environments that do not fit, or a store that turns out
+// too small, raise the overflow word: the host retries with the larger CAP and finally rebuilds the call with the
+// exact multi-kernel path.
 // ------------------------------------------------------------------------------------------------
-template <bool DEBUG>
+template <bool DEBUG, int CAP>
 struct FusedLayout {
-    static constexpr int kD2Off = 0;                                    // f64 [CAP] exact squared distances
-    static constexpr int kKeyOff = kD2Off + 8 * kFusedCap;              // u32 [CAP] sort keys
-    static constexpr int kRowOff = kKeyOff + 4 * kFusedCap;             // i32 [32] row delta (start - flat prefix)
-    static constexpr int kCatOff = kRowOff + 4 * 32;                    // u8 [CAP]
-    static constexpr int kIdxOff = kCatOff + kFusedCap;                 // u32 [CAP] (DEBUG)
-    static constexpr int kBytes = (kIdxOff + (DEBUG ? 4 * kFusedCap : 0) + 15) & ~15;
+    static constexpr int kD2Off = 0;                              // f64 [CAP] exact squared distances
+    static constexpr int kKeyOff = kD2Off + 8 * CAP;              // u32 [CAP] sort keys
+    static constexpr int kRowOff = kKeyOff + 4 * CAP;             // i32 [32] row delta (start - flat prefix)
+    static constexpr int kCatOff = kRowOff + 4 * 32;              // u8 [CAP]
+    static constexpr int kIdxOff = kCatOff + CAP;                 // u32 [CAP] (DEBUG)
+    static constexpr int kBytes = (kIdxOff + (DEBUG ? 4 * CAP : 0) + 15) & ~15;
+};
+// sort key = fixed-point squared distance << SB | slot, SB = log2(CAP) slot bits
+template <int CAP> struct FusedKey {
+    static constexpr int SB = CAP == 512 ? 9 : 10;
+    static constexpr uint32_t kSlotMask = (1u << SB) - 1u;
+    static constexpr double kScale = (double)((1u << (32 - SB)) - 16u);   // d2 < r2 -> fixed point < 2^(32-SB) - 15
+    static constexpr uint32_t kInfKey = (1u << (32 - SB)) - 8u;           // non-finite squared distance
 };
 
 // ascending compare-exchange of two registers of one lane
@@ -606,17 +614,19 @@ __device__ __noinline__ void fused_sort(uint32_t* key32, uint32_t M, int lane) {
 }
 
 // serial repair of groups with equal fixed-point distance (order by exact squared distance, category, slot)
+template <int SB>
 __device__ __noinline__ void fused_repair(uint32_t* key32, const double* d2s, const uint8_t* cats, uint32_t M) {
+    constexpr uint32_t kMask = (1u << SB) - 1u;
     for (uint32_t g = 1; g < M; ++g) {
         const uint32_t kg = key32[g];
-        const uint32_t sg = kg & 511u;
+        const uint32_t sg = kg & kMask;
         const double dg = d2s[sg];
         const uint32_t cg = cats[sg];
         uint32_t u = g;
         while (u > 0) {
             const uint32_t kf = key32[u - 1];
-            if ((kf >> 9) != (kg >> 9)) break;
-            const uint32_t sf = kf & 511u;
+            if ((kf >> SB) != (kg >> SB)) break;
+            const uint32_t sf = kf & kMask;
             const double df = d2s[sf];
             const uint32_t cf = cats[sf];
             if (df < dg || (df == dg && (cf < cg || (cf == cg && sf < sg)))) break;
@@ -665,15 +675,16 @@ __device__ __forceinline__ double fused_distance(double d2) {
     return fma(sq, r, sq);
 }
 
-template <int WFK, bool DEBUG>
-__global__ void __launch_bounds__(kFusedWarps * 32, 8) env_fused_kernel(StructsView s, KParams p, uint64_t n_env,
+template <int WFK, bool DEBUG, int CAP>
+__global__ void __launch_bounds__(kFusedWarps * 32, CAP == 512 ? 8 : 4) env_fused_kernel(StructsView s, KParams p, uint64_t n_env,
                                                                      const uint32_t* __restrict__ order,
                                                                      const uint32_t* __restrict__ anchor_struct,
                                                                      const uint32_t* __restrict__ anchor_prim,
                                                                      double threshold, EnvBuild b, FusedStats* stats,
                                                                      uint64_t capacity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using L = FusedLayout<DEBUG>;
+    using L = FusedLayout<DEBUG, CAP>;
+    using K = FusedKey<CAP>;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned char* smem = smem_raw + (size_t)wib * L::kBytes;
     double* d2s = reinterpret_cast<double*>(smem + L::kD2Off);
@@ -686,7 +697,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 8) env_fused_kernel(StructsV
 
     const double r2 = __dmul_rn(threshold, threshold);
     const bool r2_finite = isfinite(r2);
-    const double qscale = r2_finite ? 8388592.0 / r2 : 0.0;   // (2^23 - 16) / r^2: d2 < r2 -> key < 2^23 - 15
+    const double qscale = r2_finite ? K::kScale / r2 : 0.0;
     const bool simple_rule = p.tpr_kind == LOCOHD_TPR_WITHOUT_LIST;
     const bool accept_same = p.tpr_accept_same != 0;
     const WfDev& wf = p.wfs[0];
@@ -815,10 +826,10 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 8) env_fused_kernel(StructsV
                 const unsigned mask = __ballot_sync(kFull, acc);
                 if (acc) {
                     const uint32_t slot = M + __popc(mask & lt_mask);
-                    if (slot < (uint32_t)kFusedCap) {
+                    if (slot < (uint32_t)CAP) {
                         d2s[slot] = d2;
                         cats[slot] = (uint8_t)r.cat;
-                        key32[slot] = ((uint32_t)(d2 * qscale) << 9) | slot;
+                        key32[slot] = ((uint32_t)(d2 * qscale) << K::SB) | slot;
                         if (DEBUG) sidx[slot] = r.orig;
                     }
                 }
@@ -840,7 +851,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 8) env_fused_kernel(StructsV
             }
         }
         __syncwarp();
-        if (M > (uint32_t)kFusedCap) {
+        if (M > (uint32_t)CAP) {
             if (lane == 0) { atomicOr(&stats->overflow, 8u); b.count[e] = 0; b.off_out[e] = 0; }
             continue;
         }
@@ -852,11 +863,11 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 8) env_fused_kernel(StructsV
             double dmax = 0.0;
             for (uint32_t g = lane; g < M; g += 32) { const double v = d2s[g]; if (isfinite(v)) dmax = fmax(dmax, v); }
             for (int o = 16; o; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
-            const double sc = dmax > 0.0 ? 8388592.0 / dmax : 0.0;
+            const double sc = dmax > 0.0 ? K::kScale / dmax : 0.0;
             for (uint32_t g = lane; g < M; g += 32) {
                 const double v = d2s[g];
-                const uint32_t qv = isfinite(v) ? (uint32_t)(v * sc) : 8388600u;
-                key32[g] = (qv << 9) | g;
+                const uint32_t qv = isfinite(v) ? (uint32_t)(v * sc) : K::kInfKey;
+                key32[g] = (qv << K::SB) | g;
             }
             __syncwarp();
         }
@@ -864,19 +875,20 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 8) env_fused_kernel(StructsV
         // ---- sort
         if (M <= 128) fused_sort<4>(key32, M, lane);
         else if (M <= 256) fused_sort<8>(key32, M, lane);
-        else fused_sort<16>(key32, M, lane);
+        else if (CAP == 512 || M <= 512) fused_sort<16>(key32, M, lane);
+        else fused_sort<CAP == 512 ? 16 : 32>(key32, M, lane);
         {   // equal fixed-point distances: order by the exact (distance, category)
             bool viol = false;
             for (uint32_t g = lane; g + 1 < M; g += 32) {
                 const uint32_t ka = key32[g], kb = key32[g + 1];
-                if ((ka >> 9) == (kb >> 9)) {
-                    const uint32_t sa = ka & 511u, sb = kb & 511u;
+                if ((ka >> K::SB) == (kb >> K::SB)) {
+                    const uint32_t sa = ka & K::kSlotMask, sb = kb & K::kSlotMask;
                     const double da = d2s[sa], db = d2s[sb];
                     viol |= (da > db) || (da == db && cats[sa] > cats[sb]);
                 }
             }
             if (__any_sync(kFull, viol)) {
-                if (lane == 0) fused_repair(key32, d2s, cats, M);
+                if (lane == 0) fused_repair<K::SB>(key32, d2s, cats, M);
                 __syncwarp();
             }
         }
@@ -903,7 +915,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 8) env_fused_kernel(StructsV
             const uint32_t g = g0 + lane;
             uint64_t packed = 0;
             if (g < M) {
-                const uint32_t slot = key32[g] & 511u;
+                const uint32_t slot = key32[g] & K::kSlotMask;
                 const double d = fused_distance<DEBUG>(d2s[slot]);   // utils.rs:1-8
                 packed = pack_key(fused_weight<WFK>(wf, fwf, d, key_is_w), cats[slot]);
                 if (DEBUG) { b.dist[off + g] = d; b.idx[off + g] = sidx[slot]; }
@@ -1810,14 +1822,14 @@ static int fused_wfk(const KParams& p, const WfDev* host_wf, int key_is_w) {
     return 2;
 }
 
-template <int WFK, bool DEBUG>
+template <int WFK, bool DEBUG, int CAP>
 static unsigned fused_grid_t(uint64_t n_env) {
-    const int smem = FusedLayout<DEBUG>::kBytes * kFusedWarps;
-    cudaFuncSetAttribute(env_fused_kernel<WFK, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = FusedLayout<DEBUG, CAP>::kBytes * kFusedWarps;
+    cudaFuncSetAttribute(env_fused_kernel<WFK, DEBUG, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_fused_kernel<WFK, DEBUG>, kFusedWarps * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_fused_kernel<WFK, DEBUG, CAP>, kFusedWarps * 32, smem);
     if (occ < 1) occ = 1;
     if (const char* v = std::getenv("LOCOHD_FUSED_CTAS")) { const int c = std::atoi(v); if (c >= 1 && c < occ) occ = c; }
     const uint64_t need = (n_env + kFusedWarps - 1) / kFusedWarps;
@@ -1825,38 +1837,43 @@ static unsigned fused_grid_t(uint64_t n_env) {
     return (unsigned)(need < cap ? need : cap);
 }
 
-template <int WFK, bool DEBUG>
+template <int WFK, bool DEBUG, int CAP>
 static void fused_launch_t(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
                            const uint32_t* anchor_prim, double threshold, const EnvBuild& b, FusedStats* stats,
                            uint64_t capacity, unsigned grid, cudaStream_t st) {
-    const int smem = FusedLayout<DEBUG>::kBytes * kFusedWarps;
-    env_fused_kernel<WFK, DEBUG><<<grid, kFusedWarps * 32, smem, st>>>(s, p, b.n_env, b.order, anchor_struct,
-                                                                       anchor_prim, threshold, b, stats, capacity);
+    const int smem = FusedLayout<DEBUG, CAP>::kBytes * kFusedWarps;
+    env_fused_kernel<WFK, DEBUG, CAP><<<grid, kFusedWarps * 32, smem, st>>>(s, p, b.n_env, b.order, anchor_struct,
+                                                                            anchor_prim, threshold, b, stats, capacity);
 }
 
-unsigned fused_grid(const KParams& p, const WfDev* host_wf, int key_is_w, bool debug, uint64_t n_env) {
-    switch (fused_wfk(p, host_wf, key_is_w) * 2 + (debug ? 1 : 0)) {
-        case 0: return fused_grid_t<0, false>(n_env);
-        case 1: return fused_grid_t<0, true>(n_env);
-        case 2: return fused_grid_t<1, false>(n_env);
-        case 3: return fused_grid_t<1, true>(n_env);
-        case 4: return fused_grid_t<2, false>(n_env);
-        default: return fused_grid_t<2, true>(n_env);
+// dispatch over (CDF specialisation, parity arrays, members per environment)
+#define LOCOHD_FUSED_DISPATCH(CALL)                                                                        \
+    switch ((fused_wfk(p, host_wf, key_is_w) * 2 + (debug ? 1 : 0)) * 2 + (cap > 512 ? 1 : 0)) {          \
+        case 0: CALL(0, false, 512); break;   case 1: CALL(0, false, 1024); break;                        \
+        case 2: CALL(0, true, 512); break;    case 3: CALL(0, true, 1024); break;                         \
+        case 4: CALL(1, false, 512); break;   case 5: CALL(1, false, 1024); break;                        \
+        case 6: CALL(1, true, 512); break;    case 7: CALL(1, true, 1024); break;                         \
+        case 8: CALL(2, false, 512); break;   case 9: CALL(2, false, 1024); break;                        \
+        case 10: CALL(2, true, 512); break;   default: CALL(2, true, 1024); break;                        \
     }
+
+unsigned fused_grid(const KParams& p, const WfDev* host_wf, int key_is_w, bool debug, int cap, uint64_t n_env) {
+    unsigned g = 1;
+#define LOCOHD_CALL(W, D, C) g = fused_grid_t<W, D, C>(n_env)
+    LOCOHD_FUSED_DISPATCH(LOCOHD_CALL)
+#undef LOCOHD_CALL
+    return g;
 }
 
 int launch_env_fused(const StructsView& s, const KParams& p, const WfDev* host_wf, const uint32_t* anchor_struct,
-                     const uint32_t* anchor_prim, double threshold, const EnvBuild& b, FusedStats* stats,
+                     const uint32_t* anchor_prim, double threshold, const EnvBuild& b, int cap, FusedStats* stats,
                      uint64_t capacity, unsigned grid, cudaStream_t st) {
     if (!b.n_env) return 0;
-    switch (fused_wfk(p, host_wf, b.key_is_w) * 2 + (b.idx ? 1 : 0)) {
-        case 0: fused_launch_t<0, false>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
-        case 1: fused_launch_t<0, true>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
-        case 2: fused_launch_t<1, false>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
-        case 3: fused_launch_t<1, true>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
-        case 4: fused_launch_t<2, false>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
-        default: fused_launch_t<2, true>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st); break;
-    }
+    const int key_is_w = b.key_is_w;
+    const bool debug = b.idx != nullptr;
+#define LOCOHD_CALL(W, D, C) fused_launch_t<W, D, C>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st)
+    LOCOHD_FUSED_DISPATCH(LOCOHD_CALL)
+#undef LOCOHD_CALL
     return 1;
 }
 

@@ -90,14 +90,15 @@ struct ScanStats {  // written by the scan kernels, read back by the host
 
 // fused gather (env_fused_kernel)
 constexpr int kFusedWarps = 4;      // warps per CTA, one anchor per warp at a time
-constexpr int kFusedCap = 512;      // members per environment
+constexpr int kFusedCap = 512;      // members per environment (default instantiation)
+constexpr int kFusedCapBig = 1024;  // second instantiation, used when the first reports larger environments
 constexpr int kFusedChunk = 2048;   // store entries a warp reserves with one atomicAdd
 
 struct FusedStats {  // written by env_fused_kernel, read back by the host
     unsigned long long cursor;     // store entries handed out (multiple of kFusedChunk)
     unsigned long long sample;     // sum of the sampled upper-bound sizes (env_tile_kernel<false> with a stride)
     unsigned int max_count;        // largest environment
-    unsigned int overflow;         // != 0: some environment did not fit -> rebuild with the multi-kernel path
+    unsigned int overflow;         // != 0: bit 3 = an environment exceeded CAP, bit 0 = store exhausted, bit 1 = reach
 };
 
 struct EnvBuild {
@@ -153,9 +154,9 @@ int launch_env_sample(const StructsView& s, const KParams& p, uint64_t n_env, co
 // fused gather + sort + pack: grid from fused_grid(); the store needs room for the members plus one kFusedChunk per
 // warp of the grid
 // host_wf: host copy of weight function 0 (selects the CDF specialisation)
-unsigned fused_grid(const KParams& p, const WfDev* host_wf, int key_is_w, bool debug, uint64_t n_env);
+unsigned fused_grid(const KParams& p, const WfDev* host_wf, int key_is_w, bool debug, int cap, uint64_t n_env);
 int launch_env_fused(const StructsView& s, const KParams& p, const WfDev* host_wf, const uint32_t* anchor_struct,
-                     const uint32_t* anchor_prim, double threshold, const EnvBuild& b, FusedStats* stats,
+                     const uint32_t* anchor_prim, double threshold, const EnvBuild& b, int cap, FusedStats* stats,
                      uint64_t capacity, unsigned grid, cudaStream_t st);
 int launch_env_fill(const StructsView& s, const KParams& p, const uint32_t* anchor_struct, const uint32_t* anchor_prim,
                     double threshold, const EnvBuild& b, cudaStream_t st);

@@ -467,8 +467,9 @@ def test_degenerate_structures(gpu_ctx, oracle_mod, shape):
 
 
 def test_one_oversized_environment_falls_back(gpu_ctx, oracle_mod):
-    """One dense blob (> 512 members around its anchors) next to an ordinary structure: the fused gather reports the
-    overflow and the whole call is rebuilt by the multi-kernel path - same results as the oracle."""
+    """One dense blob (> 512 members around its anchors) next to an ordinary structure: the 512-member instantiation
+    of the fused gather reports the overflow and the call is redone by the 1024-member one (and the context then
+    starts with it; a later call with small environments goes back to 512) - same results as the oracle."""
     rng = np.random.default_rng(14)
     blob = rng.normal(0, 2.0, (700, 3))
     rest = rng.uniform(-40, 40, (600, 3)) + np.array([80.0, 0, 0])
@@ -479,3 +480,20 @@ def test_one_oversized_environment_falls_back(gpu_ctx, oracle_mod):
     op = set_both(gpu_ctx, oracle_mod, 6, [("kumaraswamy", (3.0, 10.0, 2.0, 5.0))], tag_rule={"accept_same": False})
     _, ref = check_from_primitives(gpu_ctx, oracle_mod, op, (xyz, cat, tag), (xyz, cat, tag), anchors, 10.0)
     assert ref["env_sizes"].max() > 512
+    # back to ordinary sizes on the same context
+    a = synth.gen(51, 120, 8, 6)
+    check_from_primitives(gpu_ctx, oracle_mod, op, (a.xyz, a.cat, a.tag), (a.xyz, a.cat, a.tag),
+                          [(i, i) for i in range(0, a.n, 7)], 10.0)
+    check_from_primitives(gpu_ctx, oracle_mod, op, (a.xyz, a.cat, a.tag), (a.xyz, a.cat, a.tag),
+                          [(i, i) for i in range(0, a.n, 7)], 10.0)
+
+
+def test_environments_between_512_and_1024_members(gpu_ctx, oracle_mod):
+    """Protein-like structure at a 14.5 A threshold: environments of 300-900 members (fused gather, 1024-member
+    instantiation, 32 keys per lane in the register sort)."""
+    a = synth.gen(53, 500, 8, 7)
+    b = synth.partner(a, 1.0, 54)
+    op = set_both(gpu_ctx, oracle_mod, 7, [("uniform", (3.0, 14.0))], tag_rule={"accept_same": False})
+    _, ref = check_from_primitives(gpu_ctx, oracle_mod, op, (a.xyz, a.cat, a.tag), (b.xyz, b.cat, b.tag),
+                                   [(i, i) for i in range(0, a.n, 9)], 14.5)
+    assert 512 < ref["env_sizes"].max() <= 1024
