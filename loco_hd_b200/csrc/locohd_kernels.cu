@@ -676,7 +676,7 @@ __device__ __forceinline__ double fused_distance(double d2) {
 }
 
 template <int WFK, bool DEBUG, int CAP>
-__global__ void __launch_bounds__(kFusedWarps * 32, CAP == 512 ? 8 : 4) env_fused_kernel(StructsView s, KParams p, uint64_t n_env,
+__global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DEBUG ? 1 : 32 / fused_warps(CAP, DEBUG)) : 16 / fused_warps(CAP, DEBUG)) env_fused_kernel(StructsView s, KParams p, uint64_t n_env,
                                                                      const uint32_t* __restrict__ order,
                                                                      const uint32_t* __restrict__ anchor_struct,
                                                                      const uint32_t* __restrict__ anchor_prim,
@@ -711,10 +711,10 @@ __global__ void __launch_bounds__(kFusedWarps * 32, CAP == 512 ? 8 : 4) env_fuse
     // every CTA takes a contiguous block of the cell-ordered anchors: consecutive rounds read overlapping
     // candidate rows (L1 hits)
     uint64_t per_block = (n_env + gridDim.x - 1) / gridDim.x;
-    per_block = (per_block + kFusedWarps - 1) / kFusedWarps * kFusedWarps;
+    per_block = (per_block + fused_warps(CAP, DEBUG) - 1) / fused_warps(CAP, DEBUG) * fused_warps(CAP, DEBUG);
     const uint64_t t_end = min(n_env, (uint64_t)(blockIdx.x + 1) * per_block);
 #pragma unroll 1
-    for (uint64_t t = (uint64_t)blockIdx.x * per_block + wib; t < t_end; t += kFusedWarps) {
+    for (uint64_t t = (uint64_t)blockIdx.x * per_block + wib; t < t_end; t += fused_warps(CAP, DEBUG)) {
         __syncwarp();
         const uint64_t e = order[t];
         const uint64_t sid = anchor_struct ? anchor_struct[e] : 0;
@@ -1824,15 +1824,15 @@ static int fused_wfk(const KParams& p, const WfDev* host_wf, int key_is_w) {
 
 template <int WFK, bool DEBUG, int CAP>
 static unsigned fused_grid_t(uint64_t n_env) {
-    const int smem = FusedLayout<DEBUG, CAP>::kBytes * kFusedWarps;
+    const int smem = FusedLayout<DEBUG, CAP>::kBytes * fused_warps(CAP, DEBUG);
     cudaFuncSetAttribute(env_fused_kernel<WFK, DEBUG, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_fused_kernel<WFK, DEBUG, CAP>, kFusedWarps * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_fused_kernel<WFK, DEBUG, CAP>, fused_warps(CAP, DEBUG) * 32, smem);
     if (occ < 1) occ = 1;
     if (const char* v = std::getenv("LOCOHD_FUSED_CTAS")) { const int c = std::atoi(v); if (c >= 1 && c < occ) occ = c; }
-    const uint64_t need = (n_env + kFusedWarps - 1) / kFusedWarps;
+    const uint64_t need = (n_env + fused_warps(CAP, DEBUG) - 1) / fused_warps(CAP, DEBUG);
     const uint64_t cap = (uint64_t)sms * occ;
     return (unsigned)(need < cap ? need : cap);
 }
@@ -1841,8 +1841,8 @@ template <int WFK, bool DEBUG, int CAP>
 static void fused_launch_t(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
                            const uint32_t* anchor_prim, double threshold, const EnvBuild& b, FusedStats* stats,
                            uint64_t capacity, unsigned grid, cudaStream_t st) {
-    const int smem = FusedLayout<DEBUG, CAP>::kBytes * kFusedWarps;
-    env_fused_kernel<WFK, DEBUG, CAP><<<grid, kFusedWarps * 32, smem, st>>>(s, p, b.n_env, b.order, anchor_struct,
+    const int smem = FusedLayout<DEBUG, CAP>::kBytes * fused_warps(CAP, DEBUG);
+    env_fused_kernel<WFK, DEBUG, CAP><<<grid, fused_warps(CAP, DEBUG) * 32, smem, st>>>(s, p, b.n_env, b.order, anchor_struct,
                                                                             anchor_prim, threshold, b, stats, capacity);
 }
 
