@@ -708,14 +708,21 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
     uint64_t chunk_pos = 0, chunk_end = 0;   // warp-uniform: the reserved part of the store
     unsigned max_m = 0;
 
-    // every CTA takes a contiguous block of the cell-ordered anchors: consecutive rounds read overlapping
-    // candidate rows (L1 hits)
-    uint64_t per_block = (n_env + gridDim.x - 1) / gridDim.x;
-    per_block = (per_block + fused_warps(CAP, DEBUG) - 1) / fused_warps(CAP, DEBUG) * fused_warps(CAP, DEBUG);
+    // Every CTA takes a contiguous block of the cell-ordered anchors and its warps draw the next anchor from a
+    // shared cursor: at any time the warps of a CTA hold consecutive anchors (they do not drift apart as with a
+    // fixed stride), read overlapping candidate rows (L1 hits) and finish together.
+    __shared__ unsigned long long cta_cursor;
+    const uint64_t per_block = (n_env + gridDim.x - 1) / gridDim.x;
     const uint64_t t_end = min(n_env, (uint64_t)(blockIdx.x + 1) * per_block);
+    if (threadIdx.x == 0) cta_cursor = (uint64_t)blockIdx.x * per_block;
+    __syncthreads();
 #pragma unroll 1
-    for (uint64_t t = (uint64_t)blockIdx.x * per_block + wib; t < t_end; t += fused_warps(CAP, DEBUG)) {
+    for (;;) {
         __syncwarp();
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(&cta_cursor, 1ull);
+        t = __shfl_sync(kFull, t, 0);
+        if (t >= t_end) break;
         const uint64_t e = order[t];
         const uint64_t sid = anchor_struct ? anchor_struct[e] : 0;
         const uint32_t prim = anchor_prim[e];
@@ -808,46 +815,43 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
                 return (i < T) ? (uint32_t)((int)i + row_delta[row]) : 0xFFFFFFFFu;
             };
             // one round: 32 candidates, one per lane
-            auto test = [&](uint32_t j, const PrimRec& r, uint32_t rtag) {
-                bool acc = false;
-                double d2 = 0.0;
-                if (j != 0xFFFFFFFFu) {
-                    const double ex = r.x - q.x, ey = r.y - q.y, ez = r.z - q.z;
-                    d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
-                    acc = d2 < r2;
-                    if (acc && !(d2 < r2_safe)) {
-                        // within rounding distance of the sphere: the crate's per-axis box test can still reject
-                        acc = !(r.x < q.x - threshold) && !(r.x > q.x + threshold) && !(r.y < q.y - threshold) &&
-                              !(r.y > q.y + threshold) && !(r.z < q.z - threshold) && !(r.z > q.z + threshold);
-                    }
-                    if (simple_rule) acc = acc && (((rtag == qtag) == accept_same) || j == jpos);
-                    else if (acc && j != jpos) acc = tag_rule_accepts(p, qtag, rtag);
+            // Lanes past the end of the list test the anchor's own record with `valid` false (no branch around the
+            // loads or the arithmetic); a slot beyond CAP is clamped (the environment is rejected after the loop).
+            auto test = [&](bool valid, uint32_t j, const PrimRec& r, uint32_t rtag) {
+                const double ex = r.x - q.x, ey = r.y - q.y, ez = r.z - q.z;
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+                bool acc = valid && d2 < r2;
+                if (acc && !(d2 < r2_safe)) {
+                    // within rounding distance of the sphere: the crate's per-axis box test can still reject
+                    acc = !(r.x < q.x - threshold) && !(r.x > q.x + threshold) && !(r.y < q.y - threshold) &&
+                          !(r.y > q.y + threshold) && !(r.z < q.z - threshold) && !(r.z > q.z + threshold);
                 }
+                if (simple_rule) acc = acc && (((rtag == qtag) == accept_same) || j == jpos);
+                else if (acc && j != jpos) acc = tag_rule_accepts(p, qtag, rtag);
                 const unsigned mask = __ballot_sync(kFull, acc);
                 if (acc) {
-                    const uint32_t slot = M + __popc(mask & lt_mask);
-                    if (slot < (uint32_t)CAP) {
-                        d2s[slot] = d2;
-                        cats[slot] = (uint8_t)r.cat;
-                        key32[slot] = ((uint32_t)(d2 * qscale) << K::SB) | slot;
-                        if (DEBUG) sidx[slot] = r.orig;
-                    }
+                    const uint32_t slot = min(M + __popc(mask & lt_mask), (uint32_t)(CAP - 1));
+                    d2s[slot] = d2;
+                    cats[slot] = (uint8_t)r.cat;
+                    key32[slot] = ((uint32_t)(d2 * qscale) << K::SB) | slot;
+                    if (DEBUG) sidx[slot] = r.orig;
                 }
                 M += __popc(mask);
             };
             // two rounds per iteration: both records are requested before either is tested
 #pragma unroll 1
             for (uint32_t i0 = 0; i0 < T; i0 += 64) {
-                const uint32_t j0 = locate(i0);
-                const uint32_t j1 = (i0 + 32 < T) ? locate(i0 + 32) : 0xFFFFFFFFu;
-                PrimRec r0, r1;
-                uint32_t t0 = 0, t1 = 0;
-                r0.x = r0.y = r0.z = 0.0; r0.orig = 0; r0.cat = 0;
-                r1 = r0;
-                if (j0 != 0xFFFFFFFFu) { r0 = pd[j0]; t0 = __ldg(s.ptag + base + j0); }
-                if (j1 != 0xFFFFFFFFu) { r1 = pd[j1]; t1 = __ldg(s.ptag + base + j1); }
-                test(j0, r0, t0);
-                if (i0 + 32 < T) test(j1, r1, t1);
+                const uint32_t l0 = locate(i0);
+                const bool second = i0 + 32 < T;
+                const uint32_t l1 = second ? locate(i0 + 32) : 0xFFFFFFFFu;
+                const bool v0 = l0 != 0xFFFFFFFFu, v1 = l1 != 0xFFFFFFFFu;
+                const uint32_t j0 = v0 ? l0 : jpos, j1 = v1 ? l1 : jpos;
+                const PrimRec r0 = pd[j0];
+                const uint32_t t0 = __ldg(s.ptag + base + j0);
+                const PrimRec r1 = pd[j1];
+                const uint32_t t1 = __ldg(s.ptag + base + j1);
+                test(v0, j0, r0, t0);
+                if (second) test(v1, j1, r1, t1);
             }
         }
         __syncwarp();
