@@ -1194,6 +1194,7 @@ __global__ void rows_copy_kernel(const double* __restrict__ dmx, const uint8_t* 
 // K2: scoring.  One warp per anchor pair (persistent warps stride over the pairs).
 // ------------------------------------------------------------------------------------------------
 constexpr int kScoreMaxWarps = 8;
+constexpr int kScoreFastMaxWarps = 28;   // fast kernel: one large CTA per SM shares a single copy of the tables
 constexpr uint64_t kWMask = ~kCatMask;
 
 __host__ __device__ inline int score_state_bytes(int C) { return ((2 * C * 32 * 8 + 2 * C * 32 * 4) + 15) & ~15; }
@@ -1439,7 +1440,7 @@ __device__ __forceinline__ double sqrt_unit(double v) {
 }
 
 template <int CP, bool KEY_IS_W, bool CHECK>
-__global__ void __launch_bounds__(kScoreMaxWarps * 32) score_fast_kernel(ScoreArgs a, KParams P, int warps_per_block,
+__global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(ScoreArgs a, KParams P, int warps_per_block,
                                                                          int per_warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -2008,9 +2009,9 @@ int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsign
     a.only_unstaged = 0;
     const int tables = 3 * (int)table_n * 8;
     const int per_warp = fast_state_bytes(CP) + (int)stage * 8;
-    const int budget = 72 * 1024;  // three CTAs per SM
+    const int budget = 220 * 1024;  // one CTA per SM: the tables are staged once, the rest goes to the warps' stages
     int warps = (budget - tables) / per_warp;
-    if (warps > kScoreMaxWarps) warps = kScoreMaxWarps;
+    if (warps > kScoreFastMaxWarps) warps = kScoreFastMaxWarps;
     if (warps < 1) warps = 1;
     const int smem = tables + per_warp * warps;
     if (CP == 8) n += key_is_w ? launch_fast<8, true>(a, p, check, warps, per_warp, smem, st)
