@@ -1193,12 +1193,40 @@ __global__ void rows_copy_kernel(const double* __restrict__ dmx, const uint8_t* 
 // ------------------------------------------------------------------------------------------------
 // K2: scoring.  One warp per anchor pair (persistent warps stride over the pairs).
 // ------------------------------------------------------------------------------------------------
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) of one environment into a warp's stage, completion on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LOCOHD_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LOCOHD_DONE;\n"
+        "bra LOCOHD_WAIT;\n"
+        "LOCOHD_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 constexpr int kScoreMaxWarps = 8;
 constexpr int kScoreFastMaxWarps = 28;   // fast kernel: one large CTA per SM shares a single copy of the tables
 constexpr uint64_t kWMask = ~kCatMask;
 
 __host__ __device__ inline int score_state_bytes(int C) { return ((2 * C * 32 * 8 + 2 * C * 32 * 4) + 15) & ~15; }
-__host__ __device__ inline int fast_state_bytes(int CP) { return CP * 32 * 4; }
+__host__ __device__ inline int fast_state_bytes(int CP) { return CP * 32 * 4 + 16; }   // counts + the warp's mbarrier
 
 struct PairEnvs {
     bool ok;
@@ -1459,7 +1487,11 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
     const int C = P.C;
     unsigned char* mine = smem_raw + (size_t)3 * table_n * 8 + (size_t)wib * per_warp_bytes;
     uint32_t* cnt = reinterpret_cast<uint32_t*>(mine);                       // [CP][32]: A count | B count << 16
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(mine + CP * 32 * 4);
     uint64_t* stage = reinterpret_cast<uint64_t*>(mine + fast_state_bytes(CP));
+    if (lane == 0) { mbar_init(mbar, 1); fence_proxy_async(); }
+    __syncwarp();
+    unsigned mbar_parity = 0;
     auto sqrt_of = [&](uint32_t k) -> double {
         if (CHECK && k >= (uint32_t)table_n) return sqrt((double)k);
         return s_sqrt[k];
@@ -1481,15 +1513,17 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
         const uint32_t Ma = pe.Ma, Mb = pe.Mb;
         const uint32_t Ma_pad = (Ma + 1) & ~1u, Mb_pad = (Mb + 1) & ~1u;
         if ((int)(Ma_pad + Mb_pad) > a.stage_cap) continue;   // left to the generic kernel (second pass)
-        {   // environments start at even offsets: 16-byte loads
-            const ulonglong2* gA = reinterpret_cast<const ulonglong2*>(a.a.key + pe.oa);
-            const ulonglong2* gB = reinterpret_cast<const ulonglong2*>(a.b.key + pe.ob);
-            ulonglong2* sA = reinterpret_cast<ulonglong2*>(stage);
-            ulonglong2* sB = reinterpret_cast<ulonglong2*>(stage + Ma_pad);
-            for (uint32_t i = lane; i < Ma_pad / 2; i += 32) sA[i] = gA[i];
-            for (uint32_t i = lane; i < Mb_pad / 2; i += 32) sB[i] = gB[i];
+        // Both environments come in as TMA bulk copies (environments start at even offsets and are padded to even
+        // sizes: 16-byte granules); the warp waits on its mbarrier.  No LDG / STS instructions, no shared-memory
+        // wavefronts on the LSU pipe for the staging.
+        if (lane == 0) {
+            fence_proxy_async();   // the previous pair's reads of the stage come before the asynchronous writes
+            mbar_expect_tx(mbar, (Ma_pad + Mb_pad) * 8u);
+            bulk_g2s(stage, a.a.key + pe.oa, Ma_pad * 8u, mbar);
+            bulk_g2s(stage + Ma_pad, a.b.key + pe.ob, Mb_pad * 8u, mbar);
         }
-        __syncwarp();
+        mbar_wait(mbar, mbar_parity);
+        mbar_parity ^= 1u;
         const uint64_t* kA = stage;
         const uint64_t* kB = stage + Ma_pad;
         const uint64_t keyA0 = kA[0], keyB0 = kB[0];
