@@ -1225,7 +1225,8 @@ constexpr int kScoreMaxWarps = 8;
 constexpr int kScoreFastMaxWarps = 28;   // fast kernel: one large CTA per SM shares a single copy of the tables
 constexpr uint64_t kWMask = ~kCatMask;
 
-__host__ __device__ inline int score_state_bytes(int C) { return ((2 * C * 32 * 8 + 2 * C * 32 * 4) + 15) & ~15; }
+// per-lane values and counts of the generic kernel + the warp's mbarrier (16 bytes at the end)
+__host__ __device__ inline int score_state_bytes(int C) { return (((2 * C * 32 * 8 + 2 * C * 32 * 4) + 15) & ~15) + 16; }
 __host__ __device__ inline int fast_state_bytes(int CP) { return CP * 32 * 4 + 16; }   // counts + the warp's mbarrier
 
 struct PairEnvs {
@@ -1293,8 +1294,12 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
     unsigned char* mine = smem_raw + (size_t)wib * per_warp_bytes;
     double* val = reinterpret_cast<double*>(mine);                         // [2C][32]
     uint32_t* cnt = reinterpret_cast<uint32_t*>(mine + 2 * C * 32 * 8);    // [2C][32]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(mine + score_state_bytes(C) - 16);
     uint64_t* stage = reinterpret_cast<uint64_t*>(mine + score_state_bytes(C));
     const bool key_is_w = a.a.key_is_w != 0;
+    if (lane == 0) { mbar_init(mbar, 1); fence_proxy_async(); }
+    __syncwarp();
+    unsigned mbar_parity = 0;
 
     for (uint64_t pair = (uint64_t)blockIdx.x * warps_per_block + wib; pair < a.n_pairs;
          pair += (uint64_t)gridDim.x * warps_per_block) {
@@ -1306,11 +1311,16 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
         if (a.only_unstaged && (int)(Ma_pad + Mb_pad) <= a.only_unstaged) continue;  // the fast kernel scored it
         const uint64_t* kA = a.a.key + pe.oa;
         const uint64_t* kB = a.b.key + pe.ob;
-        if ((int)(Ma_pad + Mb_pad) <= a.stage_cap) {
-            for (uint32_t i = lane; i < Ma; i += 32) stage[i] = kA[i];
-            for (uint32_t i = lane; i < Mb; i += 32) stage[Ma_pad + i] = kB[i];
+        if ((int)(Ma_pad + Mb_pad) <= a.stage_cap) {   // staged by two TMA bulk copies, as in the fast kernel
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(mbar, (Ma_pad + Mb_pad) * 8u);
+                bulk_g2s(stage, kA, Ma_pad * 8u, mbar);
+                bulk_g2s(stage + Ma_pad, kB, Mb_pad * 8u, mbar);
+            }
+            mbar_wait(mbar, mbar_parity);
+            mbar_parity ^= 1u;
             kA = stage; kB = stage + Ma_pad;
-            __syncwarp();
         }
         const uint64_t keyA0 = kA[0], keyB0 = kB[0];
         if (!key_is_w && ((keyA0 & kWMask) != 0 || (keyB0 & kWMask) != 0)) { raise(P.err, LOCOHD_ERR_FIRST_NOT_ZERO); continue; }
