@@ -98,7 +98,7 @@ struct locohd_structs {
     StructMeta* d_meta = nullptr;
     float4* d_pf = nullptr;
     PrimRec* d_pd = nullptr;
-    uint32_t* d_ptag = nullptr;
+    uint32_t* d_porig = nullptr;
     uint32_t* d_sorted_pos = nullptr;
     uint32_t* d_cell_start = nullptr;
     uint32_t* d_cell_fill = nullptr;
@@ -107,7 +107,7 @@ struct locohd_structs {
     StructsView view() const {
         StructsView v;
         v.n_structs = n_structs; v.prim_off = d_prim_off; v.xyz = d_xyz; v.cat = d_cat; v.tag = d_tag;
-        v.meta = d_meta; v.pf = d_pf; v.pd = d_pd; v.ptag = d_ptag; v.sorted_pos = d_sorted_pos; v.cell_start = d_cell_start;
+        v.meta = d_meta; v.pf = d_pf; v.pd = d_pd; v.porig = d_porig; v.sorted_pos = d_sorted_pos; v.cell_start = d_cell_start;
         v.cell_fill = d_cell_fill;
         return v;
     }
@@ -871,7 +871,7 @@ int locohd_structs_create(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* p
     if ((st = dev_alloc(ctx, &s->d_prim_off, n_structs + 1)) || (st = dev_alloc(ctx, &s->d_xyz, 3 * n)) ||
         (st = dev_alloc(ctx, &s->d_cat, n)) || (st = dev_alloc(ctx, &s->d_tag, n)) ||
         (st = dev_alloc(ctx, &s->d_meta, n_structs)) || (st = dev_alloc(ctx, &s->d_pf, n)) ||
-        (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_ptag, n)) ||
+        (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_porig, n)) ||
         (st = dev_alloc(ctx, &s->d_sorted_pos, n)) ||
         (st = dev_alloc(ctx, &s->d_cell_start, cell_entries(n, n_structs))) ||
         (st = dev_alloc(ctx, &s->d_cell_fill, cell_entries(n, n_structs))))
@@ -898,7 +898,7 @@ void locohd_structs_destroy(locohd_structs* s) {
     locohd_ctx* ctx = s->ctx;
     DeviceGuard g(ctx->device);
     dev_free(ctx, s->d_prim_off); dev_free(ctx, s->d_xyz); dev_free(ctx, s->d_cat); dev_free(ctx, s->d_tag);
-    dev_free(ctx, s->d_meta); dev_free(ctx, s->d_pf); dev_free(ctx, s->d_pd); dev_free(ctx, s->d_ptag);
+    dev_free(ctx, s->d_meta); dev_free(ctx, s->d_pf); dev_free(ctx, s->d_pd); dev_free(ctx, s->d_porig);
     dev_free(ctx, s->d_sorted_pos);
     dev_free(ctx, s->d_cell_start); dev_free(ctx, s->d_cell_fill);
     delete s;
@@ -1197,7 +1197,7 @@ int locohd_from_primitives(locohd_ctx* ctx, uint64_t n_a, const double* xyz_a, c
     if ((st = dev_alloc(ctx, &s->d_prim_off, 3)) || (st = dev_alloc(ctx, &s->d_xyz, 3 * n)) ||
         (st = dev_alloc(ctx, &s->d_cat, n)) || (st = dev_alloc(ctx, &s->d_tag, n)) ||
         (st = dev_alloc(ctx, &s->d_meta, 2)) || (st = dev_alloc(ctx, &s->d_pf, n)) ||
-        (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_ptag, n)) ||
+        (st = dev_alloc(ctx, &s->d_pd, n)) || (st = dev_alloc(ctx, &s->d_porig, n)) ||
         (st = dev_alloc(ctx, &s->d_sorted_pos, n)) ||
         (st = dev_alloc(ctx, &s->d_cell_start, cell_entries(n, 2))) ||
         (st = dev_alloc(ctx, &s->d_cell_fill, cell_entries(n, 2))))

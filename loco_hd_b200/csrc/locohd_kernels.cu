@@ -292,10 +292,10 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
         const uint32_t pos = atomicAdd(&cell_fill[(cz * m.ny + cy) * m.nx + cx], 1u);
         PrimRec r;
         r.x = x; r.y = y; r.z = z;
-        r.orig = i;
+        r.tag = s.tag[base + i];
         r.cat = s.cat[base + i];
         s.pd[base + pos] = r;
-        s.ptag[base + pos] = s.tag[base + i];
+        s.porig[base + pos] = i;
         s.pf[base + pos] = make_float4((float)(x - m.ox), (float)(y - m.oy), (float)(z - m.oz),
                                        __uint_as_float(s.tag[base + i]));
         s.sorted_pos[base + i] = pos;
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
         }
     }
     PrimRec q;
-    q.x = q.y = q.z = 0.0; q.orig = 0; q.cat = 0;
+    q.x = q.y = q.z = 0.0; q.tag = 0; q.cat = 0;
     float4 qf = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) { q = s.pd[base + jpos]; qf = s.pf[base + jpos]; }
     const uint32_t qtag = __float_as_uint(qf.w);
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
                             if (cnt < cap) {
                                 b.key[off + cnt] = (uint64_t)__double_as_longlong(d2);  // sqrt in the sort kernel
                                 b.cat[off + cnt] = (uint8_t)r.cat;
-                                if (b.idx) b.idx[off + cnt] = r.orig;
+                                if (b.idx) b.idx[off + cnt] = s.porig[base + j];
                             }
                             ++cnt;
                         }
@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
                     d2s[slot] = d2;
                     cats[slot] = (uint8_t)r.cat;
                     key32[slot] = ((uint32_t)(d2 * qscale) << K::SB) | slot;
-                    if (DEBUG) sidx[slot] = r.orig;
+                    if (DEBUG) sidx[slot] = __ldg(s.porig + base + j);
                 }
                 M += __popc(mask);
             };
@@ -847,11 +847,9 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
                 const bool v0 = l0 != 0xFFFFFFFFu, v1 = l1 != 0xFFFFFFFFu;
                 const uint32_t j0 = v0 ? l0 : jpos, j1 = v1 ? l1 : jpos;
                 const PrimRec r0 = pd[j0];
-                const uint32_t t0 = __ldg(s.ptag + base + j0);
                 const PrimRec r1 = pd[j1];
-                const uint32_t t1 = __ldg(s.ptag + base + j1);
-                test(v0, j0, r0, t0);
-                if (second) test(v1, j1, r1, t1);
+                test(v0, j0, r0, r0.tag);
+                if (second) test(v1, j1, r1, r1.tag);
             }
         }
         __syncwarp();

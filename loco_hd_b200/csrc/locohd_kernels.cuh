@@ -14,7 +14,7 @@ constexpr uint64_t kCatMask = 0xFFull;  // low byte of a packed key = category
 // One primitive in cell-sorted order: exact coordinates for the FP64 membership test and distance.
 struct __align__(32) PrimRec {
     double x, y, z;
-    uint32_t orig;  // index inside its structure, original order
+    uint32_t tag;   // interned tag id
     uint32_t cat;   // category id (0..254) or kUnknownCat8
 };
 
@@ -66,7 +66,7 @@ struct StructsView {
     StructMeta* meta;             // [n_structs]
     float4* pf;                   // cell-sorted: (x - ox, y - oy, z - oz) as f32, w = tag bits
     PrimRec* pd;                  // cell-sorted exact records
-    uint32_t* ptag;               // cell-sorted tag ids (fused gather)
+    uint32_t* porig;              // cell-sorted position -> index inside the structure, original order (parity dumps)
     uint32_t* sorted_pos;         // original index -> cell-sorted position (inside the structure)
     uint32_t* cell_start;         // [cell_entries]: first cell-sorted position of every cell
     uint32_t* cell_fill;          // [cell_entries]: scratch cursor of the counting sort
