@@ -1219,6 +1219,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         : "memory");
 }
 
+constexpr uint64_t kSentinel = ~0ull;   // staged behind either list of the fast kernel: above every key
 constexpr int kScoreMaxWarps = 8;
 constexpr int kScoreFastMaxWarps = 28;   // fast kernel: one large CTA per SM shares a single copy of the tables
 constexpr uint64_t kWMask = ~kCatMask;
@@ -1524,16 +1525,20 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
         // Both environments come in as TMA bulk copies (environments start at even offsets and are padded to even
         // sizes: 16-byte granules); the warp waits on its mbarrier.  No LDG / STS instructions, no shared-memory
         // wavefronts on the LSU pipe for the staging.
+        // A sentinel (all ones: above every key) follows either list in the stage, so the walk needs no bounds.
+        const uint32_t Ma_st = (Ma + 2) & ~1u;   // even, >= Ma + 1: B starts behind A's sentinel
         if (lane == 0) {
             fence_proxy_async();   // the previous pair's reads of the stage come before the asynchronous writes
             mbar_expect_tx(mbar, (Ma_pad + Mb_pad) * 8u);
             bulk_g2s(stage, a.a.key + pe.oa, Ma_pad * 8u, mbar);
-            bulk_g2s(stage + Ma_pad, a.b.key + pe.ob, Mb_pad * 8u, mbar);
+            bulk_g2s(stage + Ma_st, a.b.key + pe.ob, Mb_pad * 8u, mbar);
         }
         mbar_wait(mbar, mbar_parity);
         mbar_parity ^= 1u;
+        if (lane == 0) { stage[Ma] = kSentinel; stage[Ma_st + Mb] = kSentinel; }
+        __syncwarp();
         const uint64_t* kA = stage;
-        const uint64_t* kB = stage + Ma_pad;
+        const uint64_t* kB = stage + Ma_st;
         const uint64_t keyA0 = kA[0], keyB0 = kB[0];
         if (!KEY_IS_W && ((keyA0 & kWMask) != 0 || (keyB0 & kWMask) != 0)) { raise(P.err, LOCOHD_ERR_FIRST_NOT_ZERO); continue; }
         const uint32_t catA0 = (uint32_t)(keyA0 & kCatMask), catB0 = (uint32_t)(keyB0 & kCatMask);
@@ -1619,10 +1624,13 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
         double h = stat_dist();
         double acc = 0.0;
 
-        uint64_t ra = (i < i1) ? kA[i] : 0, rb = (j < j1) ? kB[j] : 0;
+        // The first nev events of the merge that starts at (i, j) are exactly my chunk (same comparison as the
+        // merge-path split: A before B on ties); the sentinels end the lists.
+        const uint32_t nev = (i1 - i) + (j1 - j);
+        uint64_t ra = kA[i], rb = kB[j];
         int since_refresh = 0;
-        while (i < i1 || j < j1) {
-            const bool takeA = (i < i1) && (!(j < j1) || (ra & kWMask) <= (rb & kWMask));
+        for (uint32_t it = 0; it < nev; ++it) {
+            const bool takeA = (ra & kWMask) <= (rb & kWMask);
             const uint64_t raw = takeA ? ra : rb;
             const uint32_t c = (uint32_t)(raw & kCatMask);
             const double w = weight(raw);
@@ -1643,9 +1651,7 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
                 rB = takeA ? rB : rnew;
                 i += takeA ? 1u : 0u;
                 j += takeA ? 0u : 1u;
-                const bool more = takeA ? (i < i1) : (j < j1);
-                const uint64_t* src = takeA ? (kA + i) : (kB + j);
-                const uint64_t nxt = more ? *src : 0ull;
+                const uint64_t nxt = *(takeA ? (kA + i) : (kB + j));
                 ra = takeA ? nxt : ra;
                 rb = takeA ? rb : nxt;
             }
@@ -2050,7 +2056,7 @@ int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsign
     a.stage_cap = (int)stage;
     a.only_unstaged = 0;
     const int tables = 3 * (int)table_n * 8;
-    const int per_warp = fast_state_bytes(CP) + (int)stage * 8;
+    const int per_warp = fast_state_bytes(CP) + ((int)stage + 4) * 8;   // + the two sentinels and their padding
     const int budget = 220 * 1024;  // one CTA per SM: the tables are staged once, the rest goes to the warps' stages
     int warps = (budget - tables) / per_warp;
     if (warps > kScoreFastMaxWarps) warps = kScoreFastMaxWarps;
