@@ -1460,11 +1460,10 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
 //   * identical counts give H = 0 exactly (as upstream, and as the difference form does),
 //   * H^2 < kSmallH2 (only reachable for environments of thousands of members, or proportional compositions) is
 //     recomputed in the difference form sum_r (sqrt(a_r) rA - sqrt(b_r) rB)^2 from the counts,
-//   * D is rebuilt from the counts every kRefresh events, so rounding cannot drift.
+//   * D is rebuilt from the counts at the start of every lane's chunk (at most 64 events), so rounding cannot drift.
 // Error of the fast branch: |dH| <= ~5e-16 / (2 * sqrt(kSmallH2)) = 2.5e-12 (bar: 1e-9 on the score).
 // With KEY_IS_W the environments already hold W(distance).  Pairs that do not fit the stage are left to score_kernel.
 constexpr double kSmallH2 = 1e-8;
-constexpr int kRefresh = 64;
 
 // sqrt of a double in [1e-8, ~1]: MUFU.RSQ (f32) seed + one coupled Newton step in FP64, relative error
 // 1.5 * 2^-44 = 8.5e-14.  Used for H itself (nothing amplifies the error; bar 1e-9 on the score); IEEE sqrt costs
@@ -1628,7 +1627,6 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
         // merge-path split: A before B on ties); the sentinels end the lists.
         const uint32_t nev = (i1 - i) + (j1 - j);
         uint64_t ra = kA[i], rb = kB[j];
-        int since_refresh = 0;
         for (uint32_t it = 0; it < nev; ++it) {
             const bool takeA = (ra & kWMask) <= (rb & kWMask);
             const uint64_t raw = takeA ? ra : rb;
@@ -1655,7 +1653,6 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
                 ra = takeA ? nxt : ra;
                 rb = takeA ? rb : nxt;
             }
-            if (++since_refresh == kRefresh) { since_refresh = 0; rebuild(); }
             h = stat_dist();
         }
         if (lane == 31) acc = fma(wf.w_inf - wprev, h, acc);
