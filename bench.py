@@ -439,11 +439,13 @@ def run_gpu(args, rank, local_rank, world):
                "fill": ("env_fused_kernel (K1: row pruning, exact FP64 gather, register bitonic sort, CDF, packing)",
                         f_gather),
                "count": ("env_tile_kernel<false> with stride 16 (store sizing sample)", 0.0)}
-    traffic = {}
+    traffic, pipes, prof_src = {}, {}, None
     try:
         tr = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
         if tr.get("workload") == wl.name and tr.get("anchor_pairs_per_step") == wl.n_pairs:
             traffic = tr.get("dram_bytes_per_launch", {})
+            pipes = tr.get("pipes", {})
+            prof_src = tr.get("source")
     except (OSError, ValueError):
         pass
     per_kernel = {}
@@ -452,6 +454,8 @@ def run_gpu(args, rank, local_rank, world):
             ach = flops / (kernels[g]["ms_per_step"] * 1e-3) / 1e12
             per_kernel[g] = {"kernel": name, "launch_ms": kernels[g]["ms_per_step"], "alg_flops_per_launch": flops,
                              "achieved_tflops": ach, "frac_of_fp64_peak": ach / fp64_peak, "traffic": traffic.get(g)}
+            if g in pipes:   # from the committed ncu capture of the same workload (not measured in this run)
+                per_kernel[g]["ncu"] = dict(pipes[g], source=prof_src)
     dom = max(per_kernel, key=lambda g: per_kernel[g]["launch_ms"])
     dominant, dom_flops, dom_ms = per_kernel[dom]["kernel"], per_kernel[dom]["alg_flops_per_launch"], per_kernel[dom]["launch_ms"]
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12

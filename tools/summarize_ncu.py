@@ -80,8 +80,20 @@ if lf.exists():
             continue
         out.append(f"| {n} | {c} | {v / 1e6:.3f} | {100 * v / tot:.1f}% |")
 (ROOT / "profiles" / f"{tag}_ncu_summary.md").write_text("\n".join(out) + "\n")
+# issue-slot utilisation and instruction counts of the same launches (bench.py quotes them beside the rooflines)
+pipes = {}
+for r, n in zip(kernels, names):
+    for k, g in group.items():
+        if (n.startswith(k) or k in n) and g not in pipes:
+            def val(m):
+                return float(r[hdr.index(m)]) if m in hdr else None
+            pipes[g] = {"warp_instructions": val("smsp__inst_executed.sum"),
+                        "issue_slots_busy_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                        "shared_pipe_busy_pct": val("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                        "fp64_pipe_pct": val("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")}
+            break
 (ROOT / "profiles" / "r1_traffic.json").write_text(json.dumps(
     {"workload": "cfg2", "anchor_pairs_per_step": 2560000, "source": f"profiles/{tag}_ncu_summary.md",
-     "dram_bytes_per_launch": traffic}, indent=1) + "\n")
+     "dram_bytes_per_launch": traffic, "pipes": pipes}, indent=1) + "\n")
 print("\n".join(out[:40]))
 print(traffic)
