@@ -382,9 +382,11 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
                                                                 double threshold, uint32_t* __restrict__ ub,
                                                                 EnvBuild b, uint32_t stride,
                                                                 unsigned long long* sample_sum) {
-    // stride > 1 (count mode only): every stride-th anchor is visited and the sizes are summed into *sample_sum
+    // stride > 1 (count mode only): every stride-th group of 32 consecutive anchors is visited (a warp keeps
+    // neighbouring anchors, so its lanes walk the same candidate rows) and the sizes are summed into *sample_sum
     const int tid = threadIdx.x;
-    const uint64_t t = ((uint64_t)blockIdx.x * kTileThreads + tid) * stride;
+    const uint64_t t0 = (uint64_t)blockIdx.x * kTileThreads + tid;
+    const uint64_t t = (t0 >> 5) * 32 * stride + (t0 & 31);
     bool active = t < n_env;
     const uint64_t e = active ? order[t] : 0;
     uint64_t base = 0;
@@ -1857,7 +1859,7 @@ int launch_env_sample(const StructsView& s, const KParams& p, uint64_t n_env, co
                       unsigned long long* sum, cudaStream_t st) {
     if (!n_env) return 0;
     EnvBuild none{};
-    const uint64_t n_vis = (n_env + stride - 1) / stride;
+    const uint64_t n_vis = ((n_env + 32ull * stride - 1) / (32ull * stride)) * 32;   // whole groups of 32 anchors
     env_tile_kernel<false><<<blocks_for(n_vis, kTileThreads), kTileThreads, 0, st>>>(
         s, p, n_env, order, anchor_struct, anchor_prim, threshold, nullptr, none, stride, sum);
     return 1;
