@@ -91,6 +91,7 @@ struct ProfScope {
 struct locohd_structs {
     locohd_ctx* ctx = nullptr;
     uint64_t n_structs = 0, n_prims = 0;
+    uint64_t max_prims = 0;          // largest structure
     uint64_t* d_prim_off = nullptr;
     double* d_xyz = nullptr;
     uint8_t* d_cat = nullptr;
@@ -395,7 +396,7 @@ int make_wf(locohd_ctx* ctx, const locohd_weight_function& in, WfDev* out) {
 int ensure_cells(locohd_structs* s, double threshold) {
     locohd_ctx* ctx = s->ctx;
     if (s->cells_valid && s->cell_threshold == threshold) return 0;
-    { ProfScope ps(ctx, LOCOHD_PROF_CELLS); ctx->launches += launch_build_cells(s->view(), threshold, ctx->stream); }
+    { ProfScope ps(ctx, LOCOHD_PROF_CELLS); ctx->launches += launch_build_cells(s->view(), threshold, s->max_prims, ctx->stream); }
     CU(ctx, cudaGetLastError());
     s->cells_valid = true;
     s->cell_threshold = threshold;
@@ -866,6 +867,7 @@ int locohd_structs_create(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* p
     if (n && (!xyz || !category || !tag)) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null primitive arrays");
     locohd_structs* s = new locohd_structs();
     s->ctx = ctx; s->n_structs = n_structs; s->n_prims = n;
+    for (uint64_t k = 0; k < n_structs; ++k) s->max_prims = std::max<uint64_t>(s->max_prims, offs[k + 1] - offs[k]);
     auto bail = [&](int st) { locohd_structs_destroy(s); return st; };
     int st;
     if ((st = dev_alloc(ctx, &s->d_prim_off, n_structs + 1)) || (st = dev_alloc(ctx, &s->d_xyz, 3 * n)) ||
@@ -1185,6 +1187,7 @@ int locohd_from_primitives(locohd_ctx* ctx, uint64_t n_a, const double* xyz_a, c
     // one structure set holding A then B
     locohd_structs* s = new locohd_structs();
     s->ctx = ctx; s->n_structs = 2; s->n_prims = n;
+    s->max_prims = std::max<uint64_t>(n_a, n_b);
     locohd_envset* env = nullptr;
     uint32_t *d_as = nullptr, *d_ap = nullptr;
     auto cleanup = [&](int st) {

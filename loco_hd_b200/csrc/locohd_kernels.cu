@@ -151,7 +151,11 @@ __device__ __forceinline__ int cell_coord(double rel, double inv_cell, int n) {
     return min(max(c, 0), n - 1);
 }
 
-__global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s, double threshold) {
+// SMEM: cell counters / cursors of structures whose grid fits the dynamic shared memory live there (shared-memory
+// atomics, one scan pass); larger grids use the global arrays.
+template <bool SMEM>
+__global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s, double threshold, int smem_words) {
+    extern __shared__ uint32_t sm_cells[];
     __shared__ double red[6][kCellThreads / 32];
     __shared__ StructMeta sm_meta;
     __shared__ unsigned long long sh_carry;
@@ -252,35 +256,56 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
     __syncthreads();
     const StructMeta m = sm_meta;
     const int ncell = m.nx * m.ny * m.nz;
-    for (int c = tid; c <= ncell; c += kCellThreads) cell_start[c] = 0;
+    const bool in_smem = SMEM && ncell + 1 <= smem_words;   // uniform over the CTA
+    uint32_t* cnt = in_smem ? sm_cells : cell_start;
+    for (int c = tid; c <= ncell; c += kCellThreads) cnt[c] = 0;
     __syncthreads();
 
-    // ---- histogram (global atomics: the grid can be larger than shared memory)
+    // ---- histogram
     for (uint32_t i = tid; i < n; i += kCellThreads) {
         const double x = xyz[3 * (uint64_t)i], y = xyz[3 * (uint64_t)i + 1], z = xyz[3 * (uint64_t)i + 2];
         const int cx = cell_coord(x - m.ox, m.inv_cell_x, m.nx);
         const int cy = cell_coord(y - m.oy, m.inv_cell, m.ny);
         const int cz = cell_coord(z - m.oz, m.inv_cell, m.nz);
-        atomicAdd(&cell_start[(cz * m.ny + cy) * m.nx + cx], 1u);
+        atomicAdd(&cnt[(cz * m.ny + cy) * m.nx + cx], 1u);
     }
     __syncthreads();
 
-    // ---- exclusive scan over the cells, kCellThreads cells per round
-    for (int c0 = 0; c0 < ncell; c0 += kCellThreads) {
-        const int c = c0 + tid;
-        const unsigned long long v = (c < ncell) ? cell_start[c] : 0u;
-        unsigned long long tot;
-        const unsigned long long ex = block_exclusive_scan(v, &tot);
-        const unsigned long long carry = sh_carry;
-        if (c < ncell) {
-            cell_start[c] = (uint32_t)(carry + ex);
-            cell_fill[c] = (uint32_t)(carry + ex);
+    uint32_t* fill;
+    if (in_smem) {
+        // ---- exclusive scan in shared memory: a contiguous run of cells per thread, one block scan of the run sums
+        const int per = (ncell + kCellThreads - 1) / kCellThreads;
+        const int c_lo = min(tid * per, ncell), c_hi = min(c_lo + per, ncell);
+        unsigned long long sum = 0;
+        for (int c = c_lo; c < c_hi; ++c) sum += cnt[c];
+        unsigned long long run = block_exclusive_scan(sum, nullptr);
+        for (int c = c_lo; c < c_hi; ++c) {
+            const uint32_t v = cnt[c];
+            cnt[c] = (uint32_t)run;          // from here on: the fill cursor of the cell
+            cell_start[c] = (uint32_t)run;
+            run += v;
         }
-        __syncthreads();
-        if (tid == 0) sh_carry = carry + tot;
-        __syncthreads();
+        if (tid == 0) cell_start[ncell] = n;
+        fill = cnt;
+    } else {
+        // ---- exclusive scan over the cells in global memory, kCellThreads cells per round
+        for (int c0 = 0; c0 < ncell; c0 += kCellThreads) {
+            const int c = c0 + tid;
+            const unsigned long long v = (c < ncell) ? cell_start[c] : 0u;
+            unsigned long long tot;
+            const unsigned long long ex = block_exclusive_scan(v, &tot);
+            const unsigned long long carry = sh_carry;
+            if (c < ncell) {
+                cell_start[c] = (uint32_t)(carry + ex);
+                cell_fill[c] = (uint32_t)(carry + ex);
+            }
+            __syncthreads();
+            if (tid == 0) sh_carry = carry + tot;
+            __syncthreads();
+        }
+        if (tid == 0) cell_start[ncell] = n;
+        fill = cell_fill;
     }
-    if (tid == 0) cell_start[ncell] = n;
     __syncthreads();
 
     // ---- scatter into cell order
@@ -289,7 +314,7 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
         const int cx = cell_coord(x - m.ox, m.inv_cell_x, m.nx);
         const int cy = cell_coord(y - m.oy, m.inv_cell, m.ny);
         const int cz = cell_coord(z - m.oz, m.inv_cell, m.nz);
-        const uint32_t pos = atomicAdd(&cell_fill[(cz * m.ny + cy) * m.nx + cx], 1u);
+        const uint32_t pos = atomicAdd(&fill[(cz * m.ny + cy) * m.nx + cx], 1u);
         PrimRec r;
         r.x = x; r.y = y; r.z = z;
         r.tag = s.tag[base + i];
@@ -297,7 +322,7 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
         s.pd[base + pos] = r;
         s.porig[base + pos] = i;
         s.pf[base + pos] = make_float4((float)(x - m.ox), (float)(y - m.oy), (float)(z - m.oz),
-                                       __uint_as_float(s.tag[base + i]));
+                                       __uint_as_float(r.tag));
         s.sorted_pos[base + i] = pos;
     }
 }
@@ -1813,9 +1838,17 @@ int launch_validate_xyz(const double* xyz, uint64_t n3, int* err, cudaStream_t s
     return 1;
 }
 
-int launch_build_cells(const StructsView& s, double threshold, cudaStream_t st) {
+int launch_build_cells(const StructsView& s, double threshold, uint64_t max_prims, cudaStream_t st) {
     if (!s.n_structs) return 0;
-    build_cells_kernel<<<(unsigned)s.n_structs, kCellThreads, 0, st>>>(s, threshold);
+    // a structure has at most max(2 N, 8) cells (+ the end marker)
+    const uint64_t words = (2 * max_prims > 8 ? 2 * max_prims : 8) + 1;
+    if (words * 4 <= 160 * 1024) {
+        const int smem = (int)(words * 4);
+        cudaFuncSetAttribute(build_cells_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        build_cells_kernel<true><<<(unsigned)s.n_structs, kCellThreads, smem, st>>>(s, threshold, (int)words);
+    } else {
+        build_cells_kernel<false><<<(unsigned)s.n_structs, kCellThreads, 0, st>>>(s, threshold, 0);
+    }
     return 1;
 }
 

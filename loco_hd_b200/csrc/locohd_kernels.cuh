@@ -139,7 +139,8 @@ struct ScoreArgs {
 // ---- launchers (all asynchronous on `st`; each returns the number of kernel launches it made) ----
 int launch_convert_categories(const uint16_t* in, uint8_t* out, uint64_t n, int C, cudaStream_t st);
 int launch_validate_xyz(const double* xyz, uint64_t n3, int* err, cudaStream_t st);
-int launch_build_cells(const StructsView& s, double threshold, cudaStream_t st);
+// max_prims: size of the largest structure (selects the shared-memory variant of the counting sort)
+int launch_build_cells(const StructsView& s, double threshold, uint64_t max_prims, cudaStream_t st);
 // anchors -> cell order: slot_cnt / slot_off are scratch of n_prims (+1) entries
 int launch_anchor_order(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* anchor_struct,
                         const uint32_t* anchor_prim, uint64_t n_prims, uint32_t* slot_cnt, uint64_t* slot_off,
