@@ -534,8 +534,8 @@ __device__ __forceinline__ uint64_t pack_key(double w, uint32_t cat) {
 //             cells are never smaller than r / 2): rows farther than r in the y-z plane are dropped, the x range of
 //             the others is cut to sqrt(r^2 - gap^2), in f32 with conservative margins (build_cells_kernel)
 //   gather    lanes over the flat concatenation of the rows (coalesced 32-byte records, the next round is loaded
-//             while the current one is tested); the row of a flat index comes from one REDUX.OR of the row-start
-//             bits + popc, no search loop.  Exact membership: the kd-tree crate's predicate in FP64 with unfused
+//             while the current one is tested); the row of a flat index comes from a bitmap of the row starts
+//             + popc, no search loop.  Exact membership: the kd-tree crate's predicate in FP64 with unfused
 //             arithmetic (as env_tile_kernel<true>) + tag rule; members are ballot-compacted into shared memory:
 //             squared distance, category and a 32-bit sort key = 23-bit fixed-point squared distance << 9 | slot.
 //             (No FP32 prefilter here: with a warp per anchor every lane tests a different candidate, the FP64
@@ -554,7 +554,9 @@ struct FusedLayout {
     static constexpr int kD2Off = 0;                              // f64 [CAP] exact squared distances
     static constexpr int kKeyOff = kD2Off + 8 * CAP;              // u32 [CAP] sort keys
     static constexpr int kRowOff = kKeyOff + 4 * CAP;             // i32 [32] row delta (start - flat prefix)
-    static constexpr int kCatOff = kRowOff + 4 * 32;              // u8 [CAP]
+    static constexpr int kMaskWords = CAP / 8;                    // row-start bits of up to 4 CAP candidates
+    static constexpr int kMaskOff = kRowOff + 4 * 32;             // u32 [kMaskWords]
+    static constexpr int kCatOff = kMaskOff + 4 * kMaskWords;     // u8 [CAP]
     static constexpr int kIdxOff = kCatOff + CAP;                 // u32 [CAP] (DEBUG)
     static constexpr int kBytes = (kIdxOff + (DEBUG ? 4 * CAP : 0) + 15) & ~15;
 };
@@ -717,6 +719,7 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
     double* d2s = reinterpret_cast<double*>(smem + L::kD2Off);
     uint32_t* key32 = reinterpret_cast<uint32_t*>(smem + L::kKeyOff);
     int* row_delta = reinterpret_cast<int*>(smem + L::kRowOff);
+    uint32_t* row_mask = reinterpret_cast<uint32_t*>(smem + L::kMaskOff);
     uint8_t* cats = smem + L::kCatOff;
     uint32_t* sidx = reinterpret_cast<uint32_t*>(smem + L::kIdxOff);
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -820,6 +823,14 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
             if (my_len > 0) row_delta[__popc(nonempty & lt_mask)] = (int)start - (int)my_pre;
         }
         const uint32_t T = __shfl_sync(kFull, my_pre + my_len, 31);
+        if (T > 32u * L::kMaskWords) {   // more candidates than the row-start bitmap covers: multi-kernel path
+            if (lane == 0) { atomicOr(&stats->overflow, 16u); b.count[e] = 0; b.off_out[e] = 0; }
+            continue;
+        }
+        // bitmap of the flat positions at which a row starts: one shared-memory read per round locates the rows
+        for (uint32_t w = lane; w <= (T >> 5) && w < (uint32_t)L::kMaskWords; w += 32) row_mask[w] = 0;
+        __syncwarp();
+        if (my_len > 0) atomicOr(&row_mask[my_pre >> 5], 1u << (my_pre & 31u));
         __syncwarp();
 
         // ---- candidates: lanes over the flat concatenation of the rows; exact membership with the kd-tree crate's
@@ -831,11 +842,9 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
         uint32_t M = 0;
         {
             int row_base = -1;   // compacted row of the last candidate of the previous round
-            // flat index -> cell-sorted position; one REDUX.OR of the row-start bits, no search
+            // flat index -> cell-sorted position: row = rows started up to my position (bitmap + popc), no search
             auto locate = [&](uint32_t i0) -> uint32_t {
-                const uint32_t dpos = my_pre - i0;   // does my row start inside this round?
-                const unsigned bit = (my_len > 0 && dpos < 32u) ? (1u << dpos) : 0u;
-                const unsigned starts = __reduce_or_sync(kFull, bit);
+                const unsigned starts = row_mask[i0 >> 5];
                 const int row = row_base + __popc(starts & le_mask);
                 row_base += __popc(starts);
                 const uint32_t i = i0 + lane;
