@@ -624,8 +624,10 @@ __device__ __forceinline__ void warp_bitonic(uint32_t (&k)[PER], int lane) {
     }
 }
 
-template <int PER>
-__device__ __noinline__ void fused_sort(uint32_t* key32, uint32_t M, int lane) {
+// Sorts key32[0, M) in place.  Returns (warp-uniform) whether two neighbours of the sorted order share their
+// fixed-point distance (key >> SB): only then does the caller compare exact distances.
+template <int PER, int SB>
+__device__ __noinline__ bool fused_sort(uint32_t* key32, uint32_t M, int lane) {
     uint32_t k[PER];
 #pragma unroll
     for (int r = 0; r < PER; ++r) {
@@ -634,12 +636,17 @@ __device__ __noinline__ void fused_sort(uint32_t* key32, uint32_t M, int lane) {
     }
     __syncwarp();
     warp_bitonic<PER>(k, lane);
+    bool tie = false;
+    const uint32_t next0 = __shfl_down_sync(kFull, k[0], 1);   // first key of the next lane
 #pragma unroll
     for (int r = 0; r < PER; ++r) {
         const uint32_t g = (uint32_t)(lane * PER + r);
         if (g < M) key32[g] = k[r];
+        const uint32_t nb = (r + 1 < PER) ? k[(r + 1) % PER] : next0;
+        tie |= (g + 1 < M) && ((k[r] >> SB) == (nb >> SB)) && (r + 1 < PER || lane < 31);
     }
     __syncwarp();
+    return __any_sync(kFull, tie);
 }
 
 // serial repair of groups with equal fixed-point distance (order by exact squared distance, category, slot)
@@ -911,11 +918,12 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
         }
 
         // ---- sort
-        if (M <= 128) fused_sort<4>(key32, M, lane);
-        else if (M <= 256) fused_sort<8>(key32, M, lane);
-        else if (CAP == 512 || M <= 512) fused_sort<16>(key32, M, lane);
-        else fused_sort<CAP == 512 ? 16 : 32>(key32, M, lane);
-        {   // equal fixed-point distances: order by the exact (distance, category)
+        bool ties;
+        if (M <= 128) ties = fused_sort<4, K::SB>(key32, M, lane);
+        else if (M <= 256) ties = fused_sort<8, K::SB>(key32, M, lane);
+        else if (CAP == 512 || M <= 512) ties = fused_sort<16, K::SB>(key32, M, lane);
+        else ties = fused_sort<CAP == 512 ? 16 : 32, K::SB>(key32, M, lane);
+        if (ties) {   // equal fixed-point distances (rare): order by the exact (distance, category)
             bool viol = false;
             for (uint32_t g = lane; g + 1 < M; g += 32) {
                 const uint32_t ka = key32[g], kb = key32[g + 1];
