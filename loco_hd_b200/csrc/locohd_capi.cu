@@ -433,10 +433,11 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
     e->n_env = n_anchors;
     e->key_is_w = ctx->kp.n_wf == 1;  // a single weight function: the store holds W(distance) directly
     uint32_t *d_order = nullptr, *d_slot_cnt = nullptr, *d_ub = nullptr;
+    uint2* d_order_rec = nullptr;
     uint64_t *d_slot_off = nullptr, *d_scratch = nullptr;
     uint8_t* d_cat = nullptr;
     auto release = [&]() {
-        dev_free(ctx, d_order); dev_free(ctx, d_slot_cnt); dev_free(ctx, d_ub); dev_free(ctx, d_slot_off);
+        dev_free(ctx, d_order); dev_free(ctx, d_order_rec); dev_free(ctx, d_slot_cnt); dev_free(ctx, d_ub); dev_free(ctx, d_slot_off);
         dev_free(ctx, d_scratch); dev_free(ctx, d_cat);
     };
     auto bail = [&](int st) { release(); destroy_envset(e); return st; };
@@ -450,14 +451,14 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
     }
     const uint64_t n_prims = s->n_prims;
     const uint64_t scratch_n = std::max(scan_scratch_entries(n_prims + 1), scan_scratch_entries(n_anchors));
-    if ((st = dev_alloc(ctx, &d_order, n_anchors)) || (st = dev_alloc(ctx, &d_slot_cnt, n_prims + 1)) ||
+    if ((st = dev_alloc(ctx, &d_order, n_anchors)) || (st = dev_alloc(ctx, &d_order_rec, n_anchors)) || (st = dev_alloc(ctx, &d_slot_cnt, n_prims + 1)) ||
         (st = dev_alloc(ctx, &d_slot_off, n_prims + 2)) || (st = dev_alloc(ctx, &d_scratch, scratch_n)) ||
         (st = dev_alloc(ctx, &d_ub, n_anchors)))
         return bail(st);
     {
         ProfScope ps(ctx, LOCOHD_PROF_OTHER);
         ctx->launches += launch_anchor_order(sv, ctx->kp, n_anchors, d_anchor_struct, d_anchor_prim, n_prims, d_slot_cnt,
-                                             d_slot_off, d_scratch, ctx->d_scan, d_order, ctx->stream);
+                                             d_slot_off, d_scratch, ctx->d_scan, d_order, d_order_rec, ctx->stream);
     }
     tr.mark("cells + order launched");
     // ---- fused path: sample the sizes (every anchor for small calls), reserve the store, one kernel does the rest
@@ -504,7 +505,8 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
             }
             tr.mark("store allocation");
             EnvBuild b{};
-            b.n_env = n_anchors; b.order = d_order; b.ub = nullptr; b.off = nullptr; b.off_out = e->d_off; b.count = e->d_count;
+            b.n_env = n_anchors; b.order = d_order; b.order_rec = d_order_rec; b.ub = nullptr; b.off = nullptr; b.off_out = e->d_off;
+            b.count = e->d_count;
             b.key = e->d_key; b.cat = nullptr; b.idx = e->d_idx; b.dist = e->d_dist; b.key_is_w = e->key_is_w ? 1 : 0;
             b.key_is_sq = 1; b.check_first_zero = 0;
             cudaMemsetAsync(&ctx->d_fstats->cursor, 0, sizeof(unsigned long long), ctx->stream);

@@ -379,13 +379,19 @@ __global__ void anchor_slot_count_kernel(StructsView s, KParams p, uint64_t n_en
 __global__ void anchor_slot_scatter_kernel(StructsView s, KParams p, uint64_t n_env,
                                            const uint32_t* __restrict__ anchor_struct,
                                            const uint32_t* __restrict__ anchor_prim, uint32_t* slot_cnt,
-                                           const uint64_t* __restrict__ slot_off, uint32_t* __restrict__ order) {
+                                           const uint64_t* __restrict__ slot_off, uint32_t* __restrict__ order,
+                                           uint2* __restrict__ order_rec) {
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_env) return;
     uint64_t slot = 0;
-    anchor_slot(s, anchor_struct, anchor_prim, e, p.err, &slot);
+    const bool ok = anchor_slot(s, anchor_struct, anchor_prim, e, p.err, &slot);
     const uint32_t k = atomicSub(&slot_cnt[slot], 1u) - 1u;
-    order[slot_off[slot] + k] = (uint32_t)e;
+    const uint64_t pos = slot_off[slot] + k;
+    order[pos] = (uint32_t)e;
+    if (order_rec) {   // (structure, cell-sorted position) next to the order: the gather needs one load per anchor
+        const uint32_t sid = anchor_struct ? anchor_struct[e] : 0u;
+        order_rec[pos] = ok ? make_uint2(sid, (uint32_t)(slot - s.prim_off[sid])) : make_uint2(0xFFFFFFFFu, 0u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -761,14 +767,14 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
         t = __shfl_sync(kFull, t, 0);
         if (t >= t_end) break;
         const uint64_t e = order[t];
-        const uint64_t sid = anchor_struct ? anchor_struct[e] : 0;
-        const uint32_t prim = anchor_prim[e];
-        if (sid >= s.n_structs || prim >= s.prim_off[sid + 1] - s.prim_off[sid]) {   // locohd.rs:521 panics
+        const uint2 rec = b.order_rec[t];   // (structure, cell-sorted position), written with the anchor order
+        const uint64_t sid = rec.x;
+        if (rec.x == 0xFFFFFFFFu) {   // anchor index out of range (locohd.rs:521 panics)
             if (lane == 0) { raise(p.err, LOCOHD_ERR_INDEX); b.count[e] = 0; b.off_out[e] = 0; }
             continue;
         }
         const uint64_t base = s.prim_off[sid];
-        const uint32_t jpos = s.sorted_pos[base + prim];
+        const uint32_t jpos = rec.y;
         const StructMeta m = s.meta[sid];
         const uint32_t* cell_start = s.cell_start + cell_base(base, sid);
         const PrimRec* pd = s.pd + base;
@@ -1884,13 +1890,13 @@ int launch_scan(const uint32_t* values, uint64_t n, int round_even, uint64_t* of
 
 int launch_anchor_order(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* anchor_struct,
                         const uint32_t* anchor_prim, uint64_t n_prims, uint32_t* slot_cnt, uint64_t* slot_off,
-                        uint64_t* scan_scratch, ScanStats* stats, uint32_t* order, cudaStream_t st) {
+                        uint64_t* scan_scratch, ScanStats* stats, uint32_t* order, uint2* order_rec, cudaStream_t st) {
     if (!n_env) return 0;
     cudaMemsetAsync(slot_cnt, 0, (n_prims + 1) * sizeof(uint32_t), st);
     anchor_slot_count_kernel<<<blocks_for(n_env, 256), 256, 0, st>>>(s, p, n_env, anchor_struct, anchor_prim, slot_cnt);
     int n = 1 + launch_scan(slot_cnt, n_prims + 1, 0, slot_off, scan_scratch, stats, st);
     anchor_slot_scatter_kernel<<<blocks_for(n_env, 256), 256, 0, st>>>(s, p, n_env, anchor_struct, anchor_prim,
-                                                                      slot_cnt, slot_off, order);
+                                                                      slot_cnt, slot_off, order, order_rec);
     return n + 1;
 }
 

@@ -108,6 +108,7 @@ struct FusedStats {  // written by env_fused_kernel, read back by the host
 struct EnvBuild {
     uint64_t n_env;
     const uint32_t* order;    // environments in cell order of their anchors
+    const uint2* order_rec;   // (structure, cell-sorted position) of the anchor at every place of `order`
     const uint32_t* ub;       // FP32-prefilter upper bound of every environment size
     const uint64_t* off;      // exclusive scan of the (even-rounded) upper bounds
     uint64_t* off_out;        // fused gather: store offset of every environment (written by the kernel)
@@ -144,7 +145,7 @@ int launch_build_cells(const StructsView& s, double threshold, uint64_t max_prim
 // anchors -> cell order: slot_cnt / slot_off are scratch of n_prims (+1) entries
 int launch_anchor_order(const StructsView& s, const KParams& p, uint64_t n_env, const uint32_t* anchor_struct,
                         const uint32_t* anchor_prim, uint64_t n_prims, uint32_t* slot_cnt, uint64_t* slot_off,
-                        uint64_t* scan_scratch, ScanStats* stats, uint32_t* order, cudaStream_t st);
+                        uint64_t* scan_scratch, ScanStats* stats, uint32_t* order, uint2* order_rec, cudaStream_t st);
 uint64_t scan_scratch_entries(uint64_t n);
 // exclusive scan of u32 values (optionally rounded up to even) into u64 offsets [n + 1]; stats->total / max_value
 int launch_scan(const uint32_t* values, uint64_t n, int round_even, uint64_t* off, uint64_t* scratch, ScanStats* stats,
