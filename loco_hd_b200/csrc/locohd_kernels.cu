@@ -1601,22 +1601,33 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
         uint32_t i1 = __shfl_down_sync(kFull, i, 1), j1 = __shfl_down_sync(kFull, j, 1);
         if (lane == 31) { i1 = na; j1 = nb; }
 
-        // ---- packed per-lane histogram of my chunk, exclusive prefix over the lanes, anchors added
+        // ---- per-lane histogram of my chunk, exclusive prefix over the lanes, anchors added.  The chunk counts live
+        //      in registers - 8-bit fields, 8 categories per 64-bit word and side; a lane owns at most 64 events - so
+        //      the only shared-memory traffic of this step is the final store of the prefixes.
+        constexpr int HW = CP / 8;   // 64-bit words per side
+        unsigned long long hA[HW], hB[HW];
 #pragma unroll
-        for (int r = 0; r < CP; ++r) cnt[r * 32 + lane] = 0;
+        for (int w = 0; w < HW; ++w) { hA[w] = 0; hB[w] = 0; }
         bool unknown = (catA0 >= (uint32_t)C) || (catB0 >= (uint32_t)C);
         for (uint32_t x = i; x < i1; ++x) {
             const uint32_t c = reinterpret_cast<const uint8_t*>(kA + x)[0];
-            if (c < (uint32_t)C) cnt[c * 32 + lane] += 1u; else unknown = true;
+            unknown |= c >= (uint32_t)C;
+            const unsigned long long one = 1ull << (8u * (c & 7u));
+#pragma unroll
+            for (int w = 0; w < HW; ++w) hA[w] += (HW == 1 || (int)((c >> 3) & (HW - 1)) == w) ? one : 0ull;
         }
         for (uint32_t x = j; x < j1; ++x) {
             const uint32_t c = reinterpret_cast<const uint8_t*>(kB + x)[0];
-            if (c < (uint32_t)C) cnt[c * 32 + lane] += 0x10000u; else unknown = true;
+            unknown |= c >= (uint32_t)C;
+            const unsigned long long one = 1ull << (8u * (c & 7u));
+#pragma unroll
+            for (int w = 0; w < HW; ++w) hB[w] += (HW == 1 || (int)((c >> 3) & (HW - 1)) == w) ? one : 0ull;
         }
         if (__any_sync(kFull, unknown)) { raise(P.err, LOCOHD_ERR_UNKNOWN_CATEGORY); continue; }  // pmf.rs:38-42
 #pragma unroll
         for (int r = 0; r < CP; ++r) {
-            const uint32_t v = cnt[r * 32 + lane];
+            const uint32_t v = (uint32_t)((hA[r >> 3] >> (8 * (r & 7))) & 0xFFu) |
+                               ((uint32_t)((hB[r >> 3] >> (8 * (r & 7))) & 0xFFu) << 16);
             uint32_t incl = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
