@@ -16,8 +16,9 @@ try:
                         get_device, set_device)
 except ImportError as exc:  # fail loudly: nothing else can score
     raise ImportError(
-        "loco_hd_b200._host (the CUDA-backed host module) is not built: run `python -m loco_hd_b200.build` "
-        "(needs nvcc for sm_100a and g++). loco_hd_b200 has no CPU fallback.") from exc
+        "loco_hd_b200._host (the CUDA-backed host module) is not built: run `python loco_hd_b200/build.py` or "
+        "`python -c 'import __graft_entry__ as g; g.build()'` from the repository root (needs nvcc for sm_100a and "
+        "g++). loco_hd_b200 has no CPU fallback.") from exc
 
 from .atom_converter_utils import PrimitiveAssigner, PrimitiveAtomSource, PrimitiveAtomTemplate, TypingSchemeElement
 

@@ -79,7 +79,7 @@ def load_library() -> C.CDLL:
         return _lib
     if not LIB_PATH.exists():
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m loco_hd_b200.build` (nvcc, sm_100a). "
+            f"{LIB_PATH} is missing: build it with `python loco_hd_b200/build.py` (nvcc, sm_100a). "
             "loco_hd_b200 has no CPU fallback.")
     lib = C.CDLL(str(LIB_PATH))
     vp, u64, i32, u32, dbl = C.c_void_p, C.c_uint64, C.c_int32, C.c_uint32, C.c_double

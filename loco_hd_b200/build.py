@@ -1,7 +1,7 @@
 """In-tree build recipe: nvcc for the CUDA library (sm_100a only), g++ for the CPython host module.
 
-    python -m loco_hd_b200.build            # build what is stale
-    python -m loco_hd_b200.build --force
+    python loco_hd_b200/build.py            # build what is stale (run as a script: importing the package needs
+    python loco_hd_b200/build.py --force    # the built extension, so `-m loco_hd_b200.build` only works afterwards)
 
 Outputs (git-ignored, shipped to the GPU box with the tree):
     loco_hd_b200/liblocohd_b200.so                      C ABI + kernels   (include/locohd_b200.h)
