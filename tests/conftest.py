@@ -11,6 +11,17 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a clean checkout has no built extension (the .so files are git-ignored): build it once (nvcc cross-compiles
+    # sm_100a without a GPU; about a minute), through build.py loaded by path - the package cannot be imported yet
+    import importlib.util
+    import sysconfig
+
+    pkg = ROOT / "loco_hd_b200"
+    if not (pkg / "liblocohd_b200.so").exists() or not (pkg / ("_host" + sysconfig.get_config_var("EXT_SUFFIX"))).exists():
+        spec = importlib.util.spec_from_file_location("_locohd_build", pkg / "build.py")
+        b = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(b)
+        b.build_all()
 
 
 @pytest.fixture(scope="session")
