@@ -34,6 +34,32 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
+
+
+def _ensure_built():
+    """A clean checkout has no built extension (the .so files are git-ignored): build it through build.py loaded by
+    path (the package cannot be imported before).  Rank 0 of a multi-process launch builds, the others wait."""
+    import importlib.util
+    import sysconfig
+
+    pkg = ROOT / "loco_hd_b200"
+    need = [pkg / "liblocohd_b200.so", pkg / ("_host" + sysconfig.get_config_var("EXT_SUFFIX"))]
+    if all(p.exists() for p in need):
+        return
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        spec = importlib.util.spec_from_file_location("_locohd_build", pkg / "build.py")
+        b = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(b)
+        b.build_all()
+    else:
+        for _ in range(600):
+            if all(p.exists() for p in need):
+                break
+            time.sleep(1.0)
+        time.sleep(2.0)
+
+
+_ensure_built()
 from loco_hd_b200 import synth  # noqa: E402
 
 F_WF = {"uniform": 11, "kumaraswamy": 19, "dagum": 9}  # SURVEY.md §8(d): flops of one integral_range
