@@ -717,7 +717,7 @@ __device__ __forceinline__ double fused_distance(double d2) {
     return fma(sq, r, sq);
 }
 
-template <int WFK, bool DEBUG, int CAP>
+template <int WFK, bool DEBUG, int CAP, bool LIST>
 __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DEBUG ? 1 : 32 / fused_warps(CAP, DEBUG)) : 16 / fused_warps(CAP, DEBUG)) env_fused_kernel(StructsView s, KParams p, uint64_t n_env,
                                                                      const uint32_t* __restrict__ order,
                                                                      const uint32_t* __restrict__ anchor_struct,
@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
     const double r2 = __dmul_rn(threshold, threshold);
     const bool r2_finite = isfinite(r2);
     const double qscale = r2_finite ? K::kScale / r2 : 0.0;
-    const bool simple_rule = p.tpr_kind == LOCOHD_TPR_WITHOUT_LIST;
+    constexpr bool simple_rule = !LIST;   // WithoutList rule: a tag comparison; WithList: table look-ups (own instantiation)
     const bool accept_same = p.tpr_accept_same != 0;
     const WfDev& wf = p.wfs[0];
     FusedWf fwf;
@@ -1941,14 +1941,14 @@ static int fused_wfk(const KParams& p, const WfDev* host_wf, int key_is_w) {
     return 2;
 }
 
-template <int WFK, bool DEBUG, int CAP>
+template <int WFK, bool DEBUG, int CAP, bool LIST>
 static unsigned fused_grid_t(uint64_t n_env) {
     const int smem = FusedLayout<DEBUG, CAP>::kBytes * fused_warps(CAP, DEBUG);
-    cudaFuncSetAttribute(env_fused_kernel<WFK, DEBUG, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(env_fused_kernel<WFK, DEBUG, CAP, LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_fused_kernel<WFK, DEBUG, CAP>, fused_warps(CAP, DEBUG) * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, env_fused_kernel<WFK, DEBUG, CAP, LIST>, fused_warps(CAP, DEBUG) * 32, smem);
     if (occ < 1) occ = 1;
     if (const char* v = std::getenv("LOCOHD_FUSED_CTAS")) { const int c = std::atoi(v); if (c >= 1 && c < occ) occ = c; }
     const uint64_t need = (n_env + fused_warps(CAP, DEBUG) - 1) / fused_warps(CAP, DEBUG);
@@ -1956,29 +1956,37 @@ static unsigned fused_grid_t(uint64_t n_env) {
     return (unsigned)(need < cap ? need : cap);
 }
 
-template <int WFK, bool DEBUG, int CAP>
+template <int WFK, bool DEBUG, int CAP, bool LIST>
 static void fused_launch_t(const StructsView& s, const KParams& p, const uint32_t* anchor_struct,
                            const uint32_t* anchor_prim, double threshold, const EnvBuild& b, FusedStats* stats,
                            uint64_t capacity, unsigned grid, cudaStream_t st) {
     const int smem = FusedLayout<DEBUG, CAP>::kBytes * fused_warps(CAP, DEBUG);
-    env_fused_kernel<WFK, DEBUG, CAP><<<grid, fused_warps(CAP, DEBUG) * 32, smem, st>>>(s, p, b.n_env, b.order, anchor_struct,
+    env_fused_kernel<WFK, DEBUG, CAP, LIST><<<grid, fused_warps(CAP, DEBUG) * 32, smem, st>>>(s, p, b.n_env, b.order, anchor_struct,
                                                                             anchor_prim, threshold, b, stats, capacity);
 }
 
-// dispatch over (CDF specialisation, parity arrays, members per environment)
+// dispatch over (CDF specialisation, parity arrays, members per environment, kind of tag rule)
+#define LOCOHD_FUSED_DISPATCH2(CALL, W, D, C)                                             \
+    if (p.tpr_kind == LOCOHD_TPR_WITHOUT_LIST) { CALL(W, D, C, false); } else { CALL(W, D, C, true); }
 #define LOCOHD_FUSED_DISPATCH(CALL)                                                                        \
     switch ((fused_wfk(p, host_wf, key_is_w) * 2 + (debug ? 1 : 0)) * 2 + (cap > 512 ? 1 : 0)) {          \
-        case 0: CALL(0, false, 512); break;   case 1: CALL(0, false, 1024); break;                        \
-        case 2: CALL(0, true, 512); break;    case 3: CALL(0, true, 1024); break;                         \
-        case 4: CALL(1, false, 512); break;   case 5: CALL(1, false, 1024); break;                        \
-        case 6: CALL(1, true, 512); break;    case 7: CALL(1, true, 1024); break;                         \
-        case 8: CALL(2, false, 512); break;   case 9: CALL(2, false, 1024); break;                        \
-        case 10: CALL(2, true, 512); break;   default: CALL(2, true, 1024); break;                        \
+        case 0: LOCOHD_FUSED_DISPATCH2(CALL, 0, false, 512) break;                                        \
+        case 1: LOCOHD_FUSED_DISPATCH2(CALL, 0, false, 1024) break;                                       \
+        case 2: LOCOHD_FUSED_DISPATCH2(CALL, 0, true, 512) break;                                         \
+        case 3: LOCOHD_FUSED_DISPATCH2(CALL, 0, true, 1024) break;                                        \
+        case 4: LOCOHD_FUSED_DISPATCH2(CALL, 1, false, 512) break;                                        \
+        case 5: LOCOHD_FUSED_DISPATCH2(CALL, 1, false, 1024) break;                                       \
+        case 6: LOCOHD_FUSED_DISPATCH2(CALL, 1, true, 512) break;                                         \
+        case 7: LOCOHD_FUSED_DISPATCH2(CALL, 1, true, 1024) break;                                        \
+        case 8: LOCOHD_FUSED_DISPATCH2(CALL, 2, false, 512) break;                                        \
+        case 9: LOCOHD_FUSED_DISPATCH2(CALL, 2, false, 1024) break;                                       \
+        case 10: LOCOHD_FUSED_DISPATCH2(CALL, 2, true, 512) break;                                        \
+        default: LOCOHD_FUSED_DISPATCH2(CALL, 2, true, 1024) break;                                       \
     }
 
 unsigned fused_grid(const KParams& p, const WfDev* host_wf, int key_is_w, bool debug, int cap, uint64_t n_env) {
     unsigned g = 1;
-#define LOCOHD_CALL(W, D, C) g = fused_grid_t<W, D, C>(n_env)
+#define LOCOHD_CALL(W, D, C, L) g = fused_grid_t<W, D, C, L>(n_env)
     LOCOHD_FUSED_DISPATCH(LOCOHD_CALL)
 #undef LOCOHD_CALL
     return g;
@@ -1990,7 +1998,7 @@ int launch_env_fused(const StructsView& s, const KParams& p, const WfDev* host_w
     if (!b.n_env) return 0;
     const int key_is_w = b.key_is_w;
     const bool debug = b.idx != nullptr;
-#define LOCOHD_CALL(W, D, C) fused_launch_t<W, D, C>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st)
+#define LOCOHD_CALL(W, D, C, L) fused_launch_t<W, D, C, L>(s, p, anchor_struct, anchor_prim, threshold, b, stats, capacity, grid, st)
     LOCOHD_FUSED_DISPATCH(LOCOHD_CALL)
 #undef LOCOHD_CALL
     return 1;
