@@ -679,6 +679,22 @@ __device__ __noinline__ void fused_repair(uint32_t* key32, const double* d2s, co
     }
 }
 
+// Infinite radius: the fixed-point scale of the sort keys comes from the largest finite squared distance.
+template <int CAP>
+__device__ __noinline__ void fused_rekey(uint32_t* key32, const double* d2s, uint32_t M, int lane) {
+    using K = FusedKey<CAP>;
+    double dmax = 0.0;
+    for (uint32_t g = lane; g < M; g += 32) { const double v = d2s[g]; if (isfinite(v)) dmax = fmax(dmax, v); }
+    for (int o = 16; o; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
+    const double sc = dmax > 0.0 ? K::kScale / dmax : 0.0;
+    for (uint32_t g = lane; g < M; g += 32) {
+        const double v = d2s[g];
+        const uint32_t qv = isfinite(v) ? (uint32_t)(v * sc) : K::kInfKey;
+        key32[g] = (qv << K::SB) | g;
+    }
+    __syncwarp();
+}
+
 // WFK: 0 uniform, 1 kumaraswamy with small integer exponents, 2 anything else (wf_cdf, or plain distances).
 // The parameters of variants 0 and 1 are read once per kernel into registers (FusedWf): left in global memory the
 // compiler reloads them in every round of the store loop (they may alias the stores) and the loop waits on them.
@@ -910,18 +926,7 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
             if (lane == 0) { b.count[e] = 0; b.off_out[e] = 0; }
             continue;
         }
-        if (!r2_finite) {   // infinite radius: fixed-point scale from the data
-            double dmax = 0.0;
-            for (uint32_t g = lane; g < M; g += 32) { const double v = d2s[g]; if (isfinite(v)) dmax = fmax(dmax, v); }
-            for (int o = 16; o; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
-            const double sc = dmax > 0.0 ? K::kScale / dmax : 0.0;
-            for (uint32_t g = lane; g < M; g += 32) {
-                const double v = d2s[g];
-                const uint32_t qv = isfinite(v) ? (uint32_t)(v * sc) : K::kInfKey;
-                key32[g] = (qv << K::SB) | g;
-            }
-            __syncwarp();
-        }
+        if (!r2_finite) fused_rekey<CAP>(key32, d2s, M, lane);   // infinite radius (cold): scale from the data
 
         // ---- sort
         bool ties;
