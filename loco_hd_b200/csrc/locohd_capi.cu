@@ -462,7 +462,8 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
     }
     tr.mark("cells + order launched");
     // ---- fused path: sample the sizes (every anchor for small calls), reserve the store, one kernel does the rest
-    if (!ctx->legacy_gather) {
+    // the fused kernel works with r^2 in the f32 exponent range (fixed-point sort keys, f32-seeded square roots)
+    if (!ctx->legacy_gather && threshold * threshold < 1.0e30) {
         // Store sizing.  Small calls (one structure pair is the typical call of the reference API) take the bound
         // kFusedCap per environment and skip the sizing pass and its synchronisation; large batches sample the FP32
         // upper-bound sizes of every 16th anchor.

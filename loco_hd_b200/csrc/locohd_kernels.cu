@@ -679,22 +679,6 @@ __device__ __noinline__ void fused_repair(uint32_t* key32, const double* d2s, co
     }
 }
 
-// Infinite radius: the fixed-point scale of the sort keys comes from the largest finite squared distance.
-template <int CAP>
-__device__ __noinline__ void fused_rekey(uint32_t* key32, const double* d2s, uint32_t M, int lane) {
-    using K = FusedKey<CAP>;
-    double dmax = 0.0;
-    for (uint32_t g = lane; g < M; g += 32) { const double v = d2s[g]; if (isfinite(v)) dmax = fmax(dmax, v); }
-    for (int o = 16; o; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
-    const double sc = dmax > 0.0 ? K::kScale / dmax : 0.0;
-    for (uint32_t g = lane; g < M; g += 32) {
-        const double v = d2s[g];
-        const uint32_t qv = isfinite(v) ? (uint32_t)(v * sc) : K::kInfKey;
-        key32[g] = (qv << K::SB) | g;
-    }
-    __syncwarp();
-}
-
 // WFK: 0 uniform, 1 kumaraswamy with small integer exponents, 2 anything else (wf_cdf, or plain distances).
 // The parameters of variants 0 and 1 are read once per kernel into registers (FusedWf): left in global memory the
 // compiler reloads them in every round of the store loop (they may alias the stores) and the loop waits on them.
@@ -723,9 +707,9 @@ __device__ __forceinline__ double fused_weight(const WfDev& wf, const FusedWf& f
 template <bool EXACT>
 __device__ __forceinline__ double fused_distance(double d2) {
     if (EXACT) return sqrt(d2);
-    const float f = (float)d2;
-    if (!(f > 1e-30f && f < 1e30f)) return d2 == 0.0 ? 0.0 : sqrt(d2);   // 0: the anchor, once per environment
-    const double g = (double)rsqrt_approx(f);
+    // d2 < r^2 < 1e30 here (host check).  Below 1e-30 (distances under 1e-15) the seed is clamped: the result is then
+    // only a monotone value of the same vanishing size, which is all W(d) needs there; 0 stays exactly 0.
+    const double g = (double)rsqrt_approx(fmaxf((float)d2, 1e-30f));
     double sq = d2 * g, hh = 0.5 * g;
     double r = fma(-sq, hh, 0.5);
     sq = fma(sq, r, sq); hh = fma(hh, r, hh);
@@ -755,8 +739,7 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
     const unsigned le_mask = lt_mask | (1u << lane);
 
     const double r2 = __dmul_rn(threshold, threshold);
-    const bool r2_finite = isfinite(r2);
-    const double qscale = r2_finite ? K::kScale / r2 : 0.0;
+    const double qscale = K::kScale / r2;   // the host sends radii with r^2 >= 1e30 (or infinite) to the multi-kernel path
     constexpr bool simple_rule = !LIST;   // WithoutList rule: a tag comparison; WithList: table look-ups (own instantiation)
     const bool accept_same = p.tpr_accept_same != 0;
     const WfDev& wf = p.wfs[0];
@@ -926,8 +909,6 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
             if (lane == 0) { b.count[e] = 0; b.off_out[e] = 0; }
             continue;
         }
-        if (!r2_finite) fused_rekey<CAP>(key32, d2s, M, lane);   // infinite radius (cold): scale from the data
-
         // ---- sort
         bool ties;
         if (M <= 128) ties = fused_sort<4, K::SB>(key32, M, lane);
