@@ -634,12 +634,19 @@ __device__ __forceinline__ void warp_bitonic(uint32_t (&k)[PER], int lane) {
 // fixed-point distance (key >> SB): only then does the caller compare exact distances.
 template <int PER, int SB>
 __device__ __noinline__ bool fused_sort(uint32_t* key32, uint32_t M, int lane) {
+    // A lane owns PER consecutive keys: 16-byte accesses (4 wavefronts per warp instruction; word accesses at a
+    // stride of PER words would be 8-way bank conflicts).  Entries from M on are padding on the way in and are
+    // written back as such (nothing reads key32 beyond M afterwards; 32 * PER <= CAP).
     uint32_t k[PER];
+    uint4* key4 = reinterpret_cast<uint4*>(key32) + lane * (PER / 4);
 #pragma unroll
-    for (int r = 0; r < PER; ++r) {
-        const uint32_t g = (uint32_t)(lane * PER + r);
-        k[r] = (g < M) ? key32[g] : 0xFFFFFFFFu;
+    for (int q = 0; q < PER / 4; ++q) {
+        const uint4 v = key4[q];
+        k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w;
     }
+#pragma unroll
+    for (int r = 0; r < PER; ++r)
+        if ((uint32_t)(lane * PER + r) >= M) k[r] = 0xFFFFFFFFu;
     __syncwarp();
     warp_bitonic<PER>(k, lane);
     bool tie = false;
@@ -647,10 +654,11 @@ __device__ __noinline__ bool fused_sort(uint32_t* key32, uint32_t M, int lane) {
 #pragma unroll
     for (int r = 0; r < PER; ++r) {
         const uint32_t g = (uint32_t)(lane * PER + r);
-        if (g < M) key32[g] = k[r];
         const uint32_t nb = (r + 1 < PER) ? k[(r + 1) % PER] : next0;
         tie |= (g + 1 < M) && ((k[r] >> SB) == (nb >> SB)) && (r + 1 < PER || lane < 31);
     }
+#pragma unroll
+    for (int q = 0; q < PER / 4; ++q) key4[q] = make_uint4(k[4 * q], k[4 * q + 1], k[4 * q + 2], k[4 * q + 3]);
     __syncwarp();
     return __any_sync(kFull, tie);
 }
