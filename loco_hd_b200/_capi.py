@@ -307,13 +307,18 @@ class Context:
         self._check(self.lib.locohd_score_pairs(self.h, a.h, b.h, n, _p(pairs), _p(wf_idx), _p(res)))
         return res
 
-    def score_jobs(self, a: "EnvSet", b: "EnvSet", jobs, wf_idx=None, out=None, want_scores=True, want_means=False):
+    def score_jobs(self, a: "EnvSet", b: "EnvSet", jobs, wf_idx=None, out=None, want_scores=True, want_means=False,
+                   means_out=None):
+        """`out` / `means_out`: numpy array (host) or raw device pointer; with `want_scores=False` and a `means_out`
+        only the per-job means leave the device (the 1000-structure ensemble would otherwise copy
+        20 GB of per-anchor scores back)."""
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE) if not isinstance(jobs, np.ndarray) or jobs.dtype != JOB_DTYPE \
             else np.ascontiguousarray(jobs)
         wf_idx = _arr(wf_idx, np.uint32)
         total = int(jobs["n"].sum())
         res = out if out is not None else (np.empty(total, np.float64) if want_scores else None)
-        means = np.empty(len(jobs), np.float64) if want_means else None
+        want_means = want_means or means_out is not None
+        means = means_out if means_out is not None else (np.empty(len(jobs), np.float64) if want_means else None)
         self._check(self.lib.locohd_score_jobs(self.h, a.h, b.h, len(jobs), _p(jobs), _p(wf_idx), _p(res), _p(means)))
         if want_means:
             return res, means

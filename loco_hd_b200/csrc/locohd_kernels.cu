@@ -1289,8 +1289,14 @@ __device__ __forceinline__ PairEnvs resolve_pair(const ScoreArgs& a, uint64_t pa
     } else {
         uint64_t job, within;
         if (a.uniform_n) {
-            job = pair / a.uniform_n;
-            within = pair - job * a.uniform_n;
+            if (((pair | a.uniform_n) >> 32) == 0) {   // 32-bit division: ~40 instructions fewer than the 64-bit one
+                const uint32_t q = (uint32_t)pair / (uint32_t)a.uniform_n;
+                job = q;
+                within = (uint32_t)pair - q * (uint32_t)a.uniform_n;
+            } else {
+                job = pair / a.uniform_n;
+                within = pair - job * a.uniform_n;
+            }
         } else {
             uint64_t lo = 0, hi = a.n_jobs;  // last job with job_pair_off[job] <= pair
             while (hi - lo > 1) {
