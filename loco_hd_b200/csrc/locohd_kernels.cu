@@ -1525,6 +1525,28 @@ __device__ __forceinline__ double sqrt_unit(double v) {
     return fma(s0, r, s0);
 }
 
+// Shared-memory accesses by 32-bit shared-space address (walk loop of the fast kernel: no generic -> shared
+// conversions, immediate offsets).  Tables and staged keys are read-only during the walk: plain asm, free to schedule;
+// the count words are read-modify-written: volatile with a memory clobber.
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
+    uint64_t v;
+    asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32_rmw(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32_rmw(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 template <int CP, bool KEY_IS_W, bool CHECK>
 __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(ScoreArgs a, KParams P, int warps_per_block,
                                                                          int per_warp_bytes) {
@@ -1533,12 +1555,13 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
     const int table_n = a.table_n;
     double* s_sqrt = reinterpret_cast<double*>(smem_raw);   // sqrt(k)
     double* s_dsq = s_sqrt + table_n;                       // sqrt(k + 1) - sqrt(k)   (exact: Sterbenz)
-    double* s_rsqrt = s_dsq + table_n;                      // 1 / sqrt(k)
+    double* s_rsqrt = s_dsq + table_n;                      // CHECK: 1 / sqrt(k); else sqrt(k / (k + 1)), the factor
+                                                            // that takes 1 / sqrt(k) to 1 / sqrt(k + 1)
     for (int k = threadIdx.x; k < table_n; k += blockDim.x) {
         const double s0 = P.sqrt_tbl[k], s1 = P.sqrt_tbl[k + 1];
         s_sqrt[k] = s0;
         s_dsq[k] = s1 - s0;
-        s_rsqrt[k] = P.rsqrt_tbl[k];
+        s_rsqrt[k] = CHECK ? P.rsqrt_tbl[k] : sqrt((double)k / (double)(k + 1));
     }
     __syncthreads();
     if (wib >= warps_per_block) return;
@@ -1550,6 +1573,12 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
     if (lane == 0) { mbar_init(mbar, 1); fence_proxy_async(); }
     __syncwarp();
     unsigned mbar_parity = 0;
+    // Shared-space addresses used by the walk.  They pass through an identity shuffle once so that ptxas keeps them
+    // in registers: left alone it rematerialises them (S2R, LDC, IMAD ... ~12 instructions) in every walk iteration.
+    const uint32_t sq_base = __shfl_sync(kFull, smem_u32(s_sqrt), lane);
+    const uint32_t dsq_base = __shfl_sync(kFull, smem_u32(s_dsq), lane);
+    const uint32_t ratio_base = __shfl_sync(kFull, smem_u32(s_rsqrt), lane);
+    const uint32_t cnt_lane = __shfl_sync(kFull, smem_u32(cnt + lane), lane);
     auto sqrt_of = [&](uint32_t k) -> double {
         if (CHECK && k >= (uint32_t)table_n) return sqrt((double)k);
         return s_sqrt[k];
@@ -1560,6 +1589,7 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
     };
     auto rsqrt_of = [&](uint32_t k) -> double {
         if (CHECK && k >= (uint32_t)table_n) return 1.0 / sqrt((double)k);
+        if (!CHECK) return __ldg(P.rsqrt_tbl + k);   // chunk start and the small-H^2 path only
         return s_rsqrt[k];
     };
 
@@ -1687,6 +1717,48 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
         // The first nev events of the merge that starts at (i, j) are exactly my chunk (same comparison as the
         // merge-path split: A before B on ties); the sentinels end the lists.
         const uint32_t nev = (i1 - i) + (j1 - j);
+        if constexpr (!CHECK) {
+            // Tables cover every count.  Per-lane state: shared-space addresses of the next key of either list
+            // (pa, pb); the index into the ratio table advances in step with them, so it is a constant offset
+            // (dA, dB) from the key address; R = rA * rB is carried as a product and updated by one table factor
+            // (<= 64 events per chunk: <= 64 roundings, ~1e-14 relative - H >= 1e-4 here, bar 1e-9).
+            uint32_t pa = smem_u32(kA + i), pb = smem_u32(kB + j);
+            const uint32_t dA = ratio_base + 8u * totA - pa, dB = ratio_base + 8u * totB - pb;
+            double R = __dmul_rn(rA, rB);
+            uint64_t ra = lds_u64(pa), rb = lds_u64(pb);
+            for (uint32_t it = 0; it < nev; ++it) {
+                const bool takeA = ra <= (rb | kCatMask);   // == (ra & kWMask) <= (rb & kWMask)
+                const uint64_t raw = takeA ? ra : rb;
+                const double w = weight(raw);
+                acc = fma(w - wprev, h, acc);
+                wprev = w;
+                const uint32_t ca = cnt_lane + (((uint32_t)raw & 0xFFu) << 7);
+                const uint32_t word = lds_u32_rmw(ca);
+                const uint32_t ka = word & 0xffffu, kb = word >> 16;
+                const uint32_t mine_k = takeA ? ka : kb, other_k = takeA ? kb : ka;
+                sts_u32_rmw(ca, word + (takeA ? 1u : 0x10000u));
+                mism += (mine_k == other_k ? 1 : 0) - (mine_k + 1u == other_k ? 1 : 0);
+                D = fma(lds_f64(dsq_base + 8u * mine_k), lds_f64(sq_base + 8u * other_k), D);
+                const uint32_t pk = takeA ? pa : pb;
+                R *= lds_f64(pk + (takeA ? dA : dB));
+                const uint64_t nxt = lds_u64(pk + 8u);
+                pa = takeA ? pk + 8u : pa;
+                pb = takeA ? pb : pk + 8u;
+                ra = takeA ? nxt : ra;
+                rb = takeA ? rb : nxt;
+                const double h2 = fma(-R, D, 1.0);
+                h = (mism == 0) ? 0.0 : sqrt_unit(h2);      // identical counts: exactly 0
+                if (mism != 0 && h2 < kSmallH2) {            // rare: difference form from the counts
+                    rA = rsqrt_of((pa + dA - ratio_base) >> 3);
+                    rB = rsqrt_of((pb + dB - ratio_base) >> 3);
+                    h = sqrt(exact_h2());
+                }
+            }
+            if (lane == 31) acc = fma(wf.w_inf - wprev, h, acc);
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+            if (lane == 0) a.out[pair] = acc;
+            continue;
+        }
         uint64_t ra = kA[i], rb = kB[j];
         for (uint32_t it = 0; it < nev; ++it) {
             const bool takeA = (ra & kWMask) <= (rb & kWMask);
