@@ -1732,7 +1732,8 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
                 const double w = weight(raw);
                 acc = fma(w - wprev, h, acc);
                 wprev = w;
-                const uint32_t ca = cnt_lane + (((uint32_t)raw & 0xFFu) << 7);
+                uint32_t ca;   // cnt_lane + category * 128 (one IMAD; the compiler's shift + mask + add are three)
+                asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(ca) : "r"((uint32_t)raw & 0xFFu), "r"(cnt_lane));
                 const uint32_t word = lds_u32_rmw(ca);
                 const uint32_t ka = word & 0xffffu, kb = word >> 16;
                 const uint32_t mine_k = takeA ? ka : kb, other_k = takeA ? kb : ka;
@@ -1747,7 +1748,9 @@ __global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(Sco
                 ra = takeA ? nxt : ra;
                 rb = takeA ? rb : nxt;
                 const double h2 = fma(-R, D, 1.0);
-                h = (mism == 0) ? 0.0 : sqrt_unit(h2);      // identical counts: exactly 0
+                // (measured and dropped, profiles/r4d: sum |a_r - b_r| instead of the mismatch count and an integer test
+                //  of h2's high word - fewer instructions, 1-2 % slower: the kernel is bound by the shared-memory pipe)
+                h = (mism == 0) ? 0.0 : sqrt_unit(h2);       // identical counts: exactly 0
                 if (mism != 0 && h2 < kSmallH2) {            // rare: difference form from the counts
                     rA = rsqrt_of((pa + dA - ratio_base) >> 3);
                     rB = rsqrt_of((pb + dB - ratio_base) >> 3);
