@@ -359,6 +359,11 @@ def test_batch_jobs_match_single_calls(gpu_ctx, oracle_mod):
         cpu = oracle_mod.from_primitives(op, ref.xyz, ref.cat, ref.tag, model.xyz, model.cat, model.tag, anchors, 10.0)
         assert np.abs(cpu - scores[m]).max() <= SCORE_TOL
         assert means[m] == pytest.approx(scores[m].mean(), abs=1e-14)
+    # means only (what bench.py copies out for the full-size ensemble): same values, caller's buffer
+    only = np.full(len(models), np.nan)
+    none, same = gpu_ctx.score_jobs(env, env, jobs, want_scores=False, means_out=only)
+    assert none is None and same is only
+    assert np.array_equal(only, means)
 
 
 def test_symmetry_and_permutation_invariance(gpu_ctx, oracle_mod):
