@@ -1265,7 +1265,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 
 constexpr uint64_t kSentinel = ~0ull;   // staged behind either list of the fast kernel: above every key
 constexpr int kScoreMaxWarps = 8;
-constexpr int kScoreFastMaxWarps = 28;   // fast kernel: one large CTA per SM shares a single copy of the tables
+// fast kernel: one large CTA per SM shares a single copy of the tables.  The W-keyed instantiations need 50 registers
+// (32 warps fit the register file); the distance-keyed ones (several weight functions) and the ones with table
+// bound checks need up to 72: 28 warps.
+constexpr int kScoreFastMaxWarps = 32;
+__host__ __device__ constexpr int score_fast_max_warps(bool key_is_w, bool check) { return (key_is_w && !check) ? 32 : 28; }
 constexpr uint64_t kWMask = ~kCatMask;
 
 // per-lane values and counts of the generic kernel + the warp's mbarrier (16 bytes at the end)
@@ -1548,7 +1552,7 @@ __device__ __forceinline__ void sts_u32_rmw(uint32_t addr, uint32_t v) {
 }
 
 template <int CP, bool KEY_IS_W, bool CHECK>
-__global__ void __launch_bounds__(kScoreFastMaxWarps * 32) score_fast_kernel(ScoreArgs a, KParams P, int warps_per_block,
+__global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK) * 32) score_fast_kernel(ScoreArgs a, KParams P, int warps_per_block,
                                                                          int per_warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -2208,7 +2212,7 @@ int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsign
     const int per_warp = fast_state_bytes(CP) + ((int)stage + 4) * 8;   // + the two sentinels and their padding
     const int budget = 220 * 1024;  // one CTA per SM: the tables are staged once, the rest goes to the warps' stages
     int warps = (budget - tables) / per_warp;
-    if (warps > kScoreFastMaxWarps) warps = kScoreFastMaxWarps;
+    if (warps > score_fast_max_warps(key_is_w, check)) warps = score_fast_max_warps(key_is_w, check);
     if (warps < 1) warps = 1;
     const int smem = tables + per_warp * warps;
     if (CP == 8) n += key_is_w ? launch_fast<8, true>(a, p, check, warps, per_warp, smem, st)
