@@ -63,3 +63,41 @@ def test_sharded_ensemble_matches_unsharded_and_oracle(gpu_ctx, oracle_mod):
         a, b = clouds[i], clouds[j]
         ref = oracle_mod.from_primitives(op, a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, an, 10.0)
         assert abs(ref.mean() - whole[k]) <= 1e-9
+
+
+def _load_bench():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("locohd_bench", ROOT / "bench.py")
+    mod = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.argv = argv
+    return mod
+
+
+def test_bench_ensemble_jobs_are_dealt_without_overlap():
+    """bench.py's config-5 workload: the i < j structure pairs are dealt round-robin over the ranks (strong scaling,
+    no collective), every pair exactly once, and the per-job event count used for the roofline equals the naive sum."""
+    import types
+
+    bench = _load_bench()
+    args = types.SimpleNamespace(ensemble=7, pairs=2, models=3, frames=3)
+    world = 3
+    seen = []
+    for rank in range(world):
+        wl = bench.make_workload("cfg5", rank, world, args)
+        assert wl.scaling == "strong" and wl.n_pairs == len(wl.jobs) * 5000
+        seen += [tuple(g) for g in wl.job_groups]
+        # sum of (Ma + Mb - 1) per job from environment offsets, as bench.py computes it, against the plain loop
+        rng = np.random.default_rng(rank)
+        sizes = rng.integers(1, 400, size=len(wl.anchor_prim)).astype(np.uint64)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        ja, jb, jn = (wl.jobs[k].astype(np.int64) for k in ("a_first", "b_first", "n"))
+        members = (off[ja + jn] - off[ja]).astype(np.int64) + (off[jb + jn] - off[jb]).astype(np.int64)
+        naive = sum(int(sizes[j["a_first"]:j["a_first"] + j["n"]].sum() + sizes[j["b_first"]:j["b_first"] + j["n"]].sum())
+                    for j in wl.jobs)
+        assert int(members.sum()) == naive
+    assert sorted(seen) == [(i, j) for i in range(7) for j in range(i + 1, 7)]
