@@ -285,7 +285,23 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
+def quiet_stdout():
+    """stdout carries exactly one JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    version banner there when the first communicator is created), so fd 1 is pointed at stderr for the run and the line
+    is written to the saved descriptor at the end."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def emit(saved_fd, text):
+    sys.stdout.flush()
+    os.write(saved_fd, (text + "\n").encode())
+
+
 def run_gpu(args, rank, local_rank, world):
+    stdout_fd = quiet_stdout()
     import torch
     import torch.distributed as dist
 
@@ -557,7 +573,7 @@ def run_gpu(args, rank, local_rank, world):
         "env_size_mean": float(sizes.mean()), "env_size_max": int(sizes.max()),
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(stdout_fd, json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
