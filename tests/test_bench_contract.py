@@ -1,0 +1,41 @@
+"""bench.py's output contract as far as it can be checked without a GPU: the reference arm (`--impl reference`, the
+oracle port on the host cores) prints exactly one JSON line on stdout with the keys the driver reads, and under a
+multi-rank launch only rank 0 prints."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+REQUIRED = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"}
+
+
+def _run(extra_env=None):
+    env = dict(os.environ)
+    env.update(extra_env or {})
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--pairs", "2",
+           "--ref-pairs", "4000"]
+    return subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+
+
+def test_reference_arm_prints_one_json_line():
+    res = _run()
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert REQUIRED <= set(line)
+    assert line["impl"] == "reference" and line["metric"] == "anchor_pairs_per_second" and line["unit"] == "anchor-pairs/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    res = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.strip() == ""
