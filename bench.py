@@ -43,7 +43,7 @@ def _ensure_built():
     import sysconfig
 
     pkg = ROOT / "loco_hd_b200"
-    need = [pkg / "liblocohd_b200.so", pkg / ("_host" + sysconfig.get_config_var("EXT_SUFFIX"))]
+    need = [pkg / "liblocohd_b200.so", ROOT / "loco_hd" / ("loco_hd" + sysconfig.get_config_var("EXT_SUFFIX"))]
     if all(p.exists() for p in need):
         return
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
@@ -60,7 +60,7 @@ def _ensure_built():
 
 
 _ensure_built()
-from loco_hd_b200 import synth  # noqa: E402
+from benchdata import synth  # noqa: E402
 
 F_WF = {"uniform": 11, "kumaraswamy": 19, "dagum": 9}  # flops of one integral_range
 

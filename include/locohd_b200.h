@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LOCOHD_ABI_VERSION 1
+#define LOCOHD_ABI_VERSION 2
 #define LOCOHD_UNKNOWN_CATEGORY 0xFFFFu
 #define LOCOHD_MAX_CATEGORIES 255
 
@@ -151,9 +151,24 @@ void locohd_host_free(void* p);
  * xyz is [n_prims][3] f64, category [n_prims] u16, tag [n_prims] u32.  Coordinates must be finite. */
 int locohd_structs_create(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* prim_offsets, const double* xyz,
                           const uint16_t* category, const uint32_t* tag, locohd_structs** out);
+/* Same with f32 coordinates on the wire (half the upload): Bio.PDB and MDAnalysis positions are float32 and the
+ * centroids of atom_converter_utils.py:117,126 stay float32, so for such callers the f32 -> f64 widening done on the
+ * device is exact and the results are identical to passing the widened values to locohd_structs_create. */
+int locohd_structs_create_f32(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* prim_offsets, const float* xyz,
+                              const uint16_t* category, const uint32_t* tag, locohd_structs** out);
 void locohd_structs_destroy(locohd_structs* s);
 /* Replace the coordinates of an existing set in place (trajectory frames: same topology). */
 int locohd_structs_update_xyz(locohd_structs* s, const double* xyz);
+int locohd_structs_update_xyz_f32(locohd_structs* s, const float* xyz);
+/* Primitive assignment for a compiled topology on the device (PrimitiveAssigner.assign_primitive_structure,
+ * loco_hd/atom_converter_utils.py:92-131, re-run per frame by trajectory_analyzer.py:34-74,112): structures
+ * [first_struct, first_struct + n_frames) get new coordinates, primitive p of frame f = the f32 mean (sequential sum
+ * in the given order, then one f32 division - what np.mean(atom_coords, axis=0) computes) of the atoms
+ * atom_index[segment_start[p] .. segment_start[p + 1]) of atom_xyz[f] ([n_frames][n_atoms][3] f32).  Every updated
+ * structure must have n_prims primitives; categories and tags stay as created. */
+int locohd_structs_update_from_atoms(locohd_structs* s, uint64_t first_struct, uint64_t n_frames, uint64_t n_atoms,
+                                     const float* atom_xyz, uint64_t n_prims, const uint32_t* segment_start,
+                                     const uint32_t* atom_index, uint64_t n_atom_refs);
 /* Forget the cached cell lists so that the next locohd_envset_build rebuilds them (the reference rebuilds its
  * kd-trees on every from_primitives call, locohd.rs:504-510; benchmarks use this to time that step too). */
 void locohd_structs_drop_cells(locohd_structs* s);
@@ -192,6 +207,16 @@ int locohd_score_pairs(locohd_ctx* ctx, const locohd_envset* a, const locohd_env
  * job (sum of jobs[j].n entries).  If out_job_means != NULL the per-job mean score is written there too. */
 int locohd_score_jobs(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_jobs,
                       const locohd_job* jobs, const uint32_t* wf_idx, double* out_scores, double* out_job_means);
+/* locohd_score_jobs plus the reductions the reference's callers compute from the scores next (all optional, NULL =
+ * not wanted; the per-anchor ones need jobs of one common size n and give n values):
+ *   out_job_means     mean over the anchors of every job        np.mean(lchd_scores), casp14_extend_with_locohd.py:88,
+ *                                                               lchd_dmx entries, compare_ensembles.py:293
+ *   out_anchor_means  mean of anchor p over the jobs            np.mean(lchd_by_atom, axis=0), compare_ensembles.py:299
+ *   out_anchor_stds   population std of anchor p over the jobs  np.std(all_points[1:], axis=0), trajectory_analyzer.py:310
+ * With out_scores == NULL the per-anchor scores never leave the device. */
+int locohd_score_jobs_stats(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_jobs,
+                            const locohd_job* jobs, const uint32_t* wf_idx, double* out_scores, double* out_job_means,
+                            double* out_anchor_means, double* out_anchor_stds);
 /* from_anchors (locohd.rs:392-406): one pair of caller-ordered environments, walked in the reference's
  * exact three-way-merge order (the lists are NOT required to be sorted, as in the reference). */
 int locohd_score_anchor_lists(locohd_ctx* ctx, const uint16_t* seq_a, uint64_t len_a, const double* dists_a,

@@ -2,21 +2,21 @@
 
 Layout:
     csrc/                 CUDA kernels + C ABI (include/locohd_b200.h) + the CPython host module source
-    _host                 C++ CPython module with the reference's five classes (built in-tree by build.py)
+    (loco_hd/loco_hd.*.so C++ CPython extension with the reference's five classes, built in-tree by build.py at the
+                          reference's module path; re-exported here)
     _capi                 ctypes binding of the C ABI (parity tests, bench)
     atom_converter_utils  PrimitiveAssigner and its dataclasses (Python side of the reference API)
     batch                 structure-pair / frame / ensemble batches sharded over the GPUs of one box
-    synth                 synthetic clouds of the benchmark configurations
 
 There is no CPU fallback: the scoring classes need the built extension, and every scoring call needs a CUDA
 device (a missing extension raises ImportError here, a missing device raises at the first scoring call).
 """
 try:
-    from ._host import (LoCoHD, PrimitiveAtom, StatisticalDistance, TagPairingRule, WeightFunction, device_count,
-                        get_device, set_device)
+    from loco_hd.loco_hd import (LoCoHD, PrimitiveAtom, StatisticalDistance, TagPairingRule, WeightFunction,
+                                 device_count, get_device, set_device)
 except ImportError as exc:  # fail loudly: nothing else can score
     raise ImportError(
-        "loco_hd_b200._host (the CUDA-backed host module) is not built: run `python loco_hd_b200/build.py` or "
+        "loco_hd.loco_hd (the CUDA-backed extension module) is not built: run `python loco_hd_b200/build.py` or "
         "`python -c 'import __graft_entry__ as g; g.build()'` from the repository root (needs nvcc for sm_100a and "
         "g++). loco_hd_b200 has no CPU fallback.") from exc
 

@@ -25,10 +25,12 @@ EXPORTED_SYMBOLS = [
     "locohd_abi_version", "locohd_device_count", "locohd_ctx_create", "locohd_ctx_destroy", "locohd_last_error",
     "locohd_ctx_set_params", "locohd_ctx_stream", "locohd_ctx_synchronize", "locohd_ctx_launch_count",
     "locohd_ctx_profile_enable", "locohd_ctx_profile_read", "locohd_measure_fp64_tflops",
-    "locohd_host_alloc", "locohd_host_free", "locohd_structs_create", "locohd_structs_destroy",
-    "locohd_structs_update_xyz", "locohd_structs_drop_cells", "locohd_envset_build", "locohd_envset_from_rows",
+    "locohd_host_alloc", "locohd_host_free", "locohd_structs_create", "locohd_structs_create_f32",
+    "locohd_structs_destroy", "locohd_structs_update_xyz", "locohd_structs_update_xyz_f32",
+    "locohd_structs_update_from_atoms", "locohd_structs_drop_cells", "locohd_envset_build", "locohd_envset_from_rows",
     "locohd_envset_from_coords", "locohd_envset_destroy", "locohd_envset_size", "locohd_envset_total_members",
-    "locohd_envset_dump", "locohd_score_pairs", "locohd_score_jobs", "locohd_score_anchor_lists",
+    "locohd_envset_dump", "locohd_score_pairs", "locohd_score_jobs", "locohd_score_jobs_stats",
+    "locohd_score_anchor_lists",
     "locohd_from_primitives", "locohd_wf_integral_points", "locohd_sd_run",
 ]
 
@@ -99,8 +101,11 @@ def load_library() -> C.CDLL:
         "locohd_host_alloc": (C.c_int, [u64, C.POINTER(vp)]),
         "locohd_host_free": (None, [vp]),
         "locohd_structs_create": (C.c_int, [vp, u64, vp, vp, vp, vp, C.POINTER(vp)]),
+        "locohd_structs_create_f32": (C.c_int, [vp, u64, vp, vp, vp, vp, C.POINTER(vp)]),
         "locohd_structs_destroy": (None, [vp]),
         "locohd_structs_update_xyz": (C.c_int, [vp, vp]),
+        "locohd_structs_update_xyz_f32": (C.c_int, [vp, vp]),
+        "locohd_structs_update_from_atoms": (C.c_int, [vp, u64, u64, u64, vp, u64, vp, vp, u64]),
         "locohd_structs_drop_cells": (None, [vp]),
         "locohd_envset_build": (C.c_int, [vp, vp, u64, vp, vp, dbl, C.c_int, C.POINTER(vp)]),
         "locohd_envset_from_rows": (C.c_int, [vp, u64, u64, vp, vp, C.POINTER(vp)]),
@@ -111,6 +116,7 @@ def load_library() -> C.CDLL:
         "locohd_envset_dump": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "locohd_score_pairs": (C.c_int, [vp, vp, vp, u64, vp, vp, vp]),
         "locohd_score_jobs": (C.c_int, [vp, vp, vp, u64, vp, vp, vp, vp]),
+        "locohd_score_jobs_stats": (C.c_int, [vp, vp, vp, u64, vp, vp, vp, vp, vp, vp]),
         "locohd_score_anchor_lists": (C.c_int, [vp, vp, u64, vp, u64, vp, u64, vp, u64, u32, vp]),
         "locohd_from_primitives": (C.c_int, [vp, u64, vp, vp, vp, u64, vp, vp, vp, u64, vp, vp, dbl, vp]),
         "locohd_wf_integral_points": (C.c_int, [vp, C.POINTER(WeightFunctionC), u64, vp, vp]),
@@ -262,12 +268,17 @@ class Context:
         self.n_categories = n_categories
 
     # ---- structures -------------------------------------------------------------------------------
-    def structs_create(self, prim_offsets, xyz, category, tag) -> "Structs":
+    def structs_create(self, prim_offsets, xyz, category, tag, f32: Optional[bool] = None) -> "Structs":
+        """xyz: float64 array (or raw pointer) -> locohd_structs_create; float32 array (or raw pointer with
+        f32=True) -> locohd_structs_create_f32 (half the upload, widened exactly on the device)."""
         offs = np.ascontiguousarray(prim_offsets, dtype=np.uint64)
-        xyz, category, tag = _arr(xyz, np.float64), _arr(category, np.uint16), _arr(tag, np.uint32)
+        if f32 is None:
+            f32 = isinstance(xyz, np.ndarray) and xyz.dtype == np.float32
+        xyz = _arr(xyz, np.float32 if f32 else np.float64)
+        category, tag = _arr(category, np.uint16), _arr(tag, np.uint32)
         h = C.c_void_p()
-        self._check(self.lib.locohd_structs_create(self.h, len(offs) - 1, _p(offs), _p(xyz), _p(category), _p(tag),
-                                                   C.byref(h)))
+        fn = self.lib.locohd_structs_create_f32 if f32 else self.lib.locohd_structs_create
+        self._check(fn(self.h, len(offs) - 1, _p(offs), _p(xyz), _p(category), _p(tag), C.byref(h)))
         return Structs(self, h, len(offs) - 1, int(offs[-1]))
 
     def structure(self, xyz, category, tag) -> "Structs":
@@ -306,6 +317,27 @@ class Context:
         res = np.empty(n, np.float64) if out is None else out
         self._check(self.lib.locohd_score_pairs(self.h, a.h, b.h, n, _p(pairs), _p(wf_idx), _p(res)))
         return res
+
+    def score_jobs_stats(self, a: "EnvSet", b: "EnvSet", jobs, wf_idx=None, scores=False, job_means=False,
+                         anchor_means=False, anchor_stds=False):
+        """locohd_score_jobs_stats: returns a dict with the requested arrays (each flag may also be an output array
+        or a raw device pointer).  The per-anchor statistics need jobs of one common size."""
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        wf_idx = _arr(wf_idx, np.uint32)
+        total = int(jobs["n"].sum())
+        n = int(jobs["n"][0]) if len(jobs) else 0
+
+        def buf(flag, size):
+            if flag is False or flag is None:
+                return None
+            return np.empty(size, np.float64) if flag is True else flag
+
+        res = {"scores": buf(scores, total), "job_means": buf(job_means, len(jobs)),
+               "anchor_means": buf(anchor_means, n), "anchor_stds": buf(anchor_stds, n)}
+        self._check(self.lib.locohd_score_jobs_stats(self.h, a.h, b.h, len(jobs), _p(jobs), _p(wf_idx),
+                                                     _p(res["scores"]), _p(res["job_means"]), _p(res["anchor_means"]),
+                                                     _p(res["anchor_stds"])))
+        return {k: v for k, v in res.items() if v is not None}
 
     def score_jobs(self, a: "EnvSet", b: "EnvSet", jobs, wf_idx=None, out=None, want_scores=True, want_means=False,
                    means_out=None):
@@ -371,9 +403,24 @@ class Structs:
     def __init__(self, ctx: Context, h, n_structs: int, n_prims: int):
         self.ctx, self.h, self.n_structs, self.n_prims = ctx, h, n_structs, n_prims
 
-    def update_xyz(self, xyz):
-        xyz = _arr(xyz, np.float64)
-        self.ctx._check(self.ctx.lib.locohd_structs_update_xyz(self.h, _p(xyz)))
+    def update_xyz(self, xyz, f32: Optional[bool] = None):
+        if f32 is None:
+            f32 = isinstance(xyz, np.ndarray) and xyz.dtype == np.float32
+        if f32:
+            self.ctx._check(self.ctx.lib.locohd_structs_update_xyz_f32(self.h, _p(_arr(xyz, np.float32))))
+        else:
+            self.ctx._check(self.ctx.lib.locohd_structs_update_xyz(self.h, _p(_arr(xyz, np.float64))))
+
+    def update_from_atoms(self, atom_xyz, segment_start, atom_index, first_struct: int = 0, n_frames: int = 1,
+                          n_atoms: Optional[int] = None):
+        """Frames of one compiled topology (PrimitiveAssigner.compile_topology): atom_xyz [n_frames][n_atoms][3]
+        float32 -> primitive centroids of structures [first_struct, first_struct + n_frames) on the device."""
+        seg, idx = _arr(segment_start, np.uint32), _arr(atom_index, np.uint32)
+        atoms = _arr(atom_xyz, np.float32)
+        if n_atoms is None:
+            n_atoms = atoms.size // (3 * n_frames)
+        self.ctx._check(self.ctx.lib.locohd_structs_update_from_atoms(
+            self.h, int(first_struct), int(n_frames), int(n_atoms), _p(atoms), len(seg) - 1, _p(seg), _p(idx), len(idx)))
 
     def drop_cells(self):
         self.ctx.lib.locohd_structs_drop_cells(self.h)

@@ -3,8 +3,8 @@
 The scoring path has no exchange step (anchor pairs are independent): every rank owns one GPU,
 scores its share of the jobs, and the per-rank score slabs are put together on the host.  This module holds the
 host-side logic — dealing jobs to ranks, running a rank's share through the C ABI, assembling the results — and
-nothing else; `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is only used to assemble results when the
-caller asks for them on every rank.
+nothing else.  It imports no communication library: a caller that wants the assembled results on every rank passes
+its own `allgather` callable (the tests wrap torch.distributed.all_gather_object over gloo).
 """
 from __future__ import annotations
 
@@ -44,25 +44,39 @@ def assemble(per_rank_ids: Sequence[np.ndarray], per_rank_values: Sequence[np.nd
     return out
 
 
-def gather_job_values(my_ids: np.ndarray, my_values: np.ndarray, n_jobs: int) -> np.ndarray:
-    """All ranks get the values of all jobs.  Works with any initialised torch.distributed backend."""
-    import torch.distributed as dist
-
-    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+def gather_job_values(my_ids: np.ndarray, my_values: np.ndarray, n_jobs: int,
+                      allgather: Optional[Callable[[object], Sequence[object]]] = None) -> np.ndarray:
+    """All ranks get the values of all jobs.  `allgather(obj) -> [obj of rank 0, obj of rank 1, ...]` is whatever
+    the launcher offers for exchanging small host objects (e.g. a wrapper of torch.distributed.all_gather_object or
+    mpi4py's allgather); this module itself depends on no communication library.  None = single process."""
+    if allgather is None:
         return assemble([my_ids], [my_values], n_jobs)
-    gathered: List[Optional[Tuple[np.ndarray, np.ndarray]]] = [None] * dist.get_world_size()
-    dist.all_gather_object(gathered, (np.asarray(my_ids), np.asarray(my_values)))
+    gathered = allgather((np.asarray(my_ids), np.asarray(my_values)))
     return assemble([g[0] for g in gathered], [g[1] for g in gathered], n_jobs)
 
 
 def run_sharded(job_sizes: Sequence[int], scorer: Callable[[np.ndarray], np.ndarray], rank: int, world: int,
-                gather: bool = True) -> np.ndarray:
+                gather: bool = True, allgather: Optional[Callable[[object], Sequence[object]]] = None) -> np.ndarray:
     """Score this rank's share with `scorer(job_ids) -> one value per job` and (optionally) gather everything."""
     mine = deal_jobs(job_sizes, world)[rank]
     values = np.asarray(scorer(mine), dtype=np.float64) if len(mine) else np.zeros(0)
-    if not gather:
+    if not gather or world == 1:
         return assemble([mine], [values], len(job_sizes))
-    return gather_job_values(mine, values, len(job_sizes))
+    if allgather is None:
+        raise ValueError("gather=True with world > 1 needs an `allgather` callable")
+    return gather_job_values(mine, values, len(job_sizes), allgather)
+
+
+def combine_anchor_stats(counts: Sequence[int], means: Sequence[np.ndarray], stds: Sequence[np.ndarray]):
+    """Per-rank per-anchor (job count, mean, population std) -> the statistics over all jobs (exact pooling:
+    total variance = mean of the within-rank variances + variance of the rank means, weighted by job counts)."""
+    n = np.asarray(counts, dtype=np.float64)
+    m = np.stack([np.asarray(x, dtype=np.float64) for x in means])
+    s = np.stack([np.asarray(x, dtype=np.float64) for x in stds])
+    total = n.sum()
+    mean = (n[:, None] * m).sum(axis=0) / total
+    var = (n[:, None] * (s * s + (m - mean) ** 2)).sum(axis=0) / total
+    return mean, np.sqrt(var)
 
 
 @dataclass
@@ -110,7 +124,7 @@ class ResidentEnsemble:
 
 
 def ensemble_all_vs_all(ctx, clouds, anchors, threshold: float, rank: int = 0, world: int = 1,
-                        gather: bool = True) -> np.ndarray:
+                        gather: bool = True, allgather=None) -> np.ndarray:
     """All-vs-all mean LoCoHD matrix entries (i < j, order of `all_pairs`) of an ensemble, sharded over `world`
     ranks: every rank keeps the whole ensemble resident (1000 x 5000 primitives = 145 MB) and scores its share of
     the structure pairs."""
@@ -118,6 +132,6 @@ def ensemble_all_vs_all(ctx, clouds, anchors, threshold: float, rank: int = 0, w
     ens = ResidentEnsemble.build(ctx, clouds, anchors, threshold)
     try:
         sizes = np.full(len(pairs), len(anchors))
-        return run_sharded(sizes, lambda ids: ens.pair_means(pairs[ids]), rank, world, gather)
+        return run_sharded(sizes, lambda ids: ens.pair_means(pairs[ids]), rank, world, gather, allgather)
     finally:
         ens.close()

@@ -4,8 +4,9 @@
     python loco_hd_b200/build.py --force    # the built extension, so `-m loco_hd_b200.build` only works afterwards)
 
 Outputs (git-ignored, shipped to the GPU box with the tree):
-    loco_hd_b200/liblocohd_b200.so                      C ABI + kernels   (include/locohd_b200.h)
-    loco_hd_b200/_host.cpython-312-x86_64-linux-gnu.so  CPython host module (replaces src/lib.rs of the reference)
+    loco_hd_b200/liblocohd_b200.so                 C ABI + kernels   (include/locohd_b200.h)
+    loco_hd/loco_hd.cpython-312-x86_64-linux-gnu.so  CPython host module at the reference's module path
+                                                   `loco_hd.loco_hd` (replaces src/lib.rs of the reference)
 """
 from __future__ import annotations
 
@@ -19,7 +20,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 CUDA_LIB = PKG / "liblocohd_b200.so"
-HOST_MOD = PKG / ("_host" + sysconfig.get_config_var("EXT_SUFFIX"))
+HOST_MOD = ROOT / "loco_hd" / ("loco_hd" + sysconfig.get_config_var("EXT_SUFFIX"))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
@@ -57,7 +58,7 @@ def build_host_module(force: bool = False, verbose: bool = False) -> Path:
             "g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
             f"-I{pybind11.get_include()}", f"-I{sysconfig.get_paths()['include']}", f"-I{ROOT / 'include'}",
             str(src), "-o", str(HOST_MOD),
-            f"-L{PKG}", "-llocohd_b200", "-Wl,-rpath,$ORIGIN",
+            f"-L{PKG}", "-llocohd_b200", "-Wl,-rpath,$ORIGIN/../loco_hd_b200",
         ]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)

@@ -1,4 +1,4 @@
-// host_module.cpp — CPython module `loco_hd_b200._host` (re-exported as `loco_hd.loco_hd`): the five classes of
+// host_module.cpp — CPython extension `loco_hd.loco_hd` (the reference's module path and name): the five classes of
 // the reference's PyO3 boundary (/root/reference/src/lib.rs:9-17) written from scratch in C++/pybind11 because no
 // Rust toolchain exists in this image.  It only validates, interns strings and marshals arrays; every `from_*`
 // scoring call goes to CUDA through the C ABI (include/locohd_b200.h).  There is no CPU scoring path.
@@ -273,7 +273,82 @@ struct StatisticalDistance {
 };
 
 // -------------------------------------------------------------------------------------------------- LoCoHD
-struct CtxDeleter { void operator()(locohd_ctx* c) const { locohd_ctx_destroy(c); } };
+// One CUDA context and the mutex that serialises the C-ABI calls on it (a context owns one stream).  Locking
+// discipline: the mutex is only ever taken with the GIL RELEASED and is dropped before the GIL comes back, so a
+// thread never waits for one while holding the other (two Python threads may share a LoCoHD instance, as they can
+// upstream, where the GIL simply serialises them).  Python-side state (tag table, context pointer) is only touched
+// with the GIL held.
+struct Dev {
+    locohd_ctx* c = nullptr;
+    int device = -1;
+    std::mutex mu;
+    ~Dev() { if (c) locohd_ctx_destroy(c); }
+};
+
+// Runs f(ctx) -> status without the GIL and under the device mutex; raises with the context's message.
+template <class F>
+void device_call(const std::shared_ptr<Dev>& d, F&& f) {
+    int st;
+    std::string msg;
+    {
+        py::gil_scoped_release rel;
+        std::lock_guard<std::mutex> g(d->mu);
+        st = f(d->c);
+        if (st) msg = locohd_last_error(d->c);
+    }   // the mutex is released first, then the GIL is taken again
+    if (st) raise_status(st, msg.c_str());
+}
+
+using F64Array = py::array_t<double, py::array::c_style | py::array::forcecast>;
+using U16Array = py::array_t<uint16_t, py::array::c_style | py::array::forcecast>;
+using U32Array = py::array_t<uint32_t, py::array::c_style | py::array::forcecast>;
+using U64Array = py::array_t<uint64_t, py::array::c_style | py::array::forcecast>;
+
+// Device-resident structures / environments handed out by LoCoHD.structures / LoCoHD.environments.
+// They keep the context alive; destruction only enqueues stream-ordered frees and needs no lock.
+struct Structures {
+    std::shared_ptr<Dev> dev;
+    locohd_structs* h = nullptr;
+    uint64_t n_structs = 0, n_prims = 0;
+    std::vector<uint64_t> offsets;
+    ~Structures() { close(); }
+    void close() { if (h) { locohd_structs_destroy(h); h = nullptr; } }
+    void need() const { if (!h) throw py::value_error("structures have been closed"); }
+    void update_xyz(const py::array& xyz) {
+        need();
+        if ((uint64_t)xyz.size() != 3 * n_prims) throw py::value_error("xyz must hold 3 coordinates per primitive of the set");
+        if (py::isinstance<py::array_t<float>>(xyz)) {   // float32 goes over the f32 wire (exact widening on the device)
+            auto a = py::array_t<float, py::array::c_style | py::array::forcecast>::ensure(xyz);
+            device_call(dev, [&](locohd_ctx*) { return locohd_structs_update_xyz_f32(h, a.data()); });
+        } else {
+            auto a = F64Array::ensure(xyz);
+            if (!a) throw py::type_error("xyz must be a float array");
+            device_call(dev, [&](locohd_ctx*) { return locohd_structs_update_xyz(h, a.data()); });
+        }
+    }
+    // Frames of one compiled topology (PrimitiveAssigner.compile_topology): atoms -> centroids on the device.
+    void update_from_atoms(const py::array_t<float, py::array::c_style | py::array::forcecast>& atoms,
+                           const U32Array& segment_start, const U32Array& atom_index, uint64_t first_struct) {
+        need();
+        if (segment_start.size() < 1) throw py::value_error("segment_start must have n_primitives + 1 entries");
+        if (atoms.ndim() < 2 || atoms.shape(atoms.ndim() - 1) != 3) throw py::value_error("atom coordinates must be [n_frames, n_atoms, 3] or [n_atoms, 3]");
+        const uint64_t n_frames = atoms.ndim() == 3 ? (uint64_t)atoms.shape(0) : 1;
+        const uint64_t n_atoms = (uint64_t)atoms.shape(atoms.ndim() - 2);
+        const uint64_t n_prims_t = (uint64_t)segment_start.size() - 1;
+        device_call(dev, [&](locohd_ctx*) {
+            return locohd_structs_update_from_atoms(h, first_struct, n_frames, n_atoms, atoms.data(), n_prims_t,
+                                                    segment_start.data(), atom_index.data(), (uint64_t)atom_index.size());
+        });
+    }
+};
+
+struct Environments {
+    std::shared_ptr<Dev> dev;
+    locohd_envset* h = nullptr;
+    uint64_t n_env = 0;
+    ~Environments() { close(); }
+    void close() { if (h) { locohd_envset_destroy(h); h = nullptr; } }
+};
 
 std::vector<std::string> to_strings(const py::handle& seq, const char* what) {
     if (py::isinstance<py::str>(seq)) throw py::type_error(std::string(what) + ": can't extract `str` to a list");
@@ -292,12 +367,9 @@ struct LoCoHD {
     std::unordered_map<std::string, uint32_t> wf_index;
     TagPairingRule rule;
     StatisticalDistance sd{"Hellinger", {2.0}};
-    // device side, created at the first scoring call
-    std::unique_ptr<locohd_ctx, CtxDeleter> ctx;
-    int ctx_device = -1;
+    // device side, created at the first scoring call (GIL held whenever these are touched)
+    std::shared_ptr<Dev> dev;
     std::unordered_map<std::string, uint32_t> tag_ids;   // grows with every new tag seen
-    size_t tag_pairs_interned = 0;
-    std::mutex mu;
 
     LoCoHD(const py::object& categories, const py::object& w_func, const py::object& tag_pairing_rule,
            const py::object& n_of_threads, const py::object& weights, const py::object& statistical_distance) {
@@ -374,19 +446,17 @@ struct LoCoHD {
         return it == category_index.end() ? (uint16_t)LOCOHD_UNKNOWN_CATEGORY : it->second;
     }
 
-    void check(int st) {
-        if (st) raise_status(st, locohd_last_error(ctx.get()));
-    }
-
-    // Creates the context on first use and (re)sends the parameters.
-    void ensure_ctx() {
-        const int dev = default_device();
-        if (ctx && ctx_device == dev) return;
+    // Creates the context on first use (or when the selected device changed) and sends the parameters.  Called
+    // with the GIL held; a context still in use by another thread's call stays alive through its shared_ptr.
+    std::shared_ptr<Dev> ensure_ctx() {
+        const int want = default_device();
+        if (dev && dev->device == want) return dev;
         locohd_ctx* c = nullptr;
-        const int st = locohd_ctx_create(dev, &c);
+        const int st = locohd_ctx_create(want, &c);
         if (st) raise_status(LOCOHD_ERR_CUDA, locohd_last_error(nullptr));
-        ctx.reset(c);
-        ctx_device = dev;
+        auto fresh = std::make_shared<Dev>();
+        fresh->c = c;
+        fresh->device = want;
         std::vector<uint64_t> pairs;
         if (rule.with_list)
             for (const auto& p : rule.tag_pairs) pairs.push_back(((uint64_t)intern_tag(p.first) << 32) | intern_tag(p.second));
@@ -406,7 +476,9 @@ struct LoCoHD {
         p.tpr_ordered = rule.ordered;
         p.n_tag_pairs = pairs.size();
         p.tag_pairs = pairs.data();
-        check(locohd_ctx_set_params(ctx.get(), &p));
+        if (locohd_ctx_set_params(c, &p)) raise_status(LOCOHD_ERR_BAD_PARAM, locohd_last_error(c));   // not shared yet: no lock
+        dev = fresh;
+        return dev;
     }
 
     // keys_to_weight_functions (locohd.rs:230-283): returns per-anchor indices (empty = weight function 0 for all)
@@ -444,30 +516,30 @@ struct LoCoHD {
         std::optional<std::vector<std::string>> keys;
         if (key) keys = std::vector<std::string>{*key};
         const auto idx = resolve_keys(keys, 1);
-        std::lock_guard<std::mutex> g(mu);
-        ensure_ctx();
+        const auto d = ensure_ctx();
         double out = 0.0;
-        int st;
-        {
-            py::gil_scoped_release rel;
-            st = locohd_score_anchor_lists(ctx.get(), sa.data(), sa.size(), da.data(), da.size(), sb.data(), sb.size(),
-                                           db.data(), db.size(), idx.empty() ? 0u : idx[0], &out);
-        }
-        check(st);
+        device_call(d, [&](locohd_ctx* c) {
+            return locohd_score_anchor_lists(c, sa.data(), sa.size(), da.data(), da.size(), sb.data(), sb.size(),
+                                             db.data(), db.size(), idx.empty() ? 0u : idx[0], &out);
+        });
         return out;
     }
 
-    std::vector<double> score_envsets(locohd_envset* ea, locohd_envset* eb, size_t n, const std::vector<uint32_t>& wf) {
+    // Two row sets (from_dmxs / from_coords) -> environments -> one job; everything inside one locked region.
+    template <class Build>
+    std::vector<double> score_rows(const std::shared_ptr<Dev>& d, size_t n, const std::vector<uint32_t>& wf, Build&& build) {
         std::vector<double> out(n);
-        const locohd_job job{0, 0, n};
-        int st;
-        {
-            py::gil_scoped_release rel;
-            st = locohd_score_jobs(ctx.get(), ea, eb, 1, &job, wf.empty() ? nullptr : wf.data(), out.data(), nullptr);
-        }
-        locohd_envset_destroy(ea);
-        locohd_envset_destroy(eb);
-        check(st);
+        device_call(d, [&](locohd_ctx* c) {
+            locohd_envset *ea = nullptr, *eb = nullptr;
+            int st = build(c, &ea, &eb);
+            if (!st) {
+                const locohd_job job{0, 0, n};
+                st = locohd_score_jobs(c, ea, eb, 1, &job, wf.empty() ? nullptr : wf.data(), out.data(), nullptr);
+            }
+            locohd_envset_destroy(ea);
+            locohd_envset_destroy(eb);
+            return st;
+        });
         return out;
     }
 
@@ -499,17 +571,12 @@ struct LoCoHD {
         if (sa.size() < la || sb.size() < lb)
             throw py::value_error("The category sequences are shorter than the distance matrix rows!");
         if (la == 0 || lb == 0) throw py::value_error("Empty distance matrix rows!");
-        std::lock_guard<std::mutex> g(mu);
-        ensure_ctx();
-        locohd_envset *ea = nullptr, *eb = nullptr;
-        int st;
-        {
-            py::gil_scoped_release rel;
-            st = locohd_envset_from_rows(ctx.get(), rows_a, la, ma.data(), sa.data(), &ea);
-            if (!st) st = locohd_envset_from_rows(ctx.get(), rows_b, lb, mb.data(), sb.data(), &eb);
-        }
-        if (st) { locohd_envset_destroy(ea); check(st); }
-        return score_envsets(ea, eb, rows_a, wf);
+        const auto d = ensure_ctx();
+        return score_rows(d, rows_a, wf, [&](locohd_ctx* c, locohd_envset** ea, locohd_envset** eb) {
+            int st = locohd_envset_from_rows(c, rows_a, la, ma.data(), sa.data(), ea);
+            if (!st) st = locohd_envset_from_rows(c, rows_b, lb, mb.data(), sb.data(), eb);
+            return st;
+        });
     }
 
     // ---- from_coords (locohd.rs:463-476)
@@ -530,17 +597,14 @@ struct LoCoHD {
         const auto wf = resolve_keys(keys, na);
         if (na == 0) return {};
         if (sa.size() < na || sb.size() < nb) throw py::value_error("The category sequences are shorter than the coordinate lists!");
-        std::lock_guard<std::mutex> g(mu);
-        ensure_ctx();
-        locohd_envset *ea = nullptr, *eb = nullptr;
-        int st;
-        {
-            py::gil_scoped_release rel;
-            st = locohd_envset_from_coords(ctx.get(), na, xa.data(), sa.data(), &ea);
-            if (!st) st = locohd_envset_from_coords(ctx.get(), nb, xb.data(), sb.data(), &eb);
-        }
-        if (st) { locohd_envset_destroy(ea); check(st); }
-        return score_envsets(ea, eb, na, wf);
+        const auto d = ensure_ctx();
+        const size_t n_pts = na;
+        const double *pa = xa.data(), *pb = xb.data();
+        return score_rows(d, n_pts, wf, [&](locohd_ctx* c, locohd_envset** ea, locohd_envset** eb) {
+            int st = locohd_envset_from_coords(c, n_pts, pa, sa.data(), ea);
+            if (!st) st = locohd_envset_from_coords(c, n_pts, pb, sb.data(), eb);
+            return st;
+        });
     }
 
     // ---- from_primitives (locohd.rs:479-567)
@@ -556,15 +620,17 @@ struct LoCoHD {
         if (hint > 0) { f.xyz.reserve(3 * hint); f.cat.reserve(hint); f.tag.reserve(hint); }
         // consecutive primitives usually share their tag (one tag per residue) and often their type: compare with
         // the previous strings before hashing
-        const std::string* last_tag = nullptr;
-        const std::string* last_type = nullptr;
+        // (kept BY VALUE: a generator's previous item may already be gone when the next one arrives)
+        std::string last_tag, last_type;
+        bool have_last = false;
         uint32_t last_tag_id = 0;
         uint16_t last_cat = 0;
         for (auto item : prims) {
             const PrimitiveAtom& p = item.cast<const PrimitiveAtom&>();
             f.xyz.push_back(p.coordinates[0]); f.xyz.push_back(p.coordinates[1]); f.xyz.push_back(p.coordinates[2]);
-            if (!last_type || *last_type != p.primitive_type) { last_cat = cat_id(p.primitive_type); last_type = &p.primitive_type; }
-            if (!last_tag || *last_tag != p.tag) { last_tag_id = intern_tag(p.tag); last_tag = &p.tag; }
+            if (!have_last || last_type != p.primitive_type) { last_cat = cat_id(p.primitive_type); last_type = p.primitive_type; }
+            if (!have_last || last_tag != p.tag) { last_tag_id = intern_tag(p.tag); last_tag = p.tag; }
+            have_last = true;
             f.cat.push_back(last_cat);
             f.tag.push_back(last_tag_id);
         }
@@ -611,64 +677,172 @@ struct LoCoHD {
         if (with_keys) keys = std::move(key_list);
         const auto wf = resolve_keys(keys, n_pairs);
         if (n_pairs == 0) return {};
-        std::lock_guard<std::mutex> g(mu);
-        ensure_ctx();  // interns the rule's tags first so that their ids are stable
+        const auto d = ensure_ctx();  // interns the rule's tags first so that their ids are stable
         const Flat a = flatten(prim_a, "prim_a"), b = flatten(prim_b, "prim_b");
         for (size_t k = 0; k < n_pairs; ++k)  // prim_seq[anchor_idx] panics upstream (locohd.rs:521)
             if (anchors[2 * k] >= a.cat.size() || anchors[2 * k + 1] >= b.cat.size())
                 throw py::value_error("Anchor index out of range: pair " + std::to_string(k) + " = (" + std::to_string(anchors[2 * k]) +
                                       ", " + std::to_string(anchors[2 * k + 1]) + ")");
         std::vector<double> out(n_pairs);
-        int st;
-        {
-            py::gil_scoped_release rel;
-            st = locohd_from_primitives(ctx.get(), a.cat.size(), a.xyz.data(), a.cat.data(), a.tag.data(), b.cat.size(),
-                                        b.xyz.data(), b.cat.data(), b.tag.data(), n_pairs, anchors.data(),
-                                        wf.empty() ? nullptr : wf.data(), threshold, out.data());
-        }
-        check(st);
+        device_call(d, [&](locohd_ctx* c) {
+            return locohd_from_primitives(c, a.cat.size(), a.xyz.data(), a.cat.data(), a.tag.data(), b.cat.size(),
+                                          b.xyz.data(), b.cat.data(), b.tag.data(), n_pairs, anchors.data(),
+                                          wf.empty() ? nullptr : wf.data(), threshold, out.data());
+        });
         return out;
     }
 
-    // ---- array API: integer category / tag ids and an [n, 3] coordinate array per structure
-    py::array_t<double> from_arrays(py::array_t<double, py::array::c_style | py::array::forcecast> xyz_a,
-                                    py::array_t<uint16_t, py::array::c_style | py::array::forcecast> cat_a,
-                                    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> tag_a,
-                                    py::array_t<double, py::array::c_style | py::array::forcecast> xyz_b,
-                                    py::array_t<uint16_t, py::array::c_style | py::array::forcecast> cat_b,
-                                    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> tag_b,
-                                    py::array_t<uint32_t, py::array::c_style | py::array::forcecast> anchors,
-                                    double threshold, const py::object& wf_idx) {
-        if (rule.with_list) throw py::value_error("from_arrays needs a TagPairingRule without a tag list (integer tags cannot be matched to the rule's strings)");
+    // ---- array API: integer category / tag ids and an [n, 3] coordinate array per structure.
+    // Tag ids are opaque integers for a rule without a list; with a tag-pair list they must come from intern_tags(),
+    // which maps strings to the ids the rule's pairs were interned with.
+    std::vector<uint32_t> wf_indices(const py::object& wf_idx, size_t n) const {
+        std::vector<uint32_t> wf;
+        if (!wf_idx.is_none()) {
+            wf = wf_idx.cast<std::vector<uint32_t>>();
+            if (wf.size() != n) throw py::value_error("wf_idx must have one entry per anchor pair");
+            for (uint32_t w : wf) if (w >= wfs.size()) throw py::value_error("wf_idx entry out of range");
+        }
+        return wf;
+    }
+
+    py::array_t<uint32_t> intern_tags(const py::object& tags) {
+        ensure_ctx();   // the rule's own tags get their ids first
+        const auto names = to_strings(tags, "tags");
+        py::array_t<uint32_t> out(names.size());
+        auto* o = out.mutable_data();
+        for (size_t i = 0; i < names.size(); ++i) o[i] = intern_tag(names[i]);
+        return out;
+    }
+
+    py::array_t<uint16_t> category_ids(const py::object& types) const {
+        const auto names = to_strings(types, "primitive types");
+        py::array_t<uint16_t> out(names.size());
+        auto* o = out.mutable_data();
+        for (size_t i = 0; i < names.size(); ++i) o[i] = cat_id(names[i]);
+        return out;
+    }
+
+    py::array_t<double> from_arrays(F64Array xyz_a, U16Array cat_a, U32Array tag_a, F64Array xyz_b, U16Array cat_b,
+                                    U32Array tag_b, U32Array anchors, double threshold, const py::object& wf_idx) {
         const size_t na = cat_a.size(), nb = cat_b.size();
         if ((size_t)xyz_a.size() != 3 * na || (size_t)tag_a.size() != na || (size_t)xyz_b.size() != 3 * nb || (size_t)tag_b.size() != nb)
             throw py::value_error("xyz must be [n, 3], category and tag [n]");
         if (anchors.size() % 2) throw py::value_error("anchors must be [n_pairs, 2]");
         const size_t P = anchors.size() / 2;
-        std::vector<uint32_t> wf;
-        if (!wf_idx.is_none()) {
-            wf = wf_idx.cast<std::vector<uint32_t>>();
-            if (wf.size() != P) throw py::value_error("wf_idx must have one entry per anchor pair");
-            for (uint32_t w : wf) if (w >= wfs.size()) throw py::value_error("wf_idx entry out of range");
-        }
+        const auto wf = wf_indices(wf_idx, P);
         py::array_t<double> out(P);
-        std::lock_guard<std::mutex> g(mu);
-        ensure_ctx();
-        int st;
-        {
-            py::gil_scoped_release rel;
-            st = locohd_from_primitives(ctx.get(), na, xyz_a.data(), cat_a.data(), tag_a.data(), nb, xyz_b.data(), cat_b.data(),
-                                        tag_b.data(), P, anchors.data(), wf.empty() ? nullptr : wf.data(), threshold,
-                                        out.mutable_data());
+        const auto d = ensure_ctx();
+        double* o = out.mutable_data();
+        device_call(d, [&](locohd_ctx* c) {
+            return locohd_from_primitives(c, na, xyz_a.data(), cat_a.data(), tag_a.data(), nb, xyz_b.data(), cat_b.data(),
+                                          tag_b.data(), P, anchors.data(), wf.empty() ? nullptr : wf.data(), threshold, o);
+        });
+        return out;
+    }
+
+    // ---- resident batches: what the callers loop over upstream - one reference against
+    // many models (casp14_extend_with_locohd.py:58-79), frame 0 against every frame (trajectory_analyzer.py:112-120),
+    // all pairs of an ensemble (compare_ensembles.py:273-296) - with the structures uploaded once.
+    std::shared_ptr<Structures> structures(const U64Array& offsets, const py::array& xyz, const U16Array& cat,
+                                           const U32Array& tag) {
+        if (offsets.size() < 2) throw py::value_error("prim_offsets must hold n_structures + 1 entries");
+        const uint64_t n_structs = (uint64_t)offsets.size() - 1;
+        const uint64_t n = offsets.data()[n_structs];
+        if ((uint64_t)xyz.size() != 3 * n || (uint64_t)cat.size() != n || (uint64_t)tag.size() != n)
+            throw py::value_error("xyz must be [n, 3], category and tag [n] with n = prim_offsets[-1]");
+        auto s = std::make_shared<Structures>();
+        s->dev = ensure_ctx();
+        s->n_structs = n_structs; s->n_prims = n;
+        s->offsets.assign(offsets.data(), offsets.data() + offsets.size());
+        if (py::isinstance<py::array_t<float>>(xyz)) {
+            auto a = py::array_t<float, py::array::c_style | py::array::forcecast>::ensure(xyz);
+            device_call(s->dev, [&](locohd_ctx* c) {
+                return locohd_structs_create_f32(c, n_structs, offsets.data(), a.data(), cat.data(), tag.data(), &s->h);
+            });
+        } else {
+            auto a = F64Array::ensure(xyz);
+            if (!a) throw py::type_error("xyz must be a float array");
+            device_call(s->dev, [&](locohd_ctx* c) {
+                return locohd_structs_create(c, n_structs, offsets.data(), a.data(), cat.data(), tag.data(), &s->h);
+            });
         }
-        check(st);
+        return s;
+    }
+
+    std::shared_ptr<Environments> environments(const std::shared_ptr<Structures>& st, const U32Array& anchor_prim,
+                                               double threshold, const py::object& anchor_struct) {
+        if (!st) throw py::value_error("structures is None");
+        st->need();
+        const auto d = ensure_ctx();
+        if (d != st->dev) throw py::value_error("the structures were uploaded for another device / context");
+        const uint64_t n = (uint64_t)anchor_prim.size();
+        U32Array as;
+        const uint32_t* as_ptr = nullptr;
+        if (!anchor_struct.is_none()) {
+            as = U32Array::ensure(anchor_struct);
+            if (!as || (uint64_t)as.size() != n) throw py::value_error("anchor_struct must have one entry per anchor");
+            as_ptr = as.data();
+        }
+        auto e = std::make_shared<Environments>();
+        e->dev = d;
+        e->n_env = n;
+        device_call(d, [&](locohd_ctx* c) {
+            return locohd_envset_build(c, st->h, n, as_ptr, anchor_prim.data(), threshold, 0, &e->h);
+        });
+        return e;
+    }
+
+    // jobs: [n_jobs, 3] (first environment in env_a, first environment in env_b, number of anchor pairs).
+    // reduce: None -> per-anchor scores of all jobs, concatenated; or any of "job_mean", "anchor_mean", "anchor_std"
+    // (a string or a sequence of them; "scores" may be listed too) -> dict of arrays, reduced on the device.
+    py::object score_batch(const std::shared_ptr<Environments>& ea, const std::shared_ptr<Environments>& eb,
+                           const U64Array& jobs, const py::object& reduce, const py::object& wf_idx) {
+        if (!ea || !eb || !ea->h || !eb->h) throw py::value_error("environments are None or closed");
+        if (ea->dev != eb->dev) throw py::value_error("the two environment sets live in different contexts");
+        if (jobs.ndim() != 2 || jobs.shape(1) != 3) throw py::value_error("jobs must be [n_jobs, 3]: (a_first, b_first, n)");
+        const uint64_t n_jobs = (uint64_t)jobs.shape(0);
+        std::vector<locohd_job> hj(n_jobs);
+        uint64_t total = 0;
+        for (uint64_t j = 0; j < n_jobs; ++j) {
+            hj[j] = locohd_job{jobs.data()[3 * j], jobs.data()[3 * j + 1], jobs.data()[3 * j + 2]};
+            total += hj[j].n;
+        }
+        const auto wf = wf_indices(wf_idx, total);
+        bool want_scores = reduce.is_none(), want_jm = false, want_am = false, want_as = false;
+        if (!reduce.is_none()) {
+            std::vector<std::string> names;
+            if (py::isinstance<py::str>(reduce)) names.push_back(reduce.cast<std::string>());
+            else names = to_strings(reduce, "reduce");
+            for (const auto& nme : names) {
+                if (nme == "scores") want_scores = true;
+                else if (nme == "job_mean") want_jm = true;
+                else if (nme == "anchor_mean") want_am = true;
+                else if (nme == "anchor_std") want_as = true;
+                else throw py::value_error("reduce: unknown name \"" + nme + "\" (scores, job_mean, anchor_mean, anchor_std)");
+            }
+        }
+        const uint64_t n_anchor = n_jobs ? hj[0].n : 0;
+        py::array_t<double> scores(want_scores ? total : 0), jm(want_jm ? n_jobs : 0), am(want_am ? n_anchor : 0),
+            as(want_as ? n_anchor : 0);
+        double *ps = want_scores ? scores.mutable_data() : nullptr, *pj = want_jm ? jm.mutable_data() : nullptr,
+               *pm = want_am ? am.mutable_data() : nullptr, *pd = want_as ? as.mutable_data() : nullptr;
+        if (total)
+            device_call(ea->dev, [&](locohd_ctx* c) {
+                return locohd_score_jobs_stats(c, ea->h, eb->h, n_jobs, hj.data(), wf.empty() ? nullptr : wf.data(), ps, pj, pm, pd);
+            });
+        if (reduce.is_none()) return scores;
+        py::dict out;
+        if (want_scores) out["scores"] = scores;
+        if (want_jm) out["job_mean"] = jm;
+        if (want_am) out["anchor_mean"] = am;
+        if (want_as) out["anchor_std"] = as;
         return out;
     }
 };
 
 }  // namespace
 
-PYBIND11_MODULE(_host, m) {
+PYBIND11_MODULE(loco_hd, m) {
     m.doc() = "B200-native LoCoHD host module: the reference's PyO3 classes over the CUDA C ABI (no CPU scoring path)";
     m.attr("ABI_VERSION") = locohd_abi_version();
     m.def("device_count", &locohd_device_count, "Number of visible CUDA devices");
@@ -725,6 +899,37 @@ PYBIND11_MODULE(_host, m) {
         .def("from_arrays", &LoCoHD::from_arrays, py::arg("xyz_a"), py::arg("cat_a"), py::arg("tag_a"), py::arg("xyz_b"),
              py::arg("cat_b"), py::arg("tag_b"), py::arg("anchors"), py::arg("threshold_distance"),
              py::arg("wf_idx") = py::none(),
-             "Array form of from_primitives: integer category ids (index into `categories`, 0xFFFF = unknown), "
-             "integer tag ids, [n, 3] float64 coordinates, [n_pairs, 2] anchor indices.  Returns a float64 array.");
+             "Array form of from_primitives: integer category ids (index into `categories`, 0xFFFF = unknown; see "
+             "category_ids), integer tag ids (opaque for a rule without a tag list, from intern_tags otherwise), "
+             "[n, 3] float64 coordinates, [n_pairs, 2] anchor indices.  Returns a float64 array.")
+        .def("intern_tags", &LoCoHD::intern_tags, py::arg("tags"),
+             "Tag strings -> the uint32 ids this instance uses for them (the ids of a WithList rule's tag pairs included).")
+        .def("category_ids", &LoCoHD::category_ids, py::arg("primitive_types"),
+             "Primitive type names -> uint16 category ids (0xFFFF for a name that is not in `categories`).")
+        .def("structures", &LoCoHD::structures, py::arg("prim_offsets"), py::arg("xyz"), py::arg("categories"), py::arg("tags"),
+             "Upload a set of structures once: structure s owns primitives [prim_offsets[s], prim_offsets[s + 1]) of the "
+             "concatenated arrays (float32 coordinates travel as float32 and are widened on the device).")
+        .def("environments", &LoCoHD::environments, py::arg("structures"), py::arg("anchor_prim"), py::arg("threshold_distance"),
+             py::arg("anchor_struct") = py::none(),
+             "Sorted environments of a list of anchors (structure anchor_struct[e], default 0; primitive anchor_prim[e]).")
+        .def("score_batch", &LoCoHD::score_batch, py::arg("env_a"), py::arg("env_b"), py::arg("jobs"),
+             py::arg("reduce") = py::none(), py::arg("wf_idx") = py::none(),
+             "Score runs of identity-paired environments: jobs is [n_jobs, 3] (a_first, b_first, n).  reduce=None returns "
+             "the per-anchor scores; \"job_mean\", \"anchor_mean\", \"anchor_std\" (or a list of them, optionally with "
+             "\"scores\") are reduced on the device and returned in a dict.");
+
+    py::class_<Structures, std::shared_ptr<Structures>>(m, "Structures")
+        .def_readonly("n_structures", &Structures::n_structs)
+        .def_readonly("n_primitives", &Structures::n_prims)
+        .def_property_readonly("prim_offsets", [](const Structures& s) { return s.offsets; })
+        .def("update_xyz", &Structures::update_xyz, py::arg("xyz"), "Replace all coordinates (same topology: trajectory frames).")
+        .def("update_from_atoms", &Structures::update_from_atoms, py::arg("atom_xyz"), py::arg("segment_start"),
+             py::arg("atom_index"), py::arg("first_structure") = 0,
+             "Frames of one compiled topology: float32 atom coordinates [n_frames, n_atoms, 3] -> primitive centroids of "
+             "structures first_structure ... on the device (PrimitiveAssigner.compile_topology gives the index arrays).")
+        .def("close", &Structures::close);
+
+    py::class_<Environments, std::shared_ptr<Environments>>(m, "Environments")
+        .def("__len__", [](const Environments& e) { return e.n_env; })
+        .def("close", &Environments::close);
 }

@@ -173,6 +173,7 @@ const char* status_text(int code) {
         case LOCOHD_ERR_EMPTY_ENV: return "Empty environment (non-positive or NaN threshold distance?)";
         case LOCOHD_ERR_INDEX: return "Anchor or environment index out of range";
         case LOCOHD_ERR_DMX_SHAPE: return "Expected matrices with the same length";
+        case LOCOHD_ERR_BAD_PARAM: return "weight function index out of range";
         case LOCOHD_ERR_CUDA: return "internal device error";
         default: return "error";
     }
@@ -595,8 +596,13 @@ int run_score(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, u
 }
 
 int check_wf_indices(locohd_ctx* ctx, const uint32_t* wf_idx, uint64_t n) {
-    // host-side check only possible for host arrays; device arrays are trusted to be in range
-    if (!wf_idx || is_device_ptr(ctx, wf_idx)) return 0;
+    if (!wf_idx) return 0;
+    if (is_device_ptr(ctx, wf_idx)) {
+        // device-resident indices: checked by a kernel (LOCOHD_ERR_BAD_PARAM in the device error word, reported at
+        // the call's synchronisation); the scoring kernels clamp the index, so nothing is read out of bounds
+        ctx->launches += launch_validate_wf_idx(wf_idx, n, (uint32_t)ctx->kp.n_wf, ctx->d_err, ctx->stream);
+        return 0;
+    }
     for (uint64_t i = 0; i < n; ++i)
         if (wf_idx[i] >= (uint32_t)ctx->kp.n_wf)
             return fail(ctx, LOCOHD_ERR_BAD_PARAM, "weight function index %u out of range (%d functions)", wf_idx[i], ctx->kp.n_wf);
@@ -847,8 +853,21 @@ int locohd_ctx_set_params(locohd_ctx* ctx, const locohd_params* params) {
 }
 
 // ---------------------------------------------------------------------------------------------- structures
-int locohd_structs_create(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* prim_offsets, const double* xyz,
-                          const uint16_t* category, const uint32_t* tag, locohd_structs** out) {
+// Coordinates arrive as f64 (24 B per primitive) or as f32 (12 B, widened on the device: exact).
+static int upload_xyz(locohd_ctx* ctx, double* d_xyz, const void* xyz, bool f32, uint64_t n3) {
+    if (!n3) return 0;
+    if (!f32) {
+        CU(ctx, cudaMemcpyAsync(d_xyz, xyz, n3 * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        return 0;
+    }
+    InBuf<float> in;
+    TRY_ST(in.load(ctx, static_cast<const float*>(xyz), n3));
+    ctx->launches += launch_widen_xyz(in.ptr, d_xyz, n3, ctx->stream);
+    return 0;   // a temporary of `in` is released stream-ordered, after the kernel
+}
+
+static int structs_create_impl(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* prim_offsets, const void* xyz,
+                               bool f32, const uint16_t* category, const uint32_t* tag, locohd_structs** out) {
     API_BEGIN(ctx)
     TRY_ST(need_params(ctx));
     if (!out || !prim_offsets) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
@@ -882,9 +901,9 @@ int locohd_structs_create(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* p
         (st = dev_alloc(ctx, &s->d_cell_fill, cell_entries(n, n_structs))))
         return bail(st);
     cudaError_t ce = cudaMemcpyAsync(s->d_prim_off, offs.data(), offs.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(s->d_xyz, xyz, 3 * n * sizeof(double), cudaMemcpyDefault, ctx->stream);
     if (ce == cudaSuccess && n) ce = cudaMemcpyAsync(s->d_tag, tag, n * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream);
     if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "upload failed: %s", cudaGetErrorString(ce)));
+    if ((st = upload_xyz(ctx, s->d_xyz, xyz, f32, 3 * n))) return bail(st);
     {
         InBuf<uint16_t> cat16;
         if ((st = cat16.load(ctx, category, n))) return bail(st);
@@ -896,6 +915,16 @@ int locohd_structs_create(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* p
     *out = s;
     return 0;
     API_END()
+}
+
+int locohd_structs_create(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* prim_offsets, const double* xyz,
+                          const uint16_t* category, const uint32_t* tag, locohd_structs** out) {
+    return structs_create_impl(ctx, n_structs, prim_offsets, xyz, false, category, tag, out);
+}
+
+int locohd_structs_create_f32(locohd_ctx* ctx, uint64_t n_structs, const uint64_t* prim_offsets, const float* xyz,
+                              const uint16_t* category, const uint32_t* tag, locohd_structs** out) {
+    return structs_create_impl(ctx, n_structs, prim_offsets, xyz, true, category, tag, out);
 }
 
 void locohd_structs_destroy(locohd_structs* s) {
@@ -911,16 +940,50 @@ void locohd_structs_destroy(locohd_structs* s) {
 
 void locohd_structs_drop_cells(locohd_structs* s) { if (s) s->cells_valid = false; }
 
-int locohd_structs_update_xyz(locohd_structs* s, const double* xyz) {
+static int update_xyz_impl(locohd_structs* s, const void* xyz, bool f32) {
     if (!s) return fail(nullptr, LOCOHD_ERR_BAD_PARAM, "null structures");
     API_BEGIN(s->ctx)
     locohd_ctx* ctx = s->ctx;
     if (s->n_prims && !xyz) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null xyz");
     s->cells_valid = false;
     if (s->n_prims) {
-        CU(ctx, cudaMemcpyAsync(s->d_xyz, xyz, 3 * s->n_prims * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        TRY_ST(upload_xyz(ctx, s->d_xyz, xyz, f32, 3 * s->n_prims));
         ctx->launches += launch_validate_xyz(s->d_xyz, 3 * s->n_prims, ctx->d_err, ctx->stream);
     }
+    return sync_and_check(ctx);
+    API_END()
+}
+
+int locohd_structs_update_xyz(locohd_structs* s, const double* xyz) { return update_xyz_impl(s, xyz, false); }
+int locohd_structs_update_xyz_f32(locohd_structs* s, const float* xyz) { return update_xyz_impl(s, xyz, true); }
+
+int locohd_structs_update_from_atoms(locohd_structs* s, uint64_t first_struct, uint64_t n_frames, uint64_t n_atoms,
+                                     const float* atom_xyz, uint64_t n_prims, const uint32_t* segment_start,
+                                     const uint32_t* atom_index, uint64_t n_atom_refs) {
+    if (!s) return fail(nullptr, LOCOHD_ERR_BAD_PARAM, "null structures");
+    API_BEGIN(s->ctx)
+    locohd_ctx* ctx = s->ctx;
+    if (n_frames == 0) return 0;
+    if (first_struct + n_frames > s->n_structs) return fail(ctx, LOCOHD_ERR_INDEX, "frames address structures beyond the set");
+    if (!segment_start || (n_atom_refs && !atom_index) || (n_atoms && !atom_xyz)) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
+    if (n_atom_refs > 0xFFFFFFFFull) return fail(ctx, LOCOHD_ERR_UNSUPPORTED, "more than 2^32 atom references in a topology");
+    // every updated structure must have the topology's primitive count (same topology for all frames)
+    std::vector<uint64_t> offs(n_frames + 1);
+    CU(ctx, cudaMemcpy(offs.data(), s->d_prim_off + first_struct, offs.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    for (uint64_t f = 0; f < n_frames; ++f)
+        if (offs[f + 1] - offs[f] != n_prims)
+            return fail(ctx, LOCOHD_ERR_LEN_MISMATCH, "structure %llu has %llu primitives, the topology yields %llu",
+                        (unsigned long long)(first_struct + f), (unsigned long long)(offs[f + 1] - offs[f]),
+                        (unsigned long long)n_prims);
+    InBuf<float> atoms;
+    InBuf<uint32_t> seg, idx;
+    TRY_ST(atoms.load(ctx, atom_xyz, 3 * n_atoms * n_frames));
+    TRY_ST(seg.load(ctx, segment_start, n_prims + 1));
+    TRY_ST(idx.load(ctx, atom_index, n_atom_refs));
+    s->cells_valid = false;
+    double* dst = s->d_xyz + 3 * offs[0];
+    ctx->launches += launch_centroids(atoms.ptr, n_atoms, n_frames, seg.ptr, idx.ptr, n_prims, dst, ctx->d_err, ctx->stream);
+    ctx->launches += launch_validate_xyz(dst, 3 * n_prims * n_frames, ctx->d_err, ctx->stream);
     return sync_and_check(ctx);
     API_END()
 }
@@ -1099,6 +1162,12 @@ int locohd_score_pairs(locohd_ctx* ctx, const locohd_envset* a, const locohd_env
 
 int locohd_score_jobs(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_jobs,
                       const locohd_job* jobs, const uint32_t* wf_idx, double* out_scores, double* out_job_means) {
+    return locohd_score_jobs_stats(ctx, a, b, n_jobs, jobs, wf_idx, out_scores, out_job_means, nullptr, nullptr);
+}
+
+int locohd_score_jobs_stats(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_jobs,
+                            const locohd_job* jobs, const uint32_t* wf_idx, double* out_scores, double* out_job_means,
+                            double* out_anchor_means, double* out_anchor_stds) {
     API_BEGIN(ctx)
     TRY_ST(need_params(ctx));
     if (!a || !b || (n_jobs && !jobs)) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
@@ -1117,7 +1186,11 @@ int locohd_score_jobs(locohd_ctx* ctx, const locohd_envset* a, const locohd_envs
         if (hj[j].n != hj[0].n) uniform = false;
     }
     const uint64_t n_pairs = joff[n_jobs];
-    if (n_pairs && !out_scores && !out_job_means) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "no output requested");
+    const bool anchor_stats = out_anchor_means || out_anchor_stds;
+    if (n_pairs && !out_scores && !out_job_means && !anchor_stats) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "no output requested");
+    if (anchor_stats && !(uniform && hj[0].n))
+        return fail(ctx, LOCOHD_ERR_BAD_PARAM, "per-anchor statistics need jobs of one common, non-zero size");
+    const uint64_t n_per_job = n_jobs ? hj[0].n : 0;
     TRY_ST(check_wf_indices(ctx, wf_idx, n_pairs));
     InBuf<locohd_job> dj;
     InBuf<uint64_t> djoff;
@@ -1125,22 +1198,32 @@ int locohd_score_jobs(locohd_ctx* ctx, const locohd_envset* a, const locohd_envs
     TRY_ST(dj.load(ctx, hj.data(), n_jobs));
     TRY_ST(djoff.load(ctx, joff.data(), n_jobs + 1));
     TRY_ST(wf.load(ctx, wf_idx, n_pairs));
-    OutBuf<double> out, means;
-    double* d_scores_tmp = nullptr;
-    TRY_ST(out.prepare(ctx, out_scores, n_pairs));
+    OutBuf<double> out, means, amean, astd;
+    double *d_scores_tmp = nullptr, *d_stat = nullptr;
+    auto cleanup = [&](int st) { dev_free(ctx, d_scores_tmp); dev_free(ctx, d_stat); return st; };
+    int st;
+    if ((st = out.prepare(ctx, out_scores, n_pairs))) return cleanup(st);
     double* d_scores = out.ptr;
-    if (!d_scores) { TRY_ST(dev_alloc(ctx, &d_scores_tmp, n_pairs)); d_scores = d_scores_tmp; }
-    TRY_ST(means.prepare(ctx, out_job_means, n_jobs));
-    int st = run_score(ctx, a, b, n_pairs, nullptr, dj.ptr, djoff.ptr, n_jobs, (uniform && hj[0].n) ? hj[0].n : 0,
-                       wf.ptr, d_scores);
-    if (!st && means.ptr) {
-        ctx->launches += launch_job_means(d_scores, djoff.ptr, n_jobs, means.ptr, ctx->stream);
+    if (!d_scores) { if ((st = dev_alloc(ctx, &d_scores_tmp, n_pairs))) return cleanup(st); d_scores = d_scores_tmp; }
+    if ((st = means.prepare(ctx, out_job_means, n_jobs)) || (st = amean.prepare(ctx, out_anchor_means, n_per_job)) ||
+        (st = astd.prepare(ctx, out_anchor_stds, n_per_job)))
+        return cleanup(st);
+    if (anchor_stats && (st = dev_alloc(ctx, &d_stat, 2 * n_per_job))) return cleanup(st);
+    st = run_score(ctx, a, b, n_pairs, nullptr, dj.ptr, djoff.ptr, n_jobs, (uniform && hj[0].n) ? hj[0].n : 0,
+                   wf.ptr, d_scores);
+    if (!st && (means.ptr || anchor_stats)) {
+        ProfScope ps(ctx, LOCOHD_PROF_OTHER);
+        if (means.ptr) ctx->launches += launch_job_means(d_scores, djoff.ptr, n_jobs, means.ptr, ctx->stream);
+        if (anchor_stats)
+            ctx->launches += launch_anchor_stats(d_scores, n_per_job, n_jobs, d_stat, d_stat + n_per_job, amean.ptr,
+                                                 astd.ptr, ctx->stream);
     }
     if (!st) st = out.commit();
     if (!st) st = means.commit();
+    if (!st) st = amean.commit();
+    if (!st) st = astd.commit();
     const int st2 = sync_and_check(ctx);  // also keeps hj/joff alive until the copies are done
-    dev_free(ctx, d_scores_tmp);
-    return st ? st : st2;
+    return cleanup(st ? st : st2);
     API_END()
 }
 
@@ -1158,7 +1241,8 @@ int locohd_score_anchor_lists(locohd_ctx* ctx, const uint16_t* seq_a, uint64_t l
     TRY_ST(sa16.load(ctx, seq_a, len_a)); TRY_ST(sb16.load(ctx, seq_b, len_b));
     TRY_ST(da.load(ctx, dists_a, len_a)); TRY_ST(db.load(ctx, dists_b, len_b));
     uint8_t *sa8 = nullptr, *sb8 = nullptr;
-    TRY_ST(dev_alloc(ctx, &sa8, len_a)); TRY_ST(dev_alloc(ctx, &sb8, len_b));
+    TRY_ST(dev_alloc(ctx, &sa8, len_a));
+    if (int ast = dev_alloc(ctx, &sb8, len_b)) { dev_free(ctx, sa8); return ast; }
     ctx->launches += launch_convert_categories(sa16.ptr, sa8, len_a, ctx->kp.C, ctx->stream);
     ctx->launches += launch_convert_categories(sb16.ptr, sb8, len_b, ctx->kp.C, ctx->stream);
     OutBuf<double> out;
@@ -1229,7 +1313,8 @@ int locohd_from_primitives(locohd_ctx* ctx, uint64_t n_a, const double* xyz_a, c
         const uint32_t* an = anchors;
         if (is_device_ptr(ctx, anchors)) {
             h_anchor.resize(2 * n_pairs);
-            CU(ctx, cudaMemcpy(h_anchor.data(), anchors, 2 * n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            ce = cudaMemcpy(h_anchor.data(), anchors, 2 * n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+            if (ce != cudaSuccess) return cleanup(fail(ctx, LOCOHD_ERR_CUDA, "anchor download failed: %s", cudaGetErrorString(ce)));
             an = h_anchor.data();
         }
         for (uint64_t i = 0; i < n_pairs; ++i) {

@@ -1456,7 +1456,7 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
             }
         };
 
-        const WfDev& wf = P.wfs[a.wf_idx ? a.wf_idx[pair] : 0];
+        const WfDev& wf = P.wfs[a.wf_idx ? min(a.wf_idx[pair], (uint32_t)(P.n_wf - 1)) : 0u];   // range checked by validate_wf_idx_kernel
         auto weight = [&](uint64_t k) -> double { return key_is_w ? key_value(k) : wf_cdf(wf, key_value(k)); };
         uint64_t kprev = key0;
         if (i > 0) kprev = kA[i - 1] & kWMask;
@@ -1709,7 +1709,7 @@ __global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK) * 32) sc
         };
         rebuild();
 
-        const WfDev& wf = P.wfs[(!KEY_IS_W && a.wf_idx) ? a.wf_idx[pair] : 0];
+        const WfDev& wf = P.wfs[(!KEY_IS_W && a.wf_idx) ? min(a.wf_idx[pair], (uint32_t)(P.n_wf - 1)) : 0u];
         auto weight = [&](uint64_t k) -> double { return KEY_IS_W ? key_value(k) : wf_cdf(wf, key_value(k)); };
         uint64_t kprev = key0;
         if (i > 0) kprev = kA[i - 1] & kWMask;
@@ -1811,6 +1811,82 @@ __global__ void job_means_kernel(const double* __restrict__ scores, const uint64
     for (uint64_t i = b + lane; i < e; i += 32) s += scores[i];
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
     if (lane == 0) means[job] = (e > b) ? s / (double)(e - b) : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// f32 wire format, per-frame centroids, weight-function index check, per-anchor statistics over jobs
+// ------------------------------------------------------------------------------------------------
+// Coordinates that arrive as f32 (Bio.PDB / MDAnalysis positions, atom_converter_utils.py:117,126) are widened on
+// the device: f32 -> f64 is exact, the upload is half the bytes.
+__global__ void widen_xyz_kernel(const float* __restrict__ in, double* __restrict__ out, uint64_t n3) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) out[i] = (double)in[i];
+}
+
+// PrimitiveAssigner.assign_primitive_structure for a compiled topology (atom_converter_utils.py:92-131): primitive
+// p of every frame = np.mean of its atoms' f32 coordinates, i.e. a sequential f32 sum in atom order followed by
+// an f32 division by the atom count (numpy reduces axis 0 of a [k, 3] float32 array row by row).  One thread per
+// (frame, primitive); the result is widened to the f64 coordinates of the structure set.
+__global__ void centroid_kernel(const float* __restrict__ atoms, uint64_t n_atoms, uint64_t n_frames,
+                                const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ atom_index,
+                                uint64_t n_prims, double* __restrict__ xyz_out, int* err) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_frames * n_prims) return;
+    const uint64_t f = t / n_prims, p = t - f * n_prims;
+    const uint32_t s0 = seg_start[p], s1 = seg_start[p + 1];
+    const float* fa = atoms + 3 * f * n_atoms;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (uint32_t k = s0; k < s1; ++k) {
+        const uint32_t a = atom_index[k];
+        if (a >= n_atoms) { raise(err, LOCOHD_ERR_INDEX); return; }
+        sx = __fadd_rn(sx, fa[3 * (uint64_t)a]);
+        sy = __fadd_rn(sy, fa[3 * (uint64_t)a + 1]);
+        sz = __fadd_rn(sz, fa[3 * (uint64_t)a + 2]);
+    }
+    const float cnt = (float)(s1 - s0);   // an empty segment gives 0 / 0 = NaN, as np.mean of nothing does
+    xyz_out[3 * t] = (double)__fdiv_rn(sx, cnt);
+    xyz_out[3 * t + 1] = (double)__fdiv_rn(sy, cnt);
+    xyz_out[3 * t + 2] = (double)__fdiv_rn(sz, cnt);
+}
+
+__global__ void validate_wf_idx_kernel(const uint32_t* __restrict__ wf_idx, uint64_t n, uint32_t n_wf, int* err) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && wf_idx[i] >= n_wf) raise(err, LOCOHD_ERR_BAD_PARAM);
+}
+
+// Per-anchor statistics over uniform jobs (scores is [n_jobs][n]): mean and population standard deviation of
+// anchor p over the jobs - np.mean(lchd_by_atom, axis=0) (compare_ensembles.py:299) and
+// np.std(all_points[1:], axis=0) (trajectory_analyzer.py:310).  Two passes like numpy's (mean, then squared
+// deviations); grid.y splits the jobs, partial sums meet in double atomics.
+constexpr int kStatThreads = 256;
+__global__ void __launch_bounds__(kStatThreads) anchor_sum_kernel(const double* __restrict__ scores, uint64_t n,
+                                                                 uint64_t n_jobs, double* __restrict__ sum) {
+    const uint64_t p = (uint64_t)blockIdx.x * kStatThreads + threadIdx.x;
+    if (p >= n) return;
+    double acc = 0.0;
+    for (uint64_t j = blockIdx.y; j < n_jobs; j += gridDim.y) acc += scores[j * n + p];
+    atomicAdd(sum + p, acc);
+}
+__global__ void __launch_bounds__(kStatThreads) anchor_dev_kernel(const double* __restrict__ scores, uint64_t n,
+                                                                 uint64_t n_jobs, const double* __restrict__ sum,
+                                                                 double* __restrict__ m2) {
+    const uint64_t p = (uint64_t)blockIdx.x * kStatThreads + threadIdx.x;
+    if (p >= n) return;
+    const double mean = sum[p] / (double)n_jobs;
+    double acc = 0.0;
+    for (uint64_t j = blockIdx.y; j < n_jobs; j += gridDim.y) {
+        const double d = scores[j * n + p] - mean;
+        acc = fma(d, d, acc);
+    }
+    atomicAdd(m2 + p, acc);
+}
+__global__ void anchor_finish_kernel(uint64_t n, uint64_t n_jobs, const double* __restrict__ sum,
+                                     const double* __restrict__ m2, double* __restrict__ mean_out,
+                                     double* __restrict__ std_out) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    if (mean_out) mean_out[p] = sum[p] / (double)n_jobs;
+    if (std_out) std_out[p] = sqrt(m2[p] / (double)n_jobs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2232,6 +2308,48 @@ int launch_job_means(const double* scores, const uint64_t* job_pair_off, uint64_
     if (!n_jobs) return 0;
     job_means_kernel<<<blocks_for(n_jobs * 32, 256), 256, 0, st>>>(scores, job_pair_off, n_jobs, means);
     return 1;
+}
+
+int launch_widen_xyz(const float* in, double* out, uint64_t n3, cudaStream_t st) {
+    if (!n3) return 0;
+    widen_xyz_kernel<<<blocks_for(n3, 256), 256, 0, st>>>(in, out, n3);
+    return 1;
+}
+
+int launch_centroids(const float* atoms, uint64_t n_atoms, uint64_t n_frames, const uint32_t* seg_start,
+                     const uint32_t* atom_index, uint64_t n_prims, double* xyz_out, int* err, cudaStream_t st) {
+    if (!n_frames || !n_prims) return 0;
+    centroid_kernel<<<blocks_for(n_frames * n_prims, 128), 128, 0, st>>>(atoms, n_atoms, n_frames, seg_start, atom_index,
+                                                                       n_prims, xyz_out, err);
+    return 1;
+}
+
+int launch_validate_wf_idx(const uint32_t* wf_idx, uint64_t n, uint32_t n_wf, int* err, cudaStream_t st) {
+    if (!n || !wf_idx) return 0;
+    validate_wf_idx_kernel<<<blocks_for(n, 256), 256, 0, st>>>(wf_idx, n, n_wf, err);
+    return 1;
+}
+
+int launch_anchor_stats(const double* scores, uint64_t n, uint64_t n_jobs, double* sum_scratch, double* m2_scratch,
+                        double* mean_out, double* std_out, cudaStream_t st) {
+    if (!n || !n_jobs) return 0;
+    cudaMemsetAsync(sum_scratch, 0, n * sizeof(double), st);
+    const unsigned bx = blocks_for(n, kStatThreads);
+    // enough CTAs to fill the machine; every CTA column walks its share of the jobs
+    uint64_t splits = (148ull * 16 + bx - 1) / bx;
+    if (splits > n_jobs) splits = n_jobs;
+    if (splits > 65535) splits = 65535;
+    if (splits < 1) splits = 1;
+    const dim3 grid(bx, (unsigned)splits);
+    int launches = 2;
+    anchor_sum_kernel<<<grid, kStatThreads, 0, st>>>(scores, n, n_jobs, sum_scratch);
+    if (std_out) {
+        cudaMemsetAsync(m2_scratch, 0, n * sizeof(double), st);
+        anchor_dev_kernel<<<grid, kStatThreads, 0, st>>>(scores, n, n_jobs, sum_scratch, m2_scratch);
+        ++launches;
+    }
+    anchor_finish_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, n_jobs, sum_scratch, m2_scratch, mean_out, std_out);
+    return launches;
 }
 
 int launch_anchor_lists(const KParams& p, const uint8_t* seq_a, uint64_t len_a, const double* da, const uint8_t* seq_b,

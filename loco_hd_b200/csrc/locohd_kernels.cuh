@@ -174,6 +174,14 @@ int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsign
                  cudaStream_t st);
 int launch_job_means(const double* scores, const uint64_t* job_pair_off, uint64_t n_jobs, double* means,
                      cudaStream_t st);
+int launch_widen_xyz(const float* in, double* out, uint64_t n3, cudaStream_t st);
+// centroids of n_frames frames of one topology (f32 sequential mean per primitive) -> f64 coordinates
+int launch_centroids(const float* atoms, uint64_t n_atoms, uint64_t n_frames, const uint32_t* seg_start,
+                     const uint32_t* atom_index, uint64_t n_prims, double* xyz_out, int* err, cudaStream_t st);
+int launch_validate_wf_idx(const uint32_t* wf_idx, uint64_t n, uint32_t n_wf, int* err, cudaStream_t st);
+// per-anchor mean / population std over n_jobs uniform jobs of n anchors; scratch: two arrays of n doubles
+int launch_anchor_stats(const double* scores, uint64_t n, uint64_t n_jobs, double* sum_scratch, double* m2_scratch,
+                        double* mean_out, double* std_out, cudaStream_t st);
 int launch_anchor_lists(const KParams& p, const uint8_t* seq_a, uint64_t len_a, const double* da, const uint8_t* seq_b,
                         uint64_t len_b, const double* db, uint32_t wf_idx, double* out, cudaStream_t st);
 int launch_wf_points(const WfDev* wf, uint64_t n, const double* x, double* out, int* err, cudaStream_t st);

@@ -17,7 +17,7 @@ def pytest_configure(config):
     import sysconfig
 
     pkg = ROOT / "loco_hd_b200"
-    if not (pkg / "liblocohd_b200.so").exists() or not (pkg / ("_host" + sysconfig.get_config_var("EXT_SUFFIX"))).exists():
+    if not (pkg / "liblocohd_b200.so").exists() or not (ROOT / "loco_hd" / ("loco_hd" + sysconfig.get_config_var("EXT_SUFFIX"))).exists():
         spec = importlib.util.spec_from_file_location("_locohd_build", pkg / "build.py")
         b = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(b)

@@ -24,7 +24,8 @@ def test_header_symbols_are_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/locohd_b200.h but not exported"
     assert sorted(_capi.EXPORTED_SYMBOLS) == declared
-    assert lib.locohd_abi_version() == 1
+    version = int(re.search(r"#define\s+LOCOHD_ABI_VERSION\s+(\d+)", header).group(1))
+    assert lib.locohd_abi_version() == version == 2
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -63,3 +64,6 @@ def test_product_never_imports_the_oracle():
         text = path.read_text(errors="ignore")
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{path} imports the oracle"
         assert "locohd_oracle" not in text, f"{path} references the oracle"
+        # the host layer carries no PyTorch (north_star): torch is bench / test plumbing only
+        if path.suffix == ".py":
+            assert not re.search(r"^\s*(from|import)\s+torch\b", text, re.M), f"{path} imports torch"

@@ -8,7 +8,7 @@ Known answers come from the reference's own tests:
 import numpy as np
 import pytest
 
-from loco_hd_b200 import synth
+from benchdata import synth
 from helpers import (SCORE_TOL, assert_scores_close, canonical_env, check_from_primitives, random_cloud,
                      set_both)
 

@@ -9,7 +9,8 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from loco_hd_b200 import batch, synth
+from benchdata import synth
+from loco_hd_b200 import batch
 
 ROOT = Path(__file__).resolve().parent.parent
 

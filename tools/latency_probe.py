@@ -3,7 +3,8 @@ import sys, time
 from pathlib import Path
 import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from loco_hd_b200 import _capi, synth
+from benchdata import synth
+from loco_hd_b200 import _capi
 
 ctx = _capi.Context(0)
 for name, (a, b), C, wf in (("config 1 (450 primitives, 150 anchors)", synth.config1(), 7, ("uniform", (3.0, 10.0))),
