@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """bench.py — LoCoHD anchor-pairs/second on B200 (BASELINE.json metric), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5|cfg2|cfg3|cfg4] [--impl reference]
 
-A *step* is one pass of the hot path over one batch of synthetic structure pairs (SURVEY.md §8(d) generator):
-cell lists (K0) -> environments (K1, scan, K1') -> scoring (K2).  Default workload = BASELINE.json configs[1]:
-all_atom-shaped protein pairs (10 000 primitives each), kumaraswamy [3, 10, 2, 5], 10 A threshold, hetero
-contacts only, every primitive an anchor; `--pairs` structure pairs per GPU per step (weak scaling).
+A *step* is one pass of the hot path over one batch of synthetic structures (SURVEY.md §8(d) generator):
+cell lists (K0) -> environments (K1) -> scoring (K2) -> reductions.
+
+Default workload = the north-star target of BASELINE.json (configs[4]): the all-vs-all ensemble of 1000 structures x
+5000 primitives (all_atom shape, C = 7), uniform [3, 10], 10 A threshold, hetero contacts only, every primitive an
+anchor: 499 500 structure pairs = 2.4975e9 anchor pairs per step, dealt round-robin over the GPUs (strong scaling: the
+whole ensemble is resident on every GPU, no collective on the scoring path).  Only the per-structure-pair means leave
+the device (what compare_ensembles.py:293 computes from the scores; 20 GB of per-anchor scores stay in device scratch).
+At N = 1 the line also carries one short run each of configs[1..3] (`other_workloads`) and the Python-API call
+latencies (`e2e_python`).  `--workload cfg2|cfg3|cfg4` makes one of those the main workload (weak scaling).
 
     value  whole-job throughput with the structures already resident in HBM (CUDA events on the library stream)
     e2e    same metric through the C-ABI call sequence with HOST (pinned) buffers: H2D of the structures and
-           anchors and D2H of the scores inside the timed region (wall clock between synchronisations); measured
-           with one host thread (steps back to back) and with two host threads / contexts (the copies of one step
-           overlap the kernels of the other); `e2e.value` is the better of the two, both are in the line
+           anchors and D2H of the results inside the timed region (wall clock between synchronisations); short
+           steps are also measured with two host threads / contexts (the copies of one step overlap the kernels of
+           the other) and `e2e.value` is the better of the two, both are in the line
 
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/, all host threads; the Rust crate
-cannot be built in this image) on a bounded sample of the same workload.
+cannot be built in this image) on a bounded sample of the same workload.  That arm imports only `benchdata` and
+`oracle`: it never maps the CUDA library.
 """
 from __future__ import annotations
 
@@ -59,8 +66,7 @@ def _ensure_built():
         time.sleep(2.0)
 
 
-_ensure_built()
-from benchdata import synth  # noqa: E402
+from benchdata import synth  # noqa: E402  (no product code: the reference arm must not map the CUDA library)
 
 F_WF = {"uniform": 11, "kumaraswamy": 19, "dagum": 9}  # flops of one integral_range
 
@@ -70,8 +76,9 @@ class Workload:
     """clouds: structures of this rank; groups: (structure, anchor primitive indices) -> one environment each,
     laid out group after group; jobs: (group_a, group_b) scored with identity pairing."""
 
-    def __init__(self, name, desc, n_categories, wf, clouds, groups, jobs, scaling="weak"):
+    def __init__(self, name, desc, n_categories, wf, clouds, groups, jobs, scaling="weak", means_only=False):
         self.name, self.desc, self.C, self.wf, self.scaling = name, desc, n_categories, wf, scaling
+        self.means_only = means_only
         self.rule = {"accept_same": False}
         self.threshold = 10.0
         self.clouds = clouds
@@ -82,8 +89,11 @@ class Workload:
         self.anchor_struct = np.concatenate([np.full(len(p), s, np.uint32) for s, p in groups])
         self.anchor_prim = np.concatenate([np.asarray(p, np.uint32) for _, p in groups])
         goff = np.cumsum([0] + [len(p) for _, p in groups])
-        self.jobs = np.array([(goff[a], goff[b], goff[a + 1] - goff[a]) for a, b in jobs],
-                             dtype=[("a_first", "<u8"), ("b_first", "<u8"), ("n", "<u8")])
+        self.jobs = np.empty(len(jobs), dtype=[("a_first", "<u8"), ("b_first", "<u8"), ("n", "<u8")])
+        if len(jobs):
+            ja = np.asarray(jobs, dtype=np.int64).reshape(-1, 2)
+            self.jobs["a_first"], self.jobs["b_first"] = goff[ja[:, 0]], goff[ja[:, 1]]
+            self.jobs["n"] = goff[ja[:, 0] + 1] - goff[ja[:, 0]]
         self.n_pairs = int(self.jobs["n"].sum())
         self.groups, self.job_groups = groups, jobs
 
@@ -138,7 +148,7 @@ def make_workload(name, rank, world, args):
         return Workload("cfg5", f"BASELINE configs[4]: all-vs-all ensemble of {S} structures (5000 primitives, all_atom, "
                         f"C=7), uniform [3,10], every primitive an anchor; {len(all_jobs)} structure pairs dealt "
                         f"round-robin over {world} GPU(s)", 7, ("uniform", (3.0, 10.0)), clouds, groups,
-                        all_jobs[rank::world], scaling="strong")
+                        all_jobs[rank::world], scaling="strong", means_only=True)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -300,40 +310,63 @@ def emit(saved_fd, text):
     os.write(saved_fd, (text + "\n").encode())
 
 
-def run_gpu(args, rank, local_rank, world):
-    stdout_fd = quiet_stdout()
+class Ranks:
+    """Barrier / reductions over the ranks of the launch (no-ops for one process).  torch.distributed over NCCL is
+    the benchmark's plumbing only: the scoring path has no collective."""
+
+    def __init__(self, world, local_rank):
+        import torch
+
+        self.world, self.torch, self.dist = world, torch, None
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+
+    def _reduce(self, x, op):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._reduce(x, self.dist.ReduceOp.MAX) if self.dist else x
+
+    def sum(self, x):
+        return self._reduce(x, self.dist.ReduceOp.SUM) if self.dist else x
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+class Solo:
+    """The same interface for measurements that one rank makes on its own."""
+    world = 1
+
+    def barrier(self):
+        pass
+
+    def max(self, x):
+        return x
+
+    def sum(self, x):
+        return x
+
+
+def measure(wl, ctx, local_rank, ranks, steps, warmup, args, clocks=True):
+    """Times `steps` passes of the hot path over workload `wl` with resident inputs (CUDA events on the library
+    stream, max over ranks) and through host buffers (e2e); returns the numbers and the algorithmic work counts."""
     import torch
-    import torch.distributed as dist
 
     from loco_hd_b200 import _capi
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    wl = make_workload(args.workload, rank, world, args)
-    if args.threshold:   # exploration only: the BASELINE configurations use 10 A
-        wl.threshold = float(args.threshold)
-        wl.desc += f" [threshold overridden: {wl.threshold:g}]"
-    ctx = _capi.Context(local_rank)
     ctx.set_params(wl.C, [wl.wf], tag_rule=wl.rule)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     n_env = len(wl.anchor_prim)
@@ -342,10 +375,10 @@ def run_gpu(args, rank, local_rank, world):
     structs = ctx.structs_create(wl.offsets, wl.xyz, wl.cat, wl.tag)
     d_as = torch.from_numpy(wl.anchor_struct.view(np.int32)).cuda()
     d_ap = torch.from_numpy(wl.anchor_prim.view(np.int32)).cuda()
-    # Above --score-cap anchor pairs per step only the per-job (= per structure pair) means leave the device
-    # (what compare_ensembles.py:293-299 computes next): the full 1000-structure ensemble has
+    # The ensemble (and anything above --score-cap anchor pairs per step) returns only the per-job (= per structure
+    # pair) means (what compare_ensembles.py:293-299 computes next): the 1000-structure ensemble has
     # 2.5e9 anchor pairs = 20 GB of scores per step.  The per-anchor scores still exist (device scratch).
-    means_only = wl.n_pairs > args.score_cap
+    means_only = wl.means_only or wl.n_pairs > args.score_cap
     n_out = len(wl.jobs) if means_only else wl.n_pairs
     d_out = torch.empty(n_out, dtype=torch.float64, device="cuda")
 
@@ -361,31 +394,31 @@ def run_gpu(args, rank, local_rank, world):
         score(ctx, env, d_out.data_ptr())
         env.close()
 
-    clocks = ClockSampler(local_rank)
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local_rank) if clocks else None
+    for _ in range(warmup):
         step_resident()
     ctx.synchronize()
     ctx.profile_read()
-    barrier()
+    ranks.barrier()
     torch.cuda.synchronize()
     t_begin = time.perf_counter()
     ctx.profile_enable(True)
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_resident()
     e1.record(stream)
     torch.cuda.synchronize()
     t_end = time.perf_counter()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ranks.barrier()
+    ms_total = ranks.max(e0.elapsed_time(e1))
     launches = ctx.launch_count - launches0
     prof = ctx.profile_read()
     ctx.profile_enable(False)
-    clock_info = clocks.stop(t_begin, t_end)
-    total_pairs = sum_over_ranks(float(wl.n_pairs))
-    value = total_pairs * args.steps / (ms_total * 1e-3)
+    clock_info = sampler.stop(t_begin, t_end) if sampler else None
+    total_pairs = ranks.sum(float(wl.n_pairs))
+    value = total_pairs * steps / (ms_total * 1e-3)
 
     # ---- algorithmic work from the environment sizes of one extra, untimed build
     env = ctx.envset_build(structs, d_ap.data_ptr(), wl.threshold, anchor_struct=d_as.data_ptr(), n_anchors=n_env)
@@ -393,6 +426,8 @@ def run_gpu(args, rank, local_rank, world):
     ctx._check(ctx.lib.locohd_envset_dump(ctx.h, env.h, _capi._p(off), None, None, None))
     check_scores = d_out.cpu().numpy()
     env.close()
+    structs.close()
+    del d_out
     sizes = np.diff(off).astype(np.int64)
     ja, jb, jn = (wl.jobs[k].astype(np.int64) for k in ("a_first", "b_first", "n"))
     members = (off[ja + jn] - off[ja]).astype(np.int64) + (off[jb + jn] - off[jb]).astype(np.int64)  # sum of Ma + Mb per job
@@ -410,63 +445,149 @@ def run_gpu(args, rank, local_rank, world):
     h_ap = ctx.pinned_array(wl.anchor_prim.shape, np.uint32); h_ap[...] = wl.anchor_prim
     h_out = ctx.pinned_array((n_out,), np.float64)
 
-    def step_e2e(c=ctx, out=h_out):
-        st = c.structs_create(h_off, h_xyz, h_cat, h_tag)
+    def step_e2e(c=ctx, out=h_out, xyz=h_xyz):
+        st = c.structs_create(h_off, xyz, h_cat, h_tag)
         env = c.envset_build(st, h_ap, wl.threshold, anchor_struct=h_as)
         score(c, env, out)
         env.close()
         st.close()
 
-    e2e_steps = max(2, min(args.steps, 6)) // 2 * 2
-    for _ in range(2):
+    step_ms = ms_total / steps
+    long_steps = step_ms > 500.0            # seconds-long steps: copies are noise, two timed steps are enough
+    e2e_steps = 2 if long_steps else max(2, min(steps, 6)) // 2 * 2
+    for _ in range(1 if long_steps else 2):
         step_e2e()
     ctx.synchronize()
-    barrier()
+    ranks.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
     ctx.synchronize()
-    t_serial = max_over_ranks(time.perf_counter() - t0)
+    t_serial = ranks.max(time.perf_counter() - t0)
     e2e_serial = total_pairs * e2e_steps / t_serial
     e2e_ok = bool(np.array_equal(h_out, check_scores))
+    e2e = {"value": e2e_serial, "unit": "anchor-pairs/s", "h2d_bytes_per_step": int(wl.h2d_bytes),
+           "d2h_bytes_per_step": int(8 * n_out), "steps": e2e_steps, "mode": "one host thread, steps back to back",
+           "one_thread_value": e2e_serial}
 
-    # The same calls from two host threads, each with its own context (= stream) and output buffer: the H2D copies
-    # of one step overlap the kernels of the other.  Every step still uploads its inputs from pinned host memory
-    # and reads its scores back inside the timed region.
-    ctx2 = _capi.Context(local_rank)
-    ctx2.set_params(wl.C, [wl.wf], tag_rule=wl.rule)
-    h_out2 = ctx2.pinned_array((n_out,), np.float64)
-    lanes = [(ctx, h_out), (ctx2, h_out2)]
+    if not long_steps:
+        # The same calls from two host threads, each with its own context (= stream) and output buffer: the H2D
+        # copies of one step overlap the kernels of the other.  Every step still uploads its inputs from pinned host
+        # memory and reads its scores back inside the timed region.
+        ctx2 = _capi.Context(local_rank)
+        ctx2.set_params(wl.C, [wl.wf], tag_rule=wl.rule)
+        h_out2 = ctx2.pinned_array((n_out,), np.float64)
+        lanes = [(ctx, h_out), (ctx2, h_out2)]
 
-    def worker(c, out, n):
-        torch.cuda.set_device(local_rank)
-        for _ in range(n):
-            step_e2e(c, out)
-        c.synchronize()
+        def worker(c, out, n):
+            torch.cuda.set_device(local_rank)
+            for _ in range(n):
+                step_e2e(c, out)
+            c.synchronize()
 
-    def run_pipelined(n_each):
-        ths = [threading.Thread(target=worker, args=(c, o, n_each)) for c, o in lanes]
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
+        def run_pipelined(n_each):
+            ths = [threading.Thread(target=worker, args=(c, o, n_each)) for c, o in lanes]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
 
-    run_pipelined(1)
-    barrier()
-    t0 = time.perf_counter()
-    run_pipelined(e2e_steps // 2)
-    t_pipe = max_over_ranks(time.perf_counter() - t0)
-    e2e_pipe = total_pairs * e2e_steps / t_pipe
-    e2e_ok = e2e_ok and bool(np.array_equal(h_out2, check_scores))
-    ctx2.close()
-    e2e_value, e2e_mode = (e2e_pipe, "two host threads / contexts, copies of one step overlap kernels of the other") \
-        if e2e_pipe > e2e_serial else (e2e_serial, "one host thread, steps back to back")
+        run_pipelined(1)
+        ranks.barrier()
+        t0 = time.perf_counter()
+        run_pipelined(e2e_steps // 2)
+        t_pipe = ranks.max(time.perf_counter() - t0)
+        e2e_pipe = total_pairs * e2e_steps / t_pipe
+        e2e_ok = e2e_ok and bool(np.array_equal(h_out2, check_scores))
+        ctx2.close()
+        e2e["two_thread_value"] = e2e_pipe
+        if e2e_pipe > e2e_serial:
+            e2e["value"], e2e["mode"] = e2e_pipe, "two host threads / contexts, copies of one step overlap kernels of the other"
 
+        # f32 wire format (locohd_structs_create_f32): real coordinates are float32 (Bio.PDB, MDAnalysis), the synthetic
+        # ones are rounded through float32 for this variant only; half the coordinate bytes cross the bus.  Reported
+        # beside the f64 figure, not instead of it (different inputs).
+        if wl.name in ("cfg3", "cfg4"):
+            x32 = ctx.pinned_array(wl.xyz.shape, np.float32); x32[...] = wl.xyz
+            step_e2e(xyz=x32)
+            ctx.synchronize()
+            ranks.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                step_e2e(xyz=x32)
+            ctx.synchronize()
+            t32 = ranks.max(time.perf_counter() - t0)
+            e2e["f32_wire"] = {"value": total_pairs * e2e_steps / t32, "one host thread": True,
+                               "h2d_bytes_per_step": int(wl.h2d_bytes - wl.xyz.nbytes // 2),
+                               "note": "coordinates rounded through float32 and uploaded as float32 (exact widening on the device)"}
+    e2e["scores_identical_to_resident_run"] = e2e_ok
+
+    return {"value": value, "ms_total": ms_total, "step_ms": step_ms, "launches": int(launches), "prof": prof,
+            "clocks": clock_info, "total_pairs": total_pairs, "n_env": n_env, "sizes": sizes, "f_walk": f_walk,
+            "f_gather": f_gather, "alg_bytes": alg_bytes, "check_scores": check_scores, "means_only": means_only,
+            "e2e": e2e, "n_out": n_out}
+
+
+def python_api_latency(local_rank):
+    """The drop-in Python API on single structure pairs (what a user of the reference calls): LoCoHD.from_primitives
+    with lists of PrimitiveAtom / anchor tuples, and the array form from_arrays, against the bare C-ABI call."""
+    import loco_hd
+    from loco_hd_b200 import _capi
+
+    loco_hd.loco_hd.set_device(local_rank)
+    out = {}
+    ctx = _capi.Context(local_rank)
+    for key, (a, b), C, wf, step in (("cfg1_150_anchors", synth.config1(), 7, ("uniform", (3.0, 10.0)), 3),
+                                     ("cfg2_10000_anchors", synth.config2(), 7, ("kumaraswamy", (3.0, 10.0, 2.0, 5.0)), 1)):
+        anchors = np.stack([np.arange(0, a.n, step, dtype=np.uint32)] * 2, axis=1)
+        ctx.set_params(C, [wf], tag_rule={"accept_same": False})
+        lchd = loco_hd.LoCoHD([f"T{i}" for i in range(C)], loco_hd.WeightFunction(wf[0], list(wf[1])),
+                              loco_hd.TagPairingRule({"accept_same": False}))
+        pa = [loco_hd.PrimitiveAtom(f"T{c}", str(t), x) for x, c, t in zip(a.xyz.tolist(), a.cat, a.tag)]
+        pb = [loco_hd.PrimitiveAtom(f"T{c}", str(t), x) for x, c, t in zip(b.xyz.tolist(), b.cat, b.tag)]
+        ap = [tuple(map(int, q)) for q in anchors]
+        calls = {"c_abi": lambda: ctx.from_primitives(a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, 10.0),
+                 "from_primitives_lists": lambda: lchd.from_primitives(pa, pb, ap, 10.0),
+                 "from_arrays": lambda: lchd.from_arrays(a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, 10.0)}
+        row = {}
+        ref = None
+        for name, fn in calls.items():
+            for _ in range(3):
+                r = np.asarray(fn())
+            n = 20
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            dt = (time.perf_counter() - t0) / n
+            ref = r if ref is None else ref
+            row[name] = {"ms_per_call": 1e3 * dt, "anchor_pairs_per_s": len(anchors) / dt,
+                         "identical_to_c_abi": bool(np.array_equal(r, ref))}
+        out[key] = row
+    ctx.close()
+    return out
+
+
+def run_gpu(args, rank, local_rank, world):
+    stdout_fd = quiet_stdout()
+    _ensure_built()
+    import torch
+
+    from loco_hd_b200 import _capi
+
+    torch.cuda.set_device(local_rank)
+    ranks = Ranks(world, local_rank)
+    wl = make_workload(args.workload, rank, world, args)
+    if args.threshold:   # exploration only: the BASELINE configurations use 10 A
+        wl.threshold = float(args.threshold)
+        wl.desc += f" [threshold overridden: {wl.threshold:g}]"
+    ctx = _capi.Context(local_rank)
+    m = measure(wl, ctx, local_rank, ranks, args.steps, args.warmup, args)
     if rank != 0:
         ctx.close()
-        if world > 1:
-            dist.destroy_process_group()
+        ranks.close()
         return
+    prof, sizes, step_ms = m["prof"], m["sizes"], m["step_ms"]
+    f_walk, f_gather, alg_bytes, means_only = m["f_walk"], m["f_gather"], m["alg_bytes"], m["means_only"]
 
     # ---- rooflines (rank 0's kernels; all ranks run identical shapes)
     peaks = {}
@@ -475,7 +596,10 @@ def run_gpu(args, rank, local_rank, world):
     except OSError:
         pass
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    probe_clocks = ClockSampler(local_rank)
+    t_p0 = time.perf_counter()
     fp64_peak = ctx.measure_fp64_tflops()
+    probe_info = probe_clocks.stop(t_p0, time.perf_counter())
     kernels = {g: {"ms_per_step": ms / args.steps, "share": ms / max(sum(v[0] for v in prof.values()), 1e-9)}
                for g, (ms, n) in prof.items() if n}
     # Algorithmic flops per kernel: walk E * (10 C + 4 + F_wf) -> K2; the 10 flops per environment
@@ -493,14 +617,16 @@ def run_gpu(args, rank, local_rank, world):
                         f_gather),
                "count": ("env_tile_kernel<false> with stride 16 (store sizing sample)", 0.0)}
     traffic, pipes, prof_src = {}, {}, None
-    try:
-        tr = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+    for tf in sorted((ROOT / "profiles").glob("*_traffic.json"), reverse=True):   # newest round first
+        try:
+            tr = json.loads(tf.read_text())
+        except (OSError, ValueError):
+            continue
         if tr.get("workload") == wl.name and tr.get("anchor_pairs_per_step") == wl.n_pairs:
             traffic = tr.get("dram_bytes_per_launch", {})
             pipes = tr.get("pipes", {})
             prof_src = tr.get("source")
-    except (OSError, ValueError):
-        pass
+            break
     per_kernel = {}
     for g, (name, flops) in alg.items():
         if g in kernels and kernels[g]["ms_per_step"] > 0:
@@ -512,13 +638,16 @@ def run_gpu(args, rank, local_rank, world):
     dom = max(per_kernel, key=lambda g: per_kernel[g]["launch_ms"])
     dominant, dom_flops, dom_ms = per_kernel[dom]["kernel"], per_kernel[dom]["alg_flops_per_launch"], per_kernel[dom]["launch_ms"]
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
-    step_ms = ms_total / args.steps
     roofline = {
         "kernel": dominant,
         "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-        "peak_source": "FP64 FMA probe kernel run in this process (MEASURED_PEAKS.json has no FP64 entry)",
+        "peak_source": (f"FP64 FMA probe kernel run in this process: {fp64_peak:.2f} TFLOP/s at SM "
+                        f"{probe_info.get('sm_mhz')} MHz (max {probe_info.get('sm_max_mhz')}), reasons "
+                        f"{probe_info.get('reasons')}; MEASURED_PEAKS.json has no FP64 entry (nominal 148 SM x 64 FMA/clk "
+                        "x 2 x 1.965 GHz = 37.2)"),
+        "peak_probe": {"tflops": fp64_peak, "clocks": probe_info},
         "traffic": traffic.get(dom), "alg_flops_per_launch": dom_flops, "launch_ms": dom_ms,
-        "note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch from profiles/ (ncu --set full)",
+        "note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch from profiles/ (ncu)",
     }
     roofline_hbm = {"bound": "hbm", "achieved": alg_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
@@ -529,6 +658,7 @@ def run_gpu(args, rank, local_rank, world):
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle on a bounded sample of the same workload
     cpu = None
+    check_scores = m["check_scores"]
     if world == 1 and not args.no_cpu_baseline:
         import oracle
 
@@ -552,31 +682,53 @@ def run_gpu(args, rank, local_rank, world):
                    float(abs(ref.mean() - check_scores[0]) if means_only else np.abs(ref - check_scores[:n0]).max()),
                "note": "C++/OpenMP restatement of the reference algorithm (Rust toolchain unavailable)"}
 
+    # ---- the other BASELINE configurations, one short run each (N = 1 only), and the Python API
+    others, py_api = None, None
+    if world == 1 and not args.no_extras:
+        others = {}
+        for name in ("cfg2", "cfg3", "cfg4", "cfg5"):
+            if name == wl.name:
+                continue
+            xa = argparse.Namespace(**vars(args))
+            if name == "cfg5":
+                xa.ensemble = 96
+            w2 = make_workload(name, 0, 1, xa)
+            r = measure(w2, ctx, local_rank, Solo(), max(3, min(args.steps, 5)), 3, args, clocks=False)
+            tot = max(sum(v[0] for v in r["prof"].values()), 1e-9)
+            others[name] = {"workload": w2.desc, "value": r["value"], "unit": "anchor-pairs/s",
+                            "ms_per_step": r["step_ms"], "anchor_pairs_per_step": w2.n_pairs,
+                            "e2e": r["e2e"], "gpu_launches": r["launches"],
+                            "kernel_ms_per_step": {g: ms / max(3, min(args.steps, 5)) for g, (ms, n) in r["prof"].items() if n},
+                            "kernel_share": {g: ms / tot for g, (ms, n) in r["prof"].items() if n},
+                            "roofline_step_frac_fp64": (r["f_walk"] + r["f_gather"]) / (r["step_ms"] * 1e-3) / 1e12 / fp64_peak,
+                            "env_size_mean": float(r["sizes"].mean())}
+            del r, w2
+        py_api = python_api_latency(local_rank)
+
     line = {
-        "metric": "anchor_pairs_per_second", "value": value, "unit": "anchor-pairs/s", "n_gpus": world,
+        "metric": "anchor_pairs_per_second", "value": m["value"], "unit": "anchor-pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl.desc, "anchor_pairs_per_gpu_per_step": wl.n_pairs,
-                   "environments_per_gpu_per_step": n_env,
+                   "anchor_pairs_per_step_all_gpus": int(m["total_pairs"]),
+                   "environments_per_gpu_per_step": m["n_env"],
                    "result": ("per-structure-pair mean scores (locohd_score_jobs out_job_means); the per-anchor scores "
                               "stay in device scratch") if means_only else "per-anchor scores",
                    "l2": f"inputs larger than L2 each step: {wl.h2d_bytes / 1e6:.0f} MB of structures/anchors + "
-                         f"{8 * float(sizes.sum()) / 1e6:.0f} MB environment store written and read per step"},
-        "e2e": {"value": e2e_value, "unit": "anchor-pairs/s", "h2d_bytes_per_step": int(wl.h2d_bytes),
-                "d2h_bytes_per_step": int(8 * n_out), "steps": e2e_steps, "mode": e2e_mode,
-                "one_thread_value": e2e_serial, "two_thread_value": e2e_pipe,
-                "scores_identical_to_resident_run": e2e_ok},
-        "gpu_launches": int(launches),
-        "clocks": clock_info,
+                         f"{8 * float(sizes.sum()) / 1e6:.0f} MB environment store written per step and streamed by K2"},
+        "e2e": m["e2e"],
+        "gpu_launches": m["launches"],
+        "clocks": m["clocks"],
         "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_step": roofline_step,
         "kernels": kernels, "kernel_rooflines": per_kernel,
         "env_size_mean": float(sizes.mean()), "env_size_max": int(sizes.max()),
         "cpu_baseline": cpu,
+        "other_workloads": others,
+        "e2e_python": py_api,
     }
     emit(stdout_fd, json.dumps(line))
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    ranks.close()
 
 
 def main():
@@ -585,13 +737,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--pairs", type=int, default=256, help="cfg2: structure pairs per GPU per step")
     ap.add_argument("--models", type=int, default=500, help="cfg3: models per GPU per step")
     ap.add_argument("--frames", type=int, default=1024, help="cfg4: frames per GPU per step")
-    ap.add_argument("--ensemble", type=int, default=96, help="cfg5: ensemble size (all-vs-all, jobs dealt over GPUs)")
+    ap.add_argument("--ensemble", type=int, default=1000, help="cfg5: ensemble size (all-vs-all, jobs dealt over GPUs)")
     ap.add_argument("--ref-pairs", type=int, default=160000, help="anchor pairs per CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other configurations and the Python-API latencies")
     ap.add_argument("--score-cap", type=int, default=1 << 28,
                     help="above this many anchor pairs per GPU per step only the per-job means are copied out")
     ap.add_argument("--threshold", type=float, default=0.0, help="override the 10 A threshold (exploration only)")

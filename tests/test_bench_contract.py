@@ -15,7 +15,7 @@ REQUIRED = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_
 def _run(extra_env=None):
     env = dict(os.environ)
     env.update(extra_env or {})
-    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--pairs", "2",
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ensemble", "4",
            "--ref-pairs", "4000"]
     return subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
 
@@ -33,6 +33,18 @@ def test_reference_arm_prints_one_json_line():
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and "model" not in line["config"]
+    assert "all-vs-all ensemble" in line["config"]["workload"] and line["scaling"] == "strong"   # the north-star workload is the default
+
+
+def test_reference_arm_does_not_map_the_product_library():
+    """The CPU arm must not load the CUDA library or the host extension (it only needs benchdata and the oracle)."""
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--ensemble', '3', "
+            "'--ref-pairs', '2000']; runpy.run_path('bench.py', run_name='__main__'); "
+            "maps = open('/proc/self/maps').read(); "
+            "assert 'liblocohd_b200' not in maps and 'loco_hd.cpython' not in maps, 'product library mapped'; "
+            "assert 'loco_hd_b200' not in sys.modules and 'loco_hd' not in sys.modules")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
 
 
 def test_reference_arm_other_ranks_stay_silent():

@@ -1,0 +1,106 @@
+"""CPU-side checks of what this implementation adds around the reference API: the type stub describes the
+extension module that is actually built, the id helpers work without a device, scoring without a device fails loudly
+from several threads at once (no deadlock, no fallback), and the per-rank statistics pool exactly."""
+import ast
+import threading
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import loco_hd
+from loco_hd_b200 import batch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_stub_matches_the_built_module():
+    """loco_hd/loco_hd.pyi (the API contract, reference: loco_hd/loco_hd.pyi:7-290) names exactly the public classes,
+    methods and functions of the built extension loco_hd.loco_hd; the reference's five classes keep their signatures."""
+    native = loco_hd.loco_hd
+    assert Path(native.__file__).parent == ROOT / "loco_hd" and Path(native.__file__).suffix == ".so"
+    tree = ast.parse((ROOT / "loco_hd" / "loco_hd.pyi").read_text())
+    classes = {n.name: n for n in tree.body if isinstance(n, ast.ClassDef)}
+    assert {"WeightFunction", "PrimitiveAtom", "TagPairingRule", "StatisticalDistance", "LoCoHD"} <= set(classes)
+    for cname, node in classes.items():
+        cls = getattr(native, cname)
+        stub_methods = {f.name for f in node.body if isinstance(f, ast.FunctionDef)}
+        stub_attrs = {a.target.id for a in node.body if isinstance(a, ast.AnnAssign)}
+        for name in (stub_methods | stub_attrs) - {"__init__", "__len__"}:
+            assert hasattr(cls, name), f"{cname}.{name} is in the stub but not in the module"
+        public = {n for n in vars(cls) if not n.startswith("_")}
+        assert public <= (stub_methods | stub_attrs), f"{cname}: undocumented {public - stub_methods - stub_attrs}"
+    for fn in (n.name for n in tree.body if isinstance(n, ast.FunctionDef)):
+        assert callable(getattr(native, fn))
+
+    def args_of(cname, fname):
+        f = [f for f in classes[cname].body if isinstance(f, ast.FunctionDef) and f.name == fname][0]
+        return [a.arg for a in f.args.args[1:]], len(f.args.defaults)
+
+    # positional order, names and number of defaults of the reference's signatures (src/locohd.rs:290-302, 392, 410, 463, 479)
+    assert args_of("LoCoHD", "__init__") == (["categories", "w_func", "tag_pairing_rule", "n_of_threads", "category_weights",
+                                              "statistical_distance"], 5)
+    assert args_of("LoCoHD", "from_anchors") == (["seq_a", "seq_b", "dists_a", "dists_b", "w_func_key"], 1)
+    assert args_of("LoCoHD", "from_dmxs") == (["seq_a", "seq_b", "dmx_a", "dmx_b", "w_func_keys"], 1)
+    assert args_of("LoCoHD", "from_coords") == (["seq_a", "seq_b", "coords_a", "coords_b", "w_func_keys"], 1)
+    assert args_of("LoCoHD", "from_primitives") == (["prim_a", "prim_b", "anchor_pairs", "threshold_distance"], 0)
+    assert args_of("WeightFunction", "__init__") == (["function_name", "parameters"], 0)
+    assert args_of("PrimitiveAtom", "__init__") == (["primitive_type", "tag", "coordinates"], 0)
+    assert args_of("StatisticalDistance", "__init__") == (["distance_name", "parameters"], 0)
+    # the keyword names work on the built module
+    lchd = loco_hd.LoCoHD(categories=["A", "B"], w_func=None, tag_pairing_rule=None, n_of_threads=2, category_weights=[1., 2.],
+                          statistical_distance=loco_hd.StatisticalDistance(distance_name="Hellinger", parameters=[2.]))
+    assert lchd.category_weights == [1., 2.]
+
+
+def test_category_ids_without_a_device():
+    lchd = loco_hd.LoCoHD(["O", "N", "C"])
+    ids = lchd.category_ids(np.array(["C", "O", "zzz", "N"]))
+    assert ids.dtype == np.uint16 and ids.tolist() == [2, 0, 0xFFFF, 1]
+
+
+def test_scoring_without_a_device_fails_loudly_from_two_threads():
+    if loco_hd.loco_hd.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    lchd = loco_hd.LoCoHD(["A", "B"])
+    atoms = [loco_hd.PrimitiveAtom("A", "", [0., 0., 0.]), loco_hd.PrimitiveAtom("B", "", [1., 0., 0.])]
+    seen = []
+
+    def work():
+        for _ in range(20):
+            for call in (lambda: lchd.from_primitives(atoms, atoms, [(0, 0)], 5.0),
+                         lambda: lchd.from_anchors(["A"], ["B"], [0.], [0.]),
+                         lambda: lchd.intern_tags(["x"])):
+                try:
+                    call()
+                    seen.append("returned")
+                except RuntimeError as exc:
+                    seen.append("no CPU fallback" in str(exc))
+
+    threads = [threading.Thread(target=work, daemon=True) for _ in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=60)
+    assert not any(t.is_alive() for t in threads)
+    assert len(seen) == 120 and all(v is True for v in seen)
+
+
+def test_flatten_accepts_generators_of_temporaries():
+    """from_primitives takes any iterable of PrimitiveAtom; atoms created on the fly (and gone again when the next
+    one arrives) must not be referenced afterwards (the tag / type of the previous item is compared by value)."""
+    if loco_hd.loco_hd.device_count() > 0:
+        pytest.skip("a CUDA device is present: covered by the gpu tests")
+    lchd = loco_hd.LoCoHD(["A", "B"])
+    gen = (loco_hd.PrimitiveAtom("AB"[i % 2], f"tag{i // 3}", [float(i), 0., 0.]) for i in range(5000))
+    with pytest.raises(RuntimeError):   # the device is missing, but only after the Python-side work
+        lchd.from_primitives(gen, [loco_hd.PrimitiveAtom("A", "t", [0., 0., 0.])], [(0, 0)], 5.0)
+
+
+def test_combine_anchor_stats_pools_exactly():
+    rng = np.random.default_rng(3)
+    x = rng.random((37, 11))
+    parts = [x[:5], x[5:20], x[20:]]
+    mean, std = batch.combine_anchor_stats([len(q) for q in parts], [q.mean(axis=0) for q in parts],
+                                           [q.std(axis=0) for q in parts])
+    assert np.abs(mean - x.mean(axis=0)).max() < 1e-15 and np.abs(std - x.std(axis=0)).max() < 1e-15
