@@ -687,7 +687,9 @@ __device__ __noinline__ void fused_repair(uint32_t* key32, const double* d2s, co
     }
 }
 
-// WFK: 0 uniform, 1 kumaraswamy with small integer exponents, 2 anything else (wf_cdf, or plain distances).
+// WFK: 0 uniform, 1 kumaraswamy with small integer exponents, 2 anything else (wf_cdf, or plain distances),
+// 3 kumaraswamy with the exponents (2, 5) of the reference's own parametrisation (tests/test_locohd.py:42) fixed at
+// compile time: the run-time switch of powi_small cost 151 warp instructions per environment (profiles/r4g_k1_lines.md).
 // The parameters of variants 0 and 1 are read once per kernel into registers (FusedWf): left in global memory the
 // compiler reloads them in every round of the store loop (they may alias the stores) and the loop waits on them.
 struct FusedWf {
@@ -703,6 +705,12 @@ __device__ __forceinline__ double fused_weight(const WfDev& wf, const FusedWf& f
         const double z = (d - f.p0) * f.inv_range;
         const double u = 1.0 - powi_small(z, f.int_a);
         const double v = 1.0 - powi_small(u, f.int_b);
+        return (d < f.p0) ? 0.0 : ((d > f.p1) ? 1.0 : v);
+    } else if (WFK == 3) {   // the same operations powi_small performs for e = 2 and e = 5
+        const double z = (d - f.p0) * f.inv_range;
+        const double u = 1.0 - z * z;
+        const double u2 = u * u;
+        const double v = 1.0 - u2 * u2 * u;
         return (d < f.p0) ? 0.0 : ((d > f.p1) ? 1.0 : v);
     } else {
         return key_is_w ? wf_cdf(wf, d) : d;
@@ -877,10 +885,13 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
                 const double ex = r.x - q.x, ey = r.y - q.y, ez = r.z - q.z;
                 const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
                 bool acc = valid && d2 < r2;
-                if (acc && !(d2 < r2_safe)) {
-                    // within rounding distance of the sphere: the crate's per-axis box test can still reject
-                    acc = !(r.x < q.x - threshold) && !(r.x > q.x + threshold) && !(r.y < q.y - threshold) &&
-                          !(r.y > q.y + threshold) && !(r.z < q.z - threshold) && !(r.z > q.z + threshold);
+                // Within rounding distance of the sphere the crate's per-axis box test can still reject.  The thin
+                // shell is hit by about one candidate in 1e14: a warp-uniform branch (one vote) instead of a
+                // divergent region around every test.
+                if (__any_sync(kFull, acc && !(d2 < r2_safe))) {
+                    if (acc && !(d2 < r2_safe))
+                        acc = !(r.x < q.x - threshold) && !(r.x > q.x + threshold) && !(r.y < q.y - threshold) &&
+                              !(r.y > q.y + threshold) && !(r.z < q.z - threshold) && !(r.z > q.z + threshold);
                 }
                 if (simple_rule) acc = acc && (((rtag == qtag) == accept_same) || j == jpos);
                 else if (acc && j != jpos) acc = tag_rule_accepts(p, qtag, rtag);
@@ -2092,6 +2103,7 @@ static int fused_wfk(const KParams& p, const WfDev* host_wf, int key_is_w) {
     (void)p;
     if (!key_is_w || !host_wf) return 2;
     if (host_wf->kind == LOCOHD_WF_UNIFORM) return 0;
+    if (host_wf->kind == LOCOHD_WF_KUMARASWAMY && host_wf->int_a == 2 && host_wf->int_b == 5) return 3;
     if (host_wf->kind == LOCOHD_WF_KUMARASWAMY && host_wf->int_a >= 0 && host_wf->int_b >= 0) return 1;
     return 2;
 }
@@ -2136,7 +2148,11 @@ static void fused_launch_t(const StructsView& s, const KParams& p, const uint32_
         case 8: LOCOHD_FUSED_DISPATCH2(CALL, 2, false, 512) break;                                        \
         case 9: LOCOHD_FUSED_DISPATCH2(CALL, 2, false, 1024) break;                                       \
         case 10: LOCOHD_FUSED_DISPATCH2(CALL, 2, true, 512) break;                                        \
-        default: LOCOHD_FUSED_DISPATCH2(CALL, 2, true, 1024) break;                                       \
+        case 11: LOCOHD_FUSED_DISPATCH2(CALL, 2, true, 1024) break;                                       \
+        case 12: LOCOHD_FUSED_DISPATCH2(CALL, 3, false, 512) break;                                       \
+        case 13: LOCOHD_FUSED_DISPATCH2(CALL, 3, false, 1024) break;                                      \
+        case 14: LOCOHD_FUSED_DISPATCH2(CALL, 3, true, 512) break;                                        \
+        default: LOCOHD_FUSED_DISPATCH2(CALL, 3, true, 1024) break;                                       \
     }
 
 unsigned fused_grid(const KParams& p, const WfDev* host_wf, int key_is_w, bool debug, int cap, uint64_t n_env) {
