@@ -1528,6 +1528,11 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
 //   * D is rebuilt from the counts at the start of every lane's chunk (at most 64 events), so rounding cannot drift.
 // Error of the fast branch: |dH| <= ~5e-16 / (2 * sqrt(kSmallH2)) = 2.5e-12 (bar: 1e-9 on the score).
 // With KEY_IS_W the environments already hold W(distance).  Pairs that do not fit the stage are left to score_kernel.
+// (Measured and dropped in round 2, profiles/r5c_k2_lanes_per_pair.md: 16 or 8 lanes per pair, i.e. two or four pairs
+//  per warp with a stage each.  The set-up is then issued once for two pairs - 1 503 instead of 1 949 warp instructions
+//  and 455 instead of 523 shared-memory wavefronts per pair - but a stage per pair leaves 18 warps per SM and a warp
+//  needs ~6 cycles per instruction (fixed-latency and shared-memory dependencies): issue slots 63 % busy instead of
+//  82 %, 12.3 ms against 11.6 ms.)
 constexpr double kSmallH2 = 1e-8;
 
 // sqrt of a double in [1e-8, ~1]: MUFU.RSQ (f32) seed + one coupled Newton step in FP64, relative error
@@ -2305,6 +2310,7 @@ int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsign
     const int budget = 220 * 1024;  // one CTA per SM: the tables are staged once, the rest goes to the warps' stages
     int warps = (budget - tables) / per_warp;
     if (warps > score_fast_max_warps(key_is_w, check)) warps = score_fast_max_warps(key_is_w, check);
+    if (const char* v = std::getenv("LOCOHD_SCORE_WARPS")) { const int w = std::atoi(v); if (w >= 1 && w < warps) warps = w; }   // occupancy sweeps
     if (warps < 1) warps = 1;
     const int smem = tables + per_warp * warps;
     if (CP == 8) n += key_is_w ? launch_fast<8, true>(a, p, check, warps, per_warp, smem, st)
