@@ -186,6 +186,11 @@ int locohd_envset_build(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, 
  * [row_len] is shared by all rows.  Rows are sorted on the device (utils.rs:25-39). */
 int locohd_envset_from_rows(locohd_ctx* ctx, uint64_t n_rows, uint64_t row_len, const double* dmx,
                             const uint16_t* category, locohd_envset** out);
+/* The same for rows of different lengths (the reference takes Vec<Vec<f64>>: row r is co-sorted with the first len_r
+ * entries of the category sequence, utils.rs:25-39): row r = values[row_offsets[r] .. row_offsets[r + 1]); category
+ * holds n_categories_given entries and every row must be at most that long (the reference panics otherwise). */
+int locohd_envset_from_ragged_rows(locohd_ctx* ctx, uint64_t n_rows, const uint64_t* row_offsets, const double* values,
+                                   const uint16_t* category, uint64_t n_categories_given, locohd_envset** out);
 /* from_coords (locohd.rs:463-476 + utils.rs:10-22): rows are Euclidean distances of every point to every point. */
 int locohd_envset_from_coords(locohd_ctx* ctx, uint64_t n_points, const double* xyz, const uint16_t* category,
                               locohd_envset** out);

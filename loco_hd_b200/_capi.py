@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = [
     "locohd_host_alloc", "locohd_host_free", "locohd_structs_create", "locohd_structs_create_f32",
     "locohd_structs_destroy", "locohd_structs_update_xyz", "locohd_structs_update_xyz_f32",
     "locohd_structs_update_from_atoms", "locohd_structs_drop_cells", "locohd_envset_build", "locohd_envset_from_rows",
+    "locohd_envset_from_ragged_rows",
     "locohd_envset_from_coords", "locohd_envset_destroy", "locohd_envset_size", "locohd_envset_total_members",
     "locohd_envset_dump", "locohd_score_pairs", "locohd_score_jobs", "locohd_score_jobs_stats",
     "locohd_score_anchor_lists",
@@ -109,6 +110,7 @@ def load_library() -> C.CDLL:
         "locohd_structs_drop_cells": (None, [vp]),
         "locohd_envset_build": (C.c_int, [vp, vp, u64, vp, vp, dbl, C.c_int, C.POINTER(vp)]),
         "locohd_envset_from_rows": (C.c_int, [vp, u64, u64, vp, vp, C.POINTER(vp)]),
+        "locohd_envset_from_ragged_rows": (C.c_int, [vp, u64, vp, vp, vp, u64, C.POINTER(vp)]),
         "locohd_envset_from_coords": (C.c_int, [vp, u64, vp, vp, C.POINTER(vp)]),
         "locohd_envset_destroy": (None, [vp]),
         "locohd_envset_size": (u64, [vp]),
@@ -301,6 +303,17 @@ class Context:
         cat = np.ascontiguousarray(category, dtype=np.uint16)
         h = C.c_void_p()
         self._check(self.lib.locohd_envset_from_rows(self.h, dmx.shape[0], dmx.shape[1], _p(dmx), _p(cat), C.byref(h)))
+        return EnvSet(self, h)
+
+    def envset_from_ragged_rows(self, rows, category) -> "EnvSet":
+        """rows: sequence of 1-D distance arrays of different lengths (locohd_envset_from_ragged_rows)."""
+        rows = [np.ascontiguousarray(r, dtype=np.float64).ravel() for r in rows]
+        offs = np.cumsum([0] + [len(r) for r in rows]).astype(np.uint64)
+        vals = np.concatenate(rows) if rows else np.zeros(0)
+        cat = np.ascontiguousarray(category, dtype=np.uint16)
+        h = C.c_void_p()
+        self._check(self.lib.locohd_envset_from_ragged_rows(self.h, len(rows), _p(offs), _p(vals), _p(cat), len(cat),
+                                                            C.byref(h)))
         return EnvSet(self, h)
 
     def envset_from_coords(self, xyz, category) -> "EnvSet":

@@ -544,37 +544,70 @@ struct LoCoHD {
     }
 
     // ---- from_dmxs (locohd.rs:410-458)
+    // A distance matrix as the reference takes it (Vec<Vec<f64>>): rows may have different lengths.
+    struct Rows {
+        std::vector<uint64_t> off{0};
+        std::vector<double> val;
+        size_t n() const { return off.size() - 1; }
+        size_t max_len() const {
+            size_t m = 0;
+            for (size_t r = 0; r + 1 < off.size(); ++r) m = std::max<size_t>(m, off[r + 1] - off[r]);
+            return m;
+        }
+        bool rectangular() const {
+            for (size_t r = 1; r + 1 < off.size(); ++r)
+                if (off[r + 1] - off[r] != off[1] - off[0]) return false;
+            return true;
+        }
+    };
+    static Rows to_rows(const py::object& m, const char* what) {
+        Rows rows;
+        auto a = F64Array::ensure(m);   // rectangular input (nested lists or an ndarray): one conversion
+        if (a && a.ndim() == 2) {
+            const size_t nr = a.shape(0), nc = a.shape(1);
+            rows.val.assign(a.data(), a.data() + nr * nc);
+            for (size_t r = 0; r < nr; ++r) rows.off.push_back((r + 1) * nc);
+            return rows;
+        }
+        PyErr_Clear();
+        if (a && a.ndim() == 1 && a.shape(0) == 0) return rows;
+        if (py::isinstance<py::str>(m)) throw py::type_error(std::string(what) + ": can't extract `str` to a list");
+        try {
+            for (auto row : m) {
+                const auto v = row.cast<std::vector<double>>();
+                rows.val.insert(rows.val.end(), v.begin(), v.end());
+                rows.off.push_back(rows.val.size());
+            }
+        } catch (const py::cast_error&) {
+            throw py::type_error(std::string(what) + " must be a sequence of sequences of floats");
+        }
+        return rows;
+    }
+
     std::vector<double> from_dmxs(const py::object& seq_a, const py::object& seq_b, const py::object& dmx_a,
                                   const py::object& dmx_b, const std::optional<std::vector<std::string>>& keys) {
         auto sa = cat_ids(to_strings(seq_a, "seq_a")), sb = cat_ids(to_strings(seq_b, "seq_b"));
-        auto to_matrix = [](const py::object& m, const char* what) {
-            py::array_t<double, py::array::c_style | py::array::forcecast> a;
-            try {
-                a = py::array_t<double, py::array::c_style | py::array::forcecast>::ensure(m);
-            } catch (...) { a = py::array_t<double, py::array::c_style | py::array::forcecast>(); }
-            if (!a || a.ndim() != 2) {
-                if (a && a.ndim() == 1 && a.shape(0) == 0) return a.reshape({(py::ssize_t)0, (py::ssize_t)0}).cast<py::array_t<double, py::array::c_style | py::array::forcecast>>();
-                PyErr_Clear();
-                throw py::value_error(std::string(what) + " must be a rectangular matrix of floats (ragged rows are not supported by the CUDA path)");
-            }
-            return a;
-        };
-        auto ma = to_matrix(dmx_a, "dmx_a"), mb = to_matrix(dmx_b, "dmx_b");
-        const size_t rows_a = ma.shape(0), rows_b = mb.shape(0);
+        const Rows ma = to_rows(dmx_a, "dmx_a"), mb = to_rows(dmx_b, "dmx_b");
+        const size_t rows_a = ma.n(), rows_b = mb.n();
         if (rows_a != rows_b)  // locohd.rs:420-428
             throw py::value_error("Expected matrices with the same length, got lengths " + std::to_string(rows_a) + " and " +
                                   std::to_string(rows_b) + "!");
         const auto wf = resolve_keys(keys, rows_a);
         if (rows_a == 0) return {};
-        const size_t la = ma.shape(1), lb = mb.shape(1);
-        // sort_together indexes seq by the row's indices (utils.rs:33-36): a short seq is an error, a long one is cut
-        if (sa.size() < la || sb.size() < lb)
+        // sort_together indexes seq by the row's indices (utils.rs:33-36): a short seq panics upstream, a long one is cut
+        if (sa.size() < ma.max_len() || sb.size() < mb.max_len())
             throw py::value_error("The category sequences are shorter than the distance matrix rows!");
-        if (la == 0 || lb == 0) throw py::value_error("Empty distance matrix rows!");
+        for (const Rows* m : {&ma, &mb})
+            for (size_t r = 0; r < m->n(); ++r)
+                if (m->off[r + 1] == m->off[r]) throw py::value_error("Empty distance matrix rows!");
         const auto d = ensure_ctx();
+        auto build = [&](locohd_ctx* c, const Rows& m, const std::vector<uint16_t>& cats, locohd_envset** e) {
+            if (m.rectangular()) return locohd_envset_from_rows(c, m.n(), m.off[1], m.val.data(), cats.data(), e);
+            return locohd_envset_from_ragged_rows(c, m.n(), m.off.data(), m.val.data(), cats.data(), cats.size(), e);
+        };
         return score_rows(d, rows_a, wf, [&](locohd_ctx* c, locohd_envset** ea, locohd_envset** eb) {
-            int st = locohd_envset_from_rows(c, rows_a, la, ma.data(), sa.data(), ea);
-            if (!st) st = locohd_envset_from_rows(c, rows_b, lb, mb.data(), sb.data(), eb);
+            int st = build(c, ma, sa, ea);
+            if (!st) st = build(c, mb, sb, eb);
             return st;
         });
     }

@@ -1068,6 +1068,70 @@ int locohd_envset_from_coords(locohd_ctx* ctx, uint64_t n_points, const double* 
     API_END()
 }
 
+int locohd_envset_from_ragged_rows(locohd_ctx* ctx, uint64_t n_rows, const uint64_t* row_offsets, const double* values,
+                                   const uint16_t* category, uint64_t n_categories_given, locohd_envset** out) {
+    API_BEGIN(ctx)
+    TRY_ST(need_params(ctx));
+    if (!out || !row_offsets) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
+    *out = nullptr;
+    std::vector<uint64_t> in_off(n_rows + 1), out_off(n_rows + 1, 0);
+    if (is_device_ptr(ctx, row_offsets)) CU(ctx, cudaMemcpy(in_off.data(), row_offsets, in_off.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    else std::memcpy(in_off.data(), row_offsets, in_off.size() * sizeof(uint64_t));
+    uint64_t max_len = 0;
+    for (uint64_t r = 0; r < n_rows; ++r) {
+        if (in_off[r + 1] < in_off[r]) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "row_offsets must be non-decreasing");
+        const uint64_t len = in_off[r + 1] - in_off[r];
+        if (len == 0) return fail(ctx, LOCOHD_ERR_EMPTY_ENV, "row %llu is empty (the reference panics on dists[0])", (unsigned long long)r);
+        if (len > 0xFFFFFFFFull) return fail(ctx, LOCOHD_ERR_UNSUPPORTED, "rows longer than 2^32");
+        if (len > n_categories_given)   // sort_together indexes the categories by the row's indices (utils.rs:33-36)
+            return fail(ctx, LOCOHD_ERR_LEN_MISMATCH, "row %llu has %llu distances but only %llu categories were given",
+                        (unsigned long long)r, (unsigned long long)len, (unsigned long long)n_categories_given);
+        max_len = std::max(max_len, len);
+        out_off[r + 1] = out_off[r] + ((len + 1) & ~1ull);
+    }
+    const uint64_t total_in = in_off[n_rows];
+    if (total_in && (!values || !category)) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "null argument");
+    InBuf<double> vals;
+    InBuf<uint16_t> cat16;
+    InBuf<uint64_t> d_in, d_out;
+    TRY_ST(vals.load(ctx, values, total_in));
+    TRY_ST(cat16.load(ctx, category, max_len));
+    TRY_ST(d_in.load(ctx, in_off.data(), n_rows + 1));
+    TRY_ST(d_out.load(ctx, out_off.data(), n_rows + 1));
+    uint8_t *d_cat8 = nullptr, *d_cat = nullptr;
+    locohd_envset* e = new locohd_envset();
+    e->ctx = ctx; e->n_env = n_rows; e->total = out_off[n_rows]; e->capacity = e->total + 2;
+    e->max_count = (unsigned)max_len;
+    e->key_is_w = ctx->kp.n_wf == 1;
+    auto bail = [&](int st) { dev_free(ctx, d_cat8); dev_free(ctx, d_cat); destroy_envset(e); return st; };
+    int st;
+    if ((st = dev_alloc(ctx, &d_cat8, max_len)) || (st = dev_alloc(ctx, &e->d_count, n_rows)) ||
+        (st = dev_alloc(ctx, &e->d_off, n_rows + 1)) || (st = dev_alloc(ctx, &e->d_key, e->capacity)) ||
+        (st = dev_alloc(ctx, &d_cat, e->capacity)) || (st = dev_alloc(ctx, &e->d_idx, e->capacity)) ||
+        (st = dev_alloc(ctx, &e->d_dist, e->capacity)))
+        return bail(st);
+    ctx->launches += launch_convert_categories(cat16.ptr, d_cat8, max_len, ctx->kp.C, ctx->stream);
+    EnvBuild b{};
+    b.n_env = n_rows; b.off = e->d_off; b.count = e->d_count; b.key = e->d_key; b.cat = d_cat; b.idx = e->d_idx;
+    b.dist = e->d_dist; b.key_is_w = e->key_is_w ? 1 : 0; b.key_is_sq = 0; b.check_first_zero = 1;
+    {
+        ProfScope ps(ctx, LOCOHD_PROF_OTHER);
+        ctx->launches += launch_ragged_rows_copy(vals.ptr, d_cat8, n_rows, max_len, d_in.ptr, d_out.ptr, e->d_off, e->d_count,
+                                                 b, ctx->stream);
+    }
+    {
+        ProfScope ps(ctx, LOCOHD_PROF_SORT);
+        ctx->launches += launch_env_sort(ctx->kp, b, e->max_count, 0.0, ctx->stream);
+    }
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
+    if ((st = sync_and_check(ctx))) return bail(st);   // also keeps the host offset vectors alive until their copies are done
+    dev_free(ctx, d_cat8); dev_free(ctx, d_cat);
+    *out = e;
+    return 0;
+    API_END()
+}
+
 void locohd_envset_destroy(locohd_envset* e) { destroy_envset(e); }
 uint64_t locohd_envset_size(const locohd_envset* e) { return e ? e->n_env : 0; }
 uint64_t locohd_envset_total_members(const locohd_envset* e) {

@@ -880,7 +880,7 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
             };
             // one round: 32 candidates, one per lane
             // Lanes past the end of the list test the anchor's own record with `valid` false (no branch around the
-            // loads or the arithmetic); a slot beyond CAP is clamped (the environment is rejected after the loop).
+            // loads or the arithmetic); members beyond CAP are not stored (the environment is rejected after the loop).
             auto test = [&](bool valid, uint32_t j, const PrimRec& r, uint32_t rtag) {
                 const double ex = r.x - q.x, ey = r.y - q.y, ez = r.z - q.z;
                 const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
@@ -896,8 +896,8 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DE
                 if (simple_rule) acc = acc && (((rtag == qtag) == accept_same) || j == jpos);
                 else if (acc && j != jpos) acc = tag_rule_accepts(p, qtag, rtag);
                 const unsigned mask = __ballot_sync(kFull, acc);
-                if (acc) {
-                    const uint32_t slot = min(M + __popc(mask & lt_mask), (uint32_t)(CAP - 1));
+                const uint32_t slot = M + __popc(mask & lt_mask);
+                if (acc && slot < (uint32_t)CAP) {   // members beyond CAP are only counted: the environment is redone
                     d2s[slot] = d2;
                     cats[slot] = (uint8_t)r.cat;
                     key32[slot] = ((uint32_t)(d2 * qscale) << K::SB) | slot;
@@ -1239,6 +1239,22 @@ __global__ void rows_copy_kernel(const double* __restrict__ dmx, const uint8_t* 
             b.key[row * row_stride + j] = (uint64_t)__double_as_longlong(d);
             b.cat[row * row_stride + j] = cat[j];
             if (b.idx) b.idx[row * row_stride + j] = (uint32_t)j;
+        }
+    }
+}
+
+// Ragged rows (from_dmxs with rows of different lengths, utils.rs:25-39: row r is co-sorted with the first len_r
+// categories): in_off / out_off are the offsets of the rows in the input and in the store.
+__global__ void ragged_rows_copy_kernel(const double* __restrict__ values, const uint8_t* __restrict__ cat,
+                                        uint64_t n_rows, const uint64_t* __restrict__ in_off,
+                                        const uint64_t* __restrict__ out_off, uint64_t* off, uint32_t* count, EnvBuild b) {
+    for (uint64_t row = blockIdx.y; row < n_rows; row += gridDim.y) {
+        const uint64_t i0 = in_off[row], len = in_off[row + 1] - i0, o0 = out_off[row];
+        if (blockIdx.x == 0 && threadIdx.x == 0) { off[row] = o0; count[row] = (uint32_t)len; }
+        for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < len; j += (uint64_t)gridDim.x * blockDim.x) {
+            b.key[o0 + j] = (uint64_t)__double_as_longlong(values[i0 + j]);
+            b.cat[o0 + j] = cat[j];
+            if (b.idx) b.idx[o0 + j] = (uint32_t)j;
         }
     }
 }
@@ -2227,6 +2243,17 @@ int launch_rows_copy(const double* dmx, const uint8_t* cat, uint64_t n_rows, uin
     dim3 grid((unsigned)((row_len + 255) / 256), (unsigned)(n_rows > 32768 ? 32768 : n_rows));
     if (grid.x > 64) grid.x = 64;
     rows_copy_kernel<<<grid, 256, 0, st>>>(dmx, cat, n_rows, row_len, row_stride, xyz, off, count, b);
+    return 1;
+}
+
+int launch_ragged_rows_copy(const double* values, const uint8_t* cat, uint64_t n_rows, uint64_t max_len,
+                            const uint64_t* in_off, const uint64_t* out_off, uint64_t* off, uint32_t* count,
+                            const EnvBuild& b, cudaStream_t st) {
+    if (!n_rows) return 0;
+    dim3 grid((unsigned)((max_len + 255) / 256), (unsigned)(n_rows > 32768 ? 32768 : n_rows));
+    if (grid.x > 64) grid.x = 64;
+    if (grid.x < 1) grid.x = 1;
+    ragged_rows_copy_kernel<<<grid, 256, 0, st>>>(values, cat, n_rows, in_off, out_off, off, count, b);
     return 1;
 }
 

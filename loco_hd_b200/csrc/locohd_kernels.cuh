@@ -170,6 +170,9 @@ int launch_env_fill(const StructsView& s, const KParams& p, const uint32_t* anch
 int launch_env_sort(const KParams& p, const EnvBuild& b, unsigned max_count, double threshold, cudaStream_t st);
 int launch_rows_copy(const double* dmx, const uint8_t* cat, uint64_t n_rows, uint64_t row_len, const double* xyz,
                      const KParams& p, uint64_t* off, uint32_t* count, const EnvBuild& b, cudaStream_t st);
+int launch_ragged_rows_copy(const double* values, const uint8_t* cat, uint64_t n_rows, uint64_t max_len,
+                            const uint64_t* in_off, const uint64_t* out_off, uint64_t* off, uint32_t* count,
+                            const EnvBuild& b, cudaStream_t st);
 int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsigned max_b, double mean_a, double mean_b,
                  cudaStream_t st);
 int launch_job_means(const double* scores, const uint64_t* job_pair_off, uint64_t n_jobs, double* means,

@@ -366,3 +366,47 @@ def test_device_resident_wf_indices_are_validated(gpu_ctx, oracle_mod):
     # the context stays usable
     again = gpu_ctx.from_primitives(a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, 10.0, wf_idx=good.data_ptr())
     assert np.array_equal(again, ok)
+
+
+def test_ragged_distance_rows(gpu_ctx, oracle_mod):
+    """from_dmxs with rows of different lengths, as the reference's Vec<Vec<f64>> allows: row r is co-sorted with the
+    first len_r categories (utils.rs:25-39).  Expected values: the oracle's from_anchors on every co-sorted row pair."""
+    import loco_hd
+
+    rng = np.random.default_rng(99)
+    types = ["A", "B", "C", "D"]
+    n_rows = 40
+    seq_a, seq_b = rng.choice(types, 70), rng.choice(types, 64)
+    rows_a, rows_b = [], []
+    for r in range(n_rows):
+        la, lb = int(rng.integers(1, 71)), int(rng.integers(1, 65))
+        ra, rb = rng.uniform(0.5, 14.0, la), rng.uniform(0.5, 14.0, lb)
+        za = int(rng.integers(la))
+        ra[za] = 0.0
+        rb[rng.integers(lb)] = 0.0
+        if r % 7 == 0 and la > 2:
+            ra[(za + 1) % la] = np.inf        # banned contacts of compare_ensembles.py:261-263
+        rows_a.append(ra.tolist()); rows_b.append(rb.tolist())
+    wf, sd = ("uniform", [3.0, 10.0]), ("Hellinger", [2.0])
+    lchd = loco_hd.LoCoHD(types, loco_hd.WeightFunction(*wf))
+    got = np.array(lchd.from_dmxs(seq_a, seq_b, rows_a, rows_b))
+    op = set_both(gpu_ctx, oracle_mod, 4, [(wf[0], tuple(wf[1]))], statistical_distance=(sd[0], tuple(sd[1])))
+    cat = {t: i for i, t in enumerate(types)}
+    ca, cb = np.array([cat[t] for t in seq_a]), np.array([cat[t] for t in seq_b])
+    want = []
+    for ra, rb in zip(rows_a, rows_b):
+        oa, ob = np.argsort(ra, kind="stable"), np.argsort(rb, kind="stable")
+        want.append(oracle_mod.from_anchors(op, ca[:len(ra)][oa], cb[:len(rb)][ob], np.array(ra)[oa], np.array(rb)[ob]))
+    assert_scores_close(got, np.array(want))
+    # the C ABI directly
+    ea = gpu_ctx.envset_from_ragged_rows(rows_a, ca)
+    eb = gpu_ctx.envset_from_ragged_rows(rows_b, cb)
+    jobs = np.array([(0, 0, n_rows)], dtype=JOB)
+    assert np.array_equal(gpu_ctx.score_jobs(ea, eb, jobs), got)
+    ea.close(); eb.close()
+    with pytest.raises(ValueError):   # a row longer than the category sequence (the reference panics)
+        lchd.from_dmxs(seq_a[:5], seq_b, rows_a, rows_b)
+    with pytest.raises(ValueError):
+        lchd.from_dmxs(seq_a, seq_b, rows_a + [[]], rows_b + [[0.0]])
+    with pytest.raises(ValueError):   # a row without a zero distance (locohd.rs:74-77)
+        lchd.from_dmxs(seq_a, seq_b, [[1.0, 2.0]] + rows_a[1:], rows_b)
