@@ -68,6 +68,21 @@ def _ensure_built():
 
 from benchdata import synth  # noqa: E402  (no product code: the reference arm must not map the CUDA library)
 
+
+def _load_batch_helpers():
+    """loco_hd_b200/batch.py (pure numpy job dealing) loaded by path: importing the package would map the CUDA library,
+    which the CPU reference arm must not do."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_locohd_batch", ROOT / "loco_hd_b200" / "batch.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod   # dataclasses resolve the module of a class through sys.modules
+    spec.loader.exec_module(mod)
+    return mod.blocked_pairs, mod.contiguous_share
+
+
+blocked_pairs, contiguous_share = _load_batch_helpers()
+
 F_WF = {"uniform": 11, "kumaraswamy": 19, "dagum": 9}  # SURVEY.md §8(d): flops of one integral_range
 
 
@@ -144,11 +159,14 @@ def make_workload(name, rank, world, args):
         base = synth.config5_base()
         clouds = [synth.config5_member(base, i) for i in range(S)]
         groups = [(s, np.arange(base.n)) for s in range(S)]
-        all_jobs = [(i, j) for i in range(S) for j in range(i + 1, S)]
+        # all i < j structure pairs, in 4 x 4 tiles of the upper triangle (8 structures' environments = 61 MB stay in
+        # L2 while 16 structure pairs are scored); every rank takes one contiguous run of that list
+        all_jobs = blocked_pairs(S, int(os.environ.get("LOCOHD_BENCH_BLOCK", "4")))
+        mine = all_jobs[contiguous_share(len(all_jobs), rank, world)]
         return Workload("cfg5", f"BASELINE configs[4]: all-vs-all ensemble of {S} structures (5000 primitives, all_atom, "
-                        f"C=7), uniform [3,10], every primitive an anchor; {len(all_jobs)} structure pairs dealt "
-                        f"round-robin over {world} GPU(s)", 7, ("uniform", (3.0, 10.0)), clouds, groups,
-                        all_jobs[rank::world], scaling="strong", means_only=True)
+                        f"C=7), uniform [3,10], every primitive an anchor; {len(all_jobs)} structure pairs in 4x4 tiles, "
+                        f"one contiguous run per GPU ({world} GPU(s))", 7, ("uniform", (3.0, 10.0)), clouds, groups,
+                        [tuple(q) for q in mine.tolist()], scaling="strong", means_only=True)
     raise SystemExit(f"unknown workload {name}")
 
 

@@ -36,6 +36,29 @@ def all_pairs(n: int) -> np.ndarray:
     return np.stack([i, j], axis=1)
 
 
+def blocked_pairs(n: int, block: int = 4) -> np.ndarray:
+    """The same (i, j), i < j pairs in an order that keeps a working set of 2 * block structures: block x block tiles
+    of the upper triangle, tile rows outermost.  Consecutive jobs then share their structures' environments, which
+    stay in the 126 MB L2 of a B200 (one 5000-primitive structure has ~7.6 MB of environments at 10 A): 3.0 KB of
+    DRAM reads per anchor pair in plain (i, j) order with strided CTAs, ~0.8 KB in this order with block = 4."""
+    out = []
+    for bi in range(0, n, block):
+        for bj in range(bi, n, block):
+            i = np.arange(bi, min(bi + block, n))
+            j = np.arange(bj, min(bj + block, n))
+            ii, jj = np.meshgrid(i, j, indexing="ij")
+            keep = ii < jj
+            if keep.any():
+                out.append(np.stack([ii[keep], jj[keep]], axis=1))
+    return np.concatenate(out) if out else np.zeros((0, 2), dtype=np.int64)
+
+
+def contiguous_share(n_jobs: int, rank: int, world: int) -> slice:
+    """Rank `rank`'s contiguous run of an ordered job list (equal counts within one job): keeps the locality of the
+    order, unlike dealing every world-th job."""
+    return slice(rank * n_jobs // world, (rank + 1) * n_jobs // world)
+
+
 def assemble(per_rank_ids: Sequence[np.ndarray], per_rank_values: Sequence[np.ndarray], n_jobs: int) -> np.ndarray:
     """Per-rank (job ids, values) -> one array indexed by job id."""
     out = np.full(n_jobs, np.nan, dtype=np.float64)
@@ -126,12 +149,22 @@ class ResidentEnsemble:
 def ensemble_all_vs_all(ctx, clouds, anchors, threshold: float, rank: int = 0, world: int = 1,
                         gather: bool = True, allgather=None) -> np.ndarray:
     """All-vs-all mean LoCoHD matrix entries (i < j, order of `all_pairs`) of an ensemble, sharded over `world`
-    ranks: every rank keeps the whole ensemble resident (1000 x 5000 primitives = 145 MB) and scores its share of
-    the structure pairs."""
-    pairs = all_pairs(len(clouds))
+    ranks: every rank keeps the whole ensemble resident (1000 x 5000 primitives = 145 MB) and scores one contiguous
+    run of the structure pairs taken in `blocked_pairs` order (L2-friendly); entries of other ranks are NaN unless
+    gathered."""
+    n = len(clouds)
+    pairs = all_pairs(n)
+    order = blocked_pairs(n)
+    i, j = order[:, 0].astype(np.int64), order[:, 1].astype(np.int64)
+    ids = i * n - i * (i + 1) // 2 + (j - i - 1)          # position of (i, j) in the all_pairs order
+    mine = ids[contiguous_share(len(ids), rank, world)]
     ens = ResidentEnsemble.build(ctx, clouds, anchors, threshold)
     try:
-        sizes = np.full(len(pairs), len(anchors))
-        return run_sharded(sizes, lambda ids: ens.pair_means(pairs[ids]), rank, world, gather, allgather)
+        values = ens.pair_means(pairs[mine]) if len(mine) else np.zeros(0)
     finally:
         ens.close()
+    if not gather or world == 1:
+        return assemble([mine], [values], len(pairs))
+    if allgather is None:
+        raise ValueError("gather=True with world > 1 needs an `allgather` callable")
+    return gather_job_values(mine, values, len(pairs), allgather)

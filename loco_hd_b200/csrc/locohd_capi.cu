@@ -44,6 +44,7 @@ struct locohd_ctx {
     int* d_err = nullptr;
     ScanStats* d_scan = nullptr;   // two slots: [0] anchor order, [1] environment sizes
     FusedStats* d_fstats = nullptr;  // fused gather: store cursor, sample sum, largest environment, overflow word
+    unsigned long long* d_score_cursor = nullptr;   // scoring kernel: next unclaimed pair
     int legacy_gather = 0;         // LOCOHD_LEGACY_GATHER=1: always use the multi-kernel gather (A/B runs)
     int fused_cap_hint = kFusedCap;  // members per environment the fused gather starts with (512 or 1024)
     // Large device buffers (environment stores, scratch) are recycled per context: the stream-ordered pool of the
@@ -583,6 +584,7 @@ int run_score(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, u
     sa.a = a->view(); sa.b = b->view();
     sa.n_pairs = n_pairs; sa.pairs = d_pairs; sa.jobs = d_jobs; sa.job_pair_off = d_job_off; sa.n_jobs = n_jobs;
     sa.uniform_n = uniform_n; sa.wf_idx = d_wf_idx; sa.out = d_out; sa.stage_cap = 0; sa.only_unstaged = 0; sa.table_n = 0;
+    sa.cursor = ctx->d_score_cursor;
     int n;
     if (a->key_is_w != b->key_is_w) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "environment sets were built with different weight-function modes");
     const double mean_a = a->n_env ? (double)a->total / (double)a->n_env : 0.0;
@@ -672,6 +674,7 @@ int locohd_ctx_create(int device, locohd_ctx** out) {
     if ((ce = cudaMemset(ctx->d_err, 0, sizeof(int))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMalloc(&ctx->d_scan, 2 * sizeof(ScanStats))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMalloc(&ctx->d_fstats, sizeof(FusedStats))) != cudaSuccess) return bail(ce);
+    if ((ce = cudaMalloc(&ctx->d_score_cursor, sizeof(unsigned long long))) != cudaSuccess) return bail(ce);
     {
         const char* lg = std::getenv("LOCOHD_LEGACY_GATHER");
         ctx->legacy_gather = (lg && lg[0] && lg[0] != '0') ? 1 : 0;
@@ -698,7 +701,7 @@ void locohd_ctx_destroy(locohd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_cat_w); cudaFree(ctx->d_cat_sw); cudaFree(ctx->d_wfs); cudaFree(ctx->d_tag_pairs);
     cudaFree(ctx->d_sqrt_tbl); cudaFree(ctx->d_rsqrt_tbl); cudaFree(ctx->d_err); cudaFree(ctx->d_scan);
-    cudaFree(ctx->d_fstats);
+    cudaFree(ctx->d_fstats); cudaFree(ctx->d_score_cursor);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

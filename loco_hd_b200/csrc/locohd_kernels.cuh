@@ -97,6 +97,7 @@ constexpr int kFusedWarps = 32;     // largest warps-per-CTA (store sizing)
 constexpr int kFusedCap = 512;      // members per environment (default instantiation)
 constexpr int kFusedCapBig = 1024;  // second instantiation, used when the first reports larger environments
 constexpr int kFusedChunk = 2048;   // store entries a warp reserves with one atomicAdd
+constexpr int kScoreRun = 16;       // consecutive pairs a scoring warp claims with one atomicAdd
 
 struct FusedStats {  // written by env_fused_kernel, read back by the host
     unsigned long long cursor;     // store entries handed out (multiple of kFusedChunk)
@@ -135,6 +136,8 @@ struct ScoreArgs {
     int stage_cap;                 // members (A + B) a warp can stage in shared memory
     int only_unstaged;             // second pass: score only the pairs the fast kernel skipped
     int table_n;                   // sqrt / rsqrt table entries staged by the fast kernel
+    unsigned long long* cursor;    // fast kernel: next unclaimed pair (zeroed before the launch); warps claim runs of
+                                   // kScoreRun consecutive pairs, so all resident warps work at one moving frontier
 };
 
 // ---- launchers (all asynchronous on `st`; each returns the number of kernel launches it made) ----

@@ -102,3 +102,21 @@ def test_bench_ensemble_jobs_are_dealt_without_overlap():
                     for j in wl.jobs)
         assert int(members.sum()) == naive
     assert sorted(seen) == [(i, j) for i in range(7) for j in range(i + 1, 7)]
+
+
+def test_blocked_pairs_and_contiguous_shares():
+    """The L2-friendly job order holds every i < j pair once, tiles touch at most 2 * block structures, and the
+    contiguous per-rank runs partition the list."""
+    for n, block in ((1, 4), (2, 4), (7, 4), (33, 4), (20, 3)):
+        order = batch.blocked_pairs(n, block)
+        assert sorted(map(tuple, order.tolist())) == sorted(map(tuple, batch.all_pairs(n).tolist()))
+        tiles = {}
+        for k, (i, j) in enumerate(order.tolist()):
+            tiles.setdefault((i // block, j // block), []).append(k)
+        for ks in tiles.values():          # a tile's jobs are consecutive in the order
+            assert ks == list(range(ks[0], ks[0] + len(ks)))
+    n_jobs = 101
+    for world in (1, 2, 3, 8):
+        runs = [batch.contiguous_share(n_jobs, r, world) for r in range(world)]
+        assert [x for s in runs for x in range(n_jobs)[s]] == list(range(n_jobs))
+        assert max(s.stop - s.start for s in runs) - min(s.stop - s.start for s in runs) <= 1
