@@ -127,6 +127,9 @@ class LoCoHD:
         """*extension* ``from_primitives`` on arrays: ``[n, 3]`` float64 coordinates, uint16 category ids
         (``category_ids``), uint32 tag ids (``intern_tags``; opaque integers for a rule without a tag list),
         ``[n_pairs, 2]`` anchors."""
+    def to_arrays(self, primitives: Sequence[PrimitiveAtom]) -> Tuple[ndarray, ndarray, ndarray]:
+        """*extension* ``list[PrimitiveAtom]`` -> ``(xyz [n, 3] float64, category ids uint16, tag ids uint32)``: convert a
+        structure once, then use ``from_arrays`` / ``structures``."""
     def intern_tags(self, tags: StringsLike) -> ndarray:
         """*extension* Tag strings -> the uint32 ids of this instance (consistent with a ``WithList`` rule's pairs)."""
     def category_ids(self, primitive_types: StringsLike) -> ndarray:

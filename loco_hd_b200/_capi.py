@@ -7,13 +7,14 @@ Array arguments may be numpy arrays (host) or integers (raw device pointers, e.g
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "liblocohd_b200.so"
+LIB_PATH = Path(os.environ["LOCOHD_LIB"]) if os.environ.get("LOCOHD_LIB") else _PKG / "liblocohd_b200.so"   # LOCOHD_LIB: A/B builds
 
 MAX_WF_PARAMS = 16
 UNKNOWN_CATEGORY = 0xFFFF

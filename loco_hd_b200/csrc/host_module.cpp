@@ -442,6 +442,11 @@ struct LoCoHD {
         return id;
     }
     uint16_t cat_id(const std::string& c) const {
+        if (category_names.size() <= 16) {   // a handful of short names: a linear scan beats hashing the string
+            for (size_t i = 0; i < category_names.size(); ++i)
+                if (category_names[i] == c) return (uint16_t)i;
+            return (uint16_t)LOCOHD_UNKNOWN_CATEGORY;
+        }
         auto it = category_index.find(c);
         return it == category_index.end() ? (uint16_t)LOCOHD_UNKNOWN_CATEGORY : it->second;
     }
@@ -646,27 +651,62 @@ struct LoCoHD {
         std::vector<uint16_t> cat;
         std::vector<uint32_t> tag;
     };
+    static const PrimitiveAtom& as_atom(PyObject* item) {   // subclasses etc.; anything else is a TypeError, as with PyO3
+        try {
+            return py::handle(item).cast<const PrimitiveAtom&>();
+        } catch (const py::cast_error&) {
+            throw py::type_error("'" + std::string(Py_TYPE(item)->tp_name) + "' object cannot be converted to 'PrimitiveAtom'");
+        }
+    }
     Flat flatten(const py::handle& prims, const char* what) {
         if (py::isinstance<py::str>(prims)) throw py::type_error(std::string(what) + ": can't extract `str` to a list");
         Flat f;
         const py::ssize_t hint = py::len_hint(prims);
         if (hint > 0) { f.xyz.reserve(3 * hint); f.cat.reserve(hint); f.tag.reserve(hint); }
         // consecutive primitives usually share their tag (one tag per residue) and often their type: compare with
-        // the previous strings before hashing
-        // (kept BY VALUE: a generator's previous item may already be gone when the next one arrives)
+        // the previous strings before looking anything up.  For lists / tuples the previous item stays alive (the
+        // container holds it), so the comparison goes through pointers; for other iterables the previous strings are
+        // kept BY VALUE (a generator's previous item may already be gone when the next one arrives).
+        const std::string *prev_tag = nullptr, *prev_type = nullptr;
         std::string last_tag, last_type;
-        bool have_last = false;
         uint32_t last_tag_id = 0;
         uint16_t last_cat = 0;
-        for (auto item : prims) {
-            const PrimitiveAtom& p = item.cast<const PrimitiveAtom&>();
+        auto take = [&](const PrimitiveAtom& p, bool stays_alive) {
             f.xyz.push_back(p.coordinates[0]); f.xyz.push_back(p.coordinates[1]); f.xyz.push_back(p.coordinates[2]);
-            if (!have_last || last_type != p.primitive_type) { last_cat = cat_id(p.primitive_type); last_type = p.primitive_type; }
-            if (!have_last || last_tag != p.tag) { last_tag_id = intern_tag(p.tag); last_tag = p.tag; }
-            have_last = true;
+            if (!prev_type || *prev_type != p.primitive_type) {
+                last_cat = cat_id(p.primitive_type);
+                if (stays_alive) prev_type = &p.primitive_type; else { last_type = p.primitive_type; prev_type = &last_type; }
+            }
+            if (!prev_tag || *prev_tag != p.tag) {
+                last_tag_id = intern_tag(p.tag);
+                if (stays_alive) prev_tag = &p.tag; else { last_tag = p.tag; prev_tag = &last_tag; }
+            }
             f.cat.push_back(last_cat);
             f.tag.push_back(last_tag_id);
+        };
+        // Fast path for what callers pass in practice - a list (or tuple) of exact PrimitiveAtom instances: no iterator
+        // protocol, and the C++ object is taken from the instance directly instead of through the generic caster
+        // (the reference clones every atom at this point, locohd.rs:480-481; here the cost is ~25 ns per atom).
+        static PyTypeObject* const atom_type = reinterpret_cast<PyTypeObject*>(py::type::of<PrimitiveAtom>().ptr());
+        auto fast = [&](PyObject* item, bool stays_alive) -> bool {
+            if (Py_TYPE(item) != atom_type) return false;
+            auto* inst = reinterpret_cast<py::detail::instance*>(item);
+            const auto* p = static_cast<const PrimitiveAtom*>(inst->get_value_and_holder().value_ptr());
+            if (!p) return false;
+            take(*p, stays_alive);
+            return true;
+        };
+        PyObject* seq = prims.ptr();
+        if (PyList_CheckExact(seq) || PyTuple_CheckExact(seq)) {
+            const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
+            for (Py_ssize_t k = 0; k < n; ++k) {
+                PyObject* item = PySequence_Fast_GET_ITEM(seq, k);   // borrowed; the GIL is held and nothing below runs Python code
+                if (!fast(item, true)) take(as_atom(item), true);
+            }
+            return f;
         }
+        for (auto item : prims)
+            if (!fast(item.ptr(), false)) take(as_atom(item.ptr()), false);
         return f;
     }
 
@@ -710,8 +750,10 @@ struct LoCoHD {
         if (with_keys) keys = std::move(key_list);
         const auto wf = resolve_keys(keys, n_pairs);
         if (n_pairs == 0) return {};
-        const auto d = ensure_ctx();  // interns the rule's tags first so that their ids are stable
+        // (tag ids come from one table per instance; the rule's pairs are translated through the same table when the
+        //  context is created, so the order of the two steps does not matter)
         const Flat a = flatten(prim_a, "prim_a"), b = flatten(prim_b, "prim_b");
+        const auto d = ensure_ctx();
         for (size_t k = 0; k < n_pairs; ++k)  // prim_seq[anchor_idx] panics upstream (locohd.rs:521)
             if (anchors[2 * k] >= a.cat.size() || anchors[2 * k + 1] >= b.cat.size())
                 throw py::value_error("Anchor index out of range: pair " + std::to_string(k) + " = (" + std::to_string(anchors[2 * k]) +
@@ -739,12 +781,25 @@ struct LoCoHD {
     }
 
     py::array_t<uint32_t> intern_tags(const py::object& tags) {
-        ensure_ctx();   // the rule's own tags get their ids first
         const auto names = to_strings(tags, "tags");
         py::array_t<uint32_t> out(names.size());
         auto* o = out.mutable_data();
         for (size_t i = 0; i < names.size(); ++i) o[i] = intern_tag(names[i]);
         return out;
+    }
+
+    // list[PrimitiveAtom] -> (xyz [n, 3] float64, category ids uint16, tag ids uint32): the arrays from_arrays,
+    // structures and Structures.update_xyz take; converts a structure once instead of on every call
+    py::tuple to_arrays(const py::object& prims) {
+        const Flat f = flatten(prims, "primitives");
+        const size_t n = f.cat.size();
+        py::array_t<double> xyz({(py::ssize_t)n, (py::ssize_t)3});
+        std::copy(f.xyz.begin(), f.xyz.end(), xyz.mutable_data());
+        py::array_t<uint16_t> cat(n);
+        std::copy(f.cat.begin(), f.cat.end(), cat.mutable_data());
+        py::array_t<uint32_t> tag(n);
+        std::copy(f.tag.begin(), f.tag.end(), tag.mutable_data());
+        return py::make_tuple(xyz, cat, tag);
     }
 
     py::array_t<uint16_t> category_ids(const py::object& types) const {
@@ -937,6 +992,8 @@ PYBIND11_MODULE(loco_hd, m) {
              "[n, 3] float64 coordinates, [n_pairs, 2] anchor indices.  Returns a float64 array.")
         .def("intern_tags", &LoCoHD::intern_tags, py::arg("tags"),
              "Tag strings -> the uint32 ids this instance uses for them (the ids of a WithList rule's tag pairs included).")
+        .def("to_arrays", &LoCoHD::to_arrays, py::arg("primitives"),
+             "list[PrimitiveAtom] -> (xyz [n, 3] float64, category ids uint16, tag ids uint32) for from_arrays / structures.")
         .def("category_ids", &LoCoHD::category_ids, py::arg("primitive_types"),
              "Primitive type names -> uint16 category ids (0xFFFF for a name that is not in `categories`).")
         .def("structures", &LoCoHD::structures, py::arg("prim_offsets"), py::arg("xyz"), py::arg("categories"), py::arg("tags"),

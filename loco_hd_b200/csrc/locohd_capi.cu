@@ -584,7 +584,7 @@ int run_score(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, u
     sa.a = a->view(); sa.b = b->view();
     sa.n_pairs = n_pairs; sa.pairs = d_pairs; sa.jobs = d_jobs; sa.job_pair_off = d_job_off; sa.n_jobs = n_jobs;
     sa.uniform_n = uniform_n; sa.wf_idx = d_wf_idx; sa.out = d_out; sa.stage_cap = 0; sa.only_unstaged = 0; sa.table_n = 0;
-    sa.cursor = ctx->d_score_cursor;
+    sa.cursor = ctx->d_score_cursor; sa.run = 1;
     int n;
     if (a->key_is_w != b->key_is_w) return fail(ctx, LOCOHD_ERR_BAD_PARAM, "environment sets were built with different weight-function modes");
     const double mean_a = a->n_env ? (double)a->total / (double)a->n_env : 0.0;

@@ -734,7 +734,7 @@ __device__ __forceinline__ double fused_distance(double d2) {
 }
 
 template <int WFK, bool DEBUG, int CAP, bool LIST>
-__global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? (DEBUG ? 1 : 32 / fused_warps(CAP, DEBUG)) : 16 / fused_warps(CAP, DEBUG)) env_fused_kernel(StructsView s, KParams p, uint64_t n_env,
+__global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? 1 : 16 / fused_warps(CAP, DEBUG)) env_fused_kernel(StructsView s, KParams p, uint64_t n_env,
                                                                      const uint32_t* __restrict__ order,
                                                                      const uint32_t* __restrict__ anchor_struct,
                                                                      const uint32_t* __restrict__ anchor_prim,
@@ -1639,11 +1639,11 @@ __global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK) * 32) sc
         __syncwarp();
         if (run_pos == run_end) {
             unsigned long long got = 0;
-            if (lane == 0) got = atomicAdd(a.cursor, (unsigned long long)kScoreRun);
+            if (lane == 0) got = atomicAdd(a.cursor, (unsigned long long)a.run);
             got = __shfl_sync(kFull, got, 0);
             if (got >= a.n_pairs) break;
             run_pos = got;
-            run_end = min((uint64_t)got + kScoreRun, a.n_pairs);
+            run_end = min((uint64_t)got + a.run, a.n_pairs);
         }
         const uint64_t pair = run_pos++;
         const PairEnvs pe = resolve_pair(a, pair, P.err);
@@ -2295,7 +2295,10 @@ static int launch_score_kernel(K kernel, const ScoreArgs& a, const KParams& p, i
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const unsigned grid = persistent_grid(kernel, warps * 32, smem, a.n_pairs, warps);
     if (a.cursor) cudaMemsetAsync(a.cursor, 0, sizeof(unsigned long long), st);
-    kernel<<<grid, warps * 32, smem, st>>>(a, p, warps, per_warp);
+    ScoreArgs b = a;
+    const uint64_t per_warp_pairs = a.n_pairs / ((uint64_t)grid * warps * 4) ;
+    b.run = (unsigned)(per_warp_pairs < 1 ? 1 : (per_warp_pairs > (uint64_t)kScoreRun ? (uint64_t)kScoreRun : per_warp_pairs));
+    kernel<<<grid, warps * 32, smem, st>>>(b, p, warps, per_warp);
     return 1;
 }
 

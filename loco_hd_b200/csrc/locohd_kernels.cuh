@@ -92,7 +92,10 @@ struct ScanStats {  // written by the scan kernels, read back by the host
 // warps per CTA (one anchor per warp at a time): one CTA per SM for the 512-member instantiation - the warps of a CTA
 // work on consecutive anchors of the cell order and share their candidate rows in L1; measured 24.6 / 23.6 / 22.6 ms
 // at 4 / 8 / 16 warps per CTA with the same 32 warps per SM
-__host__ __device__ constexpr int fused_warps(int cap, bool debug) { return cap == 512 ? (debug ? 16 : 32) : 8; }  // debug: the parity arrays need more shared memory per warp
+#ifndef LOCOHD_FUSED_WARPS
+#define LOCOHD_FUSED_WARPS 32   // build-time knob for register / occupancy experiments (24 warps leave 85 registers per thread)
+#endif
+__host__ __device__ constexpr int fused_warps(int cap, bool debug) { return cap == 512 ? (debug ? 16 : LOCOHD_FUSED_WARPS) : 8; }  // debug: the parity arrays need more shared memory per warp
 constexpr int kFusedWarps = 32;     // largest warps-per-CTA (store sizing)
 constexpr int kFusedCap = 512;      // members per environment (default instantiation)
 constexpr int kFusedCapBig = 1024;  // second instantiation, used when the first reports larger environments
@@ -137,7 +140,9 @@ struct ScoreArgs {
     int only_unstaged;             // second pass: score only the pairs the fast kernel skipped
     int table_n;                   // sqrt / rsqrt table entries staged by the fast kernel
     unsigned long long* cursor;    // fast kernel: next unclaimed pair (zeroed before the launch); warps claim runs of
-                                   // kScoreRun consecutive pairs, so all resident warps work at one moving frontier
+                                   // `run` consecutive pairs, so all resident warps work at one moving frontier
+    unsigned run;                  // pairs per claim: kScoreRun for large launches, fewer when the launch has fewer
+                                   // pairs than 4 runs per resident warp (single structure pairs: latency)
 };
 
 // ---- launchers (all asynchronous on `st`; each returns the number of kernel launches it made) ----

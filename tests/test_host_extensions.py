@@ -53,10 +53,25 @@ def test_stub_matches_the_built_module():
     assert lchd.category_weights == [1., 2.]
 
 
-def test_category_ids_without_a_device():
+def test_id_helpers_without_a_device():
     lchd = loco_hd.LoCoHD(["O", "N", "C"])
     ids = lchd.category_ids(np.array(["C", "O", "zzz", "N"]))
     assert ids.dtype == np.uint16 and ids.tolist() == [2, 0, 0xFFFF, 1]
+    tags = lchd.intern_tags(["A/1-GLY", "A/2-ALA", "A/1-GLY"])
+    assert tags.dtype == np.uint32 and tags[0] == tags[2] != tags[1]
+    # list[PrimitiveAtom] -> arrays (lists, tuples and generators of temporaries alike), consistent with the helpers
+    atoms = [loco_hd.PrimitiveAtom("ONC"[i % 3], f"A/{i // 4}-GLY", [float(i), 0.5, -1.0]) for i in range(50)]
+    atoms[7] = loco_hd.PrimitiveAtom("unknown", "A/1-GLY", [7.0, 0.5, -1.0])
+    for form in (atoms, tuple(atoms), (a for a in atoms), iter(atoms)):
+        xyz, cat, tag = lchd.to_arrays(form)
+        assert xyz.shape == (50, 3) and np.array_equal(xyz[:, 0], np.arange(50.0))
+        assert np.array_equal(cat, lchd.category_ids([a.primitive_type for a in atoms])) and cat[7] == 0xFFFF
+        assert np.array_equal(tag, lchd.intern_tags([a.tag for a in atoms]))
+    gen = (loco_hd.PrimitiveAtom("O", f"t{i // 3}", [float(i), 0., 0.]) for i in range(3000))   # temporaries
+    xyz, cat, tag = lchd.to_arrays(gen)
+    assert np.array_equal(tag - tag[0], np.arange(3000) // 3)
+    with pytest.raises(TypeError):
+        lchd.to_arrays([1, 2, 3])
 
 
 def test_scoring_without_a_device_fails_loudly_from_two_threads():
@@ -70,7 +85,7 @@ def test_scoring_without_a_device_fails_loudly_from_two_threads():
         for _ in range(20):
             for call in (lambda: lchd.from_primitives(atoms, atoms, [(0, 0)], 5.0),
                          lambda: lchd.from_anchors(["A"], ["B"], [0.], [0.]),
-                         lambda: lchd.intern_tags(["x"])):
+                         lambda: lchd.from_coords(["A"], ["B"], [[0., 0., 0.]], [[0., 0., 0.]])):
                 try:
                     call()
                     seen.append("returned")
@@ -86,15 +101,17 @@ def test_scoring_without_a_device_fails_loudly_from_two_threads():
     assert len(seen) == 120 and all(v is True for v in seen)
 
 
-def test_flatten_accepts_generators_of_temporaries():
-    """from_primitives takes any iterable of PrimitiveAtom; atoms created on the fly (and gone again when the next
-    one arrives) must not be referenced afterwards (the tag / type of the previous item is compared by value)."""
+def test_input_errors_come_before_the_device_error():
+    """from_primitives does its Python-side work (anchor parsing, flattening of any iterable of PrimitiveAtom) before
+    it touches the device: bad inputs are reported as such even on a box without a GPU."""
     if loco_hd.loco_hd.device_count() > 0:
         pytest.skip("a CUDA device is present: covered by the gpu tests")
     lchd = loco_hd.LoCoHD(["A", "B"])
     gen = (loco_hd.PrimitiveAtom("AB"[i % 2], f"tag{i // 3}", [float(i), 0., 0.]) for i in range(5000))
     with pytest.raises(RuntimeError):   # the device is missing, but only after the Python-side work
         lchd.from_primitives(gen, [loco_hd.PrimitiveAtom("A", "t", [0., 0., 0.])], [(0, 0)], 5.0)
+    with pytest.raises(TypeError):
+        lchd.from_primitives([object()], [loco_hd.PrimitiveAtom("A", "t", [0., 0., 0.])], [(0, 0)], 5.0)
 
 
 def test_combine_anchor_stats_pools_exactly():
