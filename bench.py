@@ -697,7 +697,7 @@ def run_gpu(args, rank, local_rank, world):
 
         oracle.build()
         op = oracle_params(oracle, wl)
-        ids = sample_jobs(wl, args.ref_pairs)
+        ids = sample_jobs(wl, args.cpu_pairs)   # ~10 s of CPU work on 16 threads
         cores = host_threads()
         oracle_run_jobs(oracle, op, wl, ids[:1], n_threads=cores)
         p, dt, steps, members = oracle_run_jobs(oracle, op, wl, ids, n_threads=cores)
@@ -775,7 +775,8 @@ def main():
     ap.add_argument("--models", type=int, default=500, help="cfg3: models per GPU per step")
     ap.add_argument("--frames", type=int, default=1024, help="cfg4: frames per GPU per step")
     ap.add_argument("--ensemble", type=int, default=1000, help="cfg5: ensemble size (all-vs-all, jobs dealt over GPUs)")
-    ap.add_argument("--ref-pairs", type=int, default=160000, help="anchor pairs per CPU sample")
+    ap.add_argument("--ref-pairs", type=int, default=160000, help="anchor pairs per step of the CPU reference arm")
+    ap.add_argument("--cpu-pairs", type=int, default=1000000, help="anchor pairs of the cpu_baseline sample of the GPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other configurations and the Python-API latencies")
     ap.add_argument("--score-cap", type=int, default=1 << 28,
