@@ -47,6 +47,9 @@ struct locohd_ctx {
     unsigned long long* d_score_cursor = nullptr;   // scoring kernel: next unclaimed pair
     int legacy_gather = 0;         // LOCOHD_LEGACY_GATHER=1: always use the multi-kernel gather (A/B runs)
     int fused_cap_hint = kFusedCap;  // members per environment the fused gather starts with (512 or 1024)
+    uint64_t hist_n_anchors = 0, hist_capacity = 0;   // store size that worked for the last call of this shape (0: none)
+    double hist_threshold = 0.0;
+    int hist_cap = 0;
     // Large device buffers (environment stores, scratch) are recycled per context: the stream-ordered pool of the
     // driver splits and re-merges multi-GB blocks unpredictably, which shows up as 30-60 ms stalls per call.
     std::mutex cache_mu;
@@ -471,9 +474,15 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
         // upper-bound sizes of every 16th anchor.
         const bool sized_by_bound = n_anchors <= 32768;
         const uint32_t stride = 16u;
+    resize:
+        // A call of the same shape as the last one (a benchmark step, the next block of trajectory frames) takes the
+        // store size that worked then and skips the sizing pass and its synchronisation; if the store turns out too
+        // small after all, the history is dropped and the call is sized by a sample like a first call.
+        const bool by_history = !sized_by_bound && ctx->hist_capacity && ctx->hist_n_anchors == n_anchors &&
+                                ctx->hist_threshold == threshold && ctx->hist_cap == ctx->fused_cap_hint;
         cudaMemsetAsync(ctx->d_fstats, 0, sizeof(FusedStats), ctx->stream);
         FusedStats fs{};
-        if (!sized_by_bound) {
+        if (!sized_by_bound && !by_history) {
             {
                 ProfScope ps(ctx, LOCOHD_PROF_COUNT);
                 ctx->launches += launch_env_sample(sv, ctx->kp, n_anchors, d_order, d_anchor_struct, d_anchor_prim,
@@ -499,6 +508,7 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
             // cudaMallocAsync costs 0.5-2 s).
             for (uint64_t step = 1ull << 62; step >= 32; step >>= 1)
                 if (capacity & step) { step >>= 4; capacity = (capacity + step - 1) & ~(step - 1); break; }
+            if (by_history) capacity = ctx->hist_capacity;
             tr.mark("grid + capacity");
             if (tr.on) std::fprintf(stderr, "[locohd trace] cap %d, capacity %llu entries, grid %u, cached blocks %zu\n", cap,
                                     (unsigned long long)capacity, grid, ctx->big_free.size());
@@ -527,6 +537,9 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
             if ((st = sync_and_check(ctx))) return bail(st);
             tr.mark("fused kernel + sync");
             if (!fr.overflow) {
+                // remember the size for the next call of this shape unless it was a tight fit
+                ctx->hist_n_anchors = n_anchors; ctx->hist_threshold = threshold; ctx->hist_cap = cap;
+                ctx->hist_capacity = (!sized_by_bound && (double)fr.cursor <= 0.94 * (double)capacity) ? capacity : 0;
                 if (cap == kFusedCapBig && fr.max_count <= (unsigned)(kFusedCap * 3 / 4)) ctx->fused_cap_hint = kFusedCap;
                 e->capacity = capacity;
                 e->total = fr.cursor < capacity ? fr.cursor : capacity;
@@ -536,6 +549,7 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
                 return 0;
             }
             dev_free(ctx, e->d_key); dev_free(ctx, e->d_idx); dev_free(ctx, e->d_dist);
+            if (by_history) { ctx->hist_capacity = 0; if (fr.overflow == 8u) ctx->fused_cap_hint = kFusedCapBig; goto resize; }
             if (fr.overflow != 8u) break;          // not (only) "more members than cap": the larger kernel will not help
             ctx->fused_cap_hint = kFusedCapBig;     // environments beyond 512 members: go on with the 1024 instantiation
         }

@@ -410,3 +410,32 @@ def test_ragged_distance_rows(gpu_ctx, oracle_mod):
         lchd.from_dmxs(seq_a, seq_b, rows_a + [[]], rows_b + [[0.0]])
     with pytest.raises(ValueError):   # a row without a zero distance (locohd.rs:74-77)
         lchd.from_dmxs(seq_a, seq_b, [[1.0, 2.0]] + rows_a[1:], rows_b)
+
+
+def test_store_sizing_history_recovers_from_a_denser_call(gpu_ctx, oracle_mod):
+    """Calls of the same shape reuse the store size of the previous call (no sizing pass); when the same number of
+    anchors suddenly has much larger environments the store overflows, the history is dropped and the call is redone
+    with a sampled size - the environments must come out complete either way."""
+    rng = np.random.default_rng(31)
+    n = 40000                                     # above the 32 768-anchor bound below which no sizing is needed
+    cat = rng.integers(0, 5, n).astype(np.uint16)
+    tag = np.arange(n, dtype=np.uint32)
+    anchors = np.arange(n, dtype=np.uint32)
+    op = set_both(gpu_ctx, oracle_mod, 5, [("uniform", (3.0, 10.0))], tag_rule={"accept_same": False})
+    sizes = {}
+    for label, extent in (("sparse", 120.0), ("sparse again", 120.0), ("dense", 42.0), ("dense again", 42.0), ("sparse once more", 120.0)):
+        xyz = np.random.default_rng(7 if extent > 100 else 8).uniform(-extent, extent, (n, 3))
+        st = gpu_ctx.structure(xyz, cat, tag)
+        env = gpu_ctx.envset_build(st, anchors, 10.0)
+        off = np.empty(n + 1, np.uint64)
+        from loco_hd_b200 import _capi
+        gpu_ctx._check(gpu_ctx.lib.locohd_envset_dump(gpu_ctx.h, env.h, _capi._p(off), None, None, None))
+        got = np.diff(off).astype(np.int64)
+        env.close(); st.close()
+        for a in (0, 1234, 39999):
+            idx, _, _ = oracle_mod.environment(op, xyz, cat, tag, a, 10.0)
+            assert got[a] == len(idx), (label, a)
+        sizes[label] = got
+    assert np.array_equal(sizes["sparse"], sizes["sparse again"]) and np.array_equal(sizes["sparse"], sizes["sparse once more"])
+    assert np.array_equal(sizes["dense"], sizes["dense again"])
+    assert sizes["dense"].mean() > 10 * sizes["sparse"].mean()
