@@ -168,3 +168,63 @@ def ensemble_all_vs_all(ctx, clouds, anchors, threshold: float, rank: int = 0, w
     if allgather is None:
         raise ValueError("gather=True with world > 1 needs an `allgather` callable")
     return gather_job_values(mine, values, len(pairs), allgather)
+
+
+def trajectory_scores(lchd, topology, categories, tags, frame0_atoms, frame_blocks, anchors, threshold: float,
+                      reduce: Optional[Sequence[str]] = None, max_block: Optional[int] = None):
+    """Frame 0 of a trajectory against every later frame, from ATOM coordinates to scores on the device: what
+    trajectory_analyzer.py:89-129 does per frame with `assign_from_universe` + `from_primitives`, without the per-frame
+    regex pass and without re-uploading frame 0.
+
+    lchd          a loco_hd.LoCoHD instance (public class)
+    topology      PrimitiveAssigner.compile_topology(structure): which atoms feed which primitive
+    categories    uint16 category id of every primitive (lchd.category_ids(topology.primitive_types))
+    tags          uint32 tag id of every primitive (lchd.intern_tags(...), one tag per residue)
+    frame0_atoms  [n_atoms, 3] float32
+    frame_blocks  iterable of [B, n_atoms, 3] float32 blocks of frames (B may vary up to max_block / the first block's B)
+    anchors       primitive indices used as anchors in frame 0 and in every frame (e.g. the "Cent" primitives)
+    reduce        None -> yields one [B, n_anchors] score array per block; or names understood by LoCoHD.score_batch
+                  ("anchor_mean", "anchor_std", "job_mean", "scores") -> yields the dict of that block
+
+    Generator: one result per block, in order."""
+    categories = np.ascontiguousarray(categories, dtype=np.uint16)
+    tags = np.ascontiguousarray(tags, dtype=np.uint32)
+    anchors = np.ascontiguousarray(anchors, dtype=np.uint32)
+    seg = np.ascontiguousarray(topology.segment_start, dtype=np.uint32)
+    idx = np.ascontiguousarray(topology.atom_index, dtype=np.uint32)
+    n_prims = len(categories)
+    if len(seg) != n_prims + 1 or len(tags) != n_prims:
+        raise ValueError("categories / tags must have one entry per primitive of the topology")
+    blocks = iter(frame_blocks)
+    first = next(blocks, None)
+    if first is None:
+        return
+    first = np.ascontiguousarray(first, dtype=np.float32)
+    cap = int(max_block or first.shape[0])
+    offsets = (np.arange(cap + 2, dtype=np.uint64) * n_prims)
+    st = lchd.structures(offsets, np.zeros(((cap + 1) * n_prims, 3), dtype=np.float32), np.tile(categories, cap + 1),
+                         np.tile(tags, cap + 1))
+    env0 = None
+    try:
+        st.update_from_atoms(np.ascontiguousarray(frame0_atoms, dtype=np.float32), seg, idx, first_structure=0)
+        env0 = lchd.environments(st, anchors, threshold)                      # frame 0: built once
+        block = first
+        while block is not None:
+            b = block.shape[0]
+            if b > cap:
+                raise ValueError(f"a block of {b} frames exceeds max_block = {cap}")
+            st.update_from_atoms(block, seg, idx, first_structure=1)
+            env = lchd.environments(st, np.tile(anchors, b), threshold,
+                                    anchor_struct=np.repeat(np.arange(1, b + 1, dtype=np.uint32), len(anchors)))
+            jobs = np.array([(0, f * len(anchors), len(anchors)) for f in range(b)], dtype=np.uint64)
+            try:
+                out = lchd.score_batch(env0, env, jobs, reduce=reduce)
+            finally:
+                env.close()
+            yield out.reshape(b, len(anchors)) if reduce is None else out
+            nxt = next(blocks, None)
+            block = None if nxt is None else np.ascontiguousarray(nxt, dtype=np.float32)
+    finally:
+        if env0 is not None:
+            env0.close()
+        st.close()

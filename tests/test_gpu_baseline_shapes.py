@@ -439,3 +439,53 @@ def test_store_sizing_history_recovers_from_a_denser_call(gpu_ctx, oracle_mod):
     assert np.array_equal(sizes["sparse"], sizes["sparse again"]) and np.array_equal(sizes["sparse"], sizes["sparse once more"])
     assert np.array_equal(sizes["dense"], sizes["dense again"])
     assert sizes["dense"].mean() > 10 * sizes["sparse"].mean()
+
+
+def test_trajectory_helper_from_atoms_to_scores(oracle_mod):
+    """batch.trajectory_scores: frame 0 against blocks of frames, atom coordinates in, scores out (N1 + N3 + N4 on the
+    public class) - equal to the reference API's loop of assign + from_primitives per frame
+    (trajectory_analyzer.py:89-129), bit for bit."""
+    import loco_hd
+    from loco_hd_b200 import batch
+    from loco_hd_b200.atom_converter_utils import TYPING_DIR, PrimitiveAssigner
+    from test_primitive_assigner import SIDE, make_structure
+
+    assigner = PrimitiveAssigner(TYPING_DIR / "coarse_grained_with_centroid.config.json")
+    rng = np.random.default_rng(21)
+    structure = make_structure(9, tuple(rng.choice(sorted(SIDE), 60)))
+    for k, res in enumerate(structure.get_residues()):
+        centre = np.mean([a.coord for a in res._atoms], axis=0)
+        target = np.array([5.0 * (k % 4), 5.0 * ((k // 4) % 4), 5.0 * (k // 16)], dtype=np.float32)
+        for atom in res._atoms:
+            atom.coord = (atom.coord - centre + target).astype(np.float32)
+    topo = assigner.compile_topology(structure)
+    types = assigner.all_primitive_types
+    lchd = loco_hd.LoCoHD(types, loco_hd.WeightFunction("uniform", [3.0, 10.0]), loco_hd.TagPairingRule({"accept_same": False}))
+    cats = lchd.category_ids(topo.primitive_types)
+    tag_names = [f"{s.source_residue[2]}/{s.source_residue[3][1]}-{s.source_residue_name}" for s in topo.sources]
+    tags = lchd.intern_tags(tag_names)
+    atoms0 = np.array([a.coord for r in structure.get_residues() for a in r.get_atoms()], dtype=np.float32)
+    frames = np.stack([atoms0 + rng.normal(0, 0.5, atoms0.shape).astype(np.float32) for _ in range(7)])
+    anchors = np.flatnonzero(np.array(topo.primitive_types) == "Cent").astype(np.uint32)
+    got = np.concatenate(list(batch.trajectory_scores(lchd, topo, cats, tags, atoms0, [frames[:3], frames[3:6], frames[6:]],
+                                                      anchors, 10.0)))
+    assert got.shape == (7, len(anchors))
+
+    def primitive_atoms(atom_xyz):      # the reference's way: move the atoms, run the assigner, build PrimitiveAtoms
+        it = iter(atom_xyz)
+        for res in structure.get_residues():
+            for atom in res._atoms:
+                atom.coord = next(it)
+        return [loco_hd.PrimitiveAtom(t.primitive_type, tag, [float(v) for v in t.coordinates])
+                for t, tag in zip(assigner.assign_primitive_structure(structure), tag_names)]
+
+    pa0 = primitive_atoms(atoms0)
+    pairs = [(int(a), int(a)) for a in anchors]
+    for f in range(7):
+        want = np.array(lchd.from_primitives(pa0, primitive_atoms(frames[f]), pairs, 10.0))
+        assert np.array_equal(got[f], want), f"frame {f}"
+    stats = list(batch.trajectory_scores(lchd, topo, cats, tags, atoms0, [frames], anchors, 10.0,
+                                         reduce=["anchor_mean", "anchor_std"]))
+    assert len(stats) == 1 and np.abs(stats[0]["anchor_std"] - got.std(axis=0)).max() <= 1e-14
+    assert np.abs(stats[0]["anchor_mean"] - got.mean(axis=0)).max() <= 1e-14
+    assert list(batch.trajectory_scores(lchd, topo, cats, tags, atoms0, [], anchors, 10.0)) == []
