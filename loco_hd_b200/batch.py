@@ -141,6 +141,23 @@ class ResidentEnsemble:
             out[lo:lo + chunk] = means
         return out
 
+    def pair_means_and_anchor_stats(self, pairs: np.ndarray, chunk: int = 4096):
+        """Per structure pair the mean score, and per anchor the mean and population standard deviation over all the
+        given structure pairs (`lchd_dmx` entries and `lchd_by_atom` of compare_ensembles.py:293-299), all reduced on
+        the device; chunks of structure pairs are pooled exactly on the host."""
+        means = np.empty(len(pairs), dtype=np.float64)
+        counts, amean, astd = [], [], []
+        for lo in range(0, len(pairs), chunk):
+            jobs = self.job_table(pairs[lo:lo + chunk])
+            res = self.ctx.score_jobs_stats(self.env, self.env, jobs, job_means=True, anchor_means=True, anchor_stds=True)
+            means[lo:lo + chunk] = res["job_means"]
+            counts.append(len(jobs)); amean.append(res["anchor_means"]); astd.append(res["anchor_stds"])
+        if not counts:
+            empty = np.zeros(self.anchors_per_structure)
+            return means, empty, empty
+        mean, std = combine_anchor_stats(counts, amean, astd)
+        return means, mean, std
+
     def close(self):
         self.env.close()
         self.structs.close()

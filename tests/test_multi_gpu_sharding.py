@@ -56,6 +56,17 @@ def test_sharded_ensemble_matches_unsharded_and_oracle(gpu_ctx, oracle_mod):
     parts = [batch.ensemble_all_vs_all(gpu_ctx, clouds, anchors, 10.0, rank=r, world=3, gather=False) for r in range(3)]
     merged = np.where(np.isnan(parts[0]), np.where(np.isnan(parts[1]), parts[2], parts[1]), parts[0])
     assert np.array_equal(merged, whole)
+    # per-atom statistics over all structure pairs, pooled over chunks of pairs (compare_ensembles.py:299)
+    ens = batch.ResidentEnsemble.build(gpu_ctx, clouds, anchors, 10.0)
+    all_p = batch.all_pairs(len(clouds))
+    m1, am1, as1 = ens.pair_means_and_anchor_stats(all_p)
+    m2, am2, as2 = ens.pair_means_and_anchor_stats(all_p, chunk=4)
+    jobs = ens.job_table(all_p)
+    per_anchor = gpu_ctx.score_jobs(ens.env, ens.env, jobs).reshape(len(all_p), len(anchors))
+    ens.close()
+    assert np.array_equal(m1, whole) and np.array_equal(m2, whole)
+    for am, asd in ((am1, as1), (am2, as2)):
+        assert np.abs(am - per_anchor.mean(axis=0)).max() <= 1e-14 and np.abs(asd - per_anchor.std(axis=0)).max() <= 1e-14
     op = oracle_mod.Params(7, [("uniform", [3.0, 10.0])], tag_rule={"accept_same": False})
     pairs = batch.all_pairs(len(clouds))
     an = np.stack([anchors, anchors], axis=1)
