@@ -45,6 +45,13 @@ struct locohd_ctx {
     ScanStats* d_scan = nullptr;   // two slots: [0] anchor order, [1] environment sizes
     FusedStats* d_fstats = nullptr;  // fused gather: store cursor, sample sum, largest environment, overflow word
     unsigned long long* d_score_cursor = nullptr;   // scoring kernel: next unclaimed pair
+    // pinned host mirrors: the error word and the gather statistics come back with asynchronous copies queued before
+    // the stream synchronisation (no separate blocking cudaMemcpy per synchronisation point)
+    int* h_err = nullptr;
+    FusedStats* h_fstats = nullptr;   // two slots: [0] sizing sample, [1] result of the fused gather
+    // pinned staging area of the one-call entry point (small calls: all inputs travel in one copy)
+    unsigned char* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
     int legacy_gather = 0;         // LOCOHD_LEGACY_GATHER=1: always use the multi-kernel gather (A/B runs)
     int fused_cap_hint = kFusedCap;  // members per environment the fused gather starts with (512 or 1024)
     uint64_t hist_n_anchors = 0, hist_capacity = 0;   // store size that worked for the last call of this shape (0: none)
@@ -109,6 +116,7 @@ struct locohd_structs {
     uint32_t* d_cell_fill = nullptr;
     bool cells_valid = false;
     double cell_threshold = 0.0;
+    void* blob = nullptr;            // one-call entry point: all arrays above are views into this single device block
     StructsView view() const {
         StructsView v;
         v.n_structs = n_structs; v.prim_off = d_prim_off; v.xyz = d_xyz; v.cat = d_cat; v.tag = d_tag;
@@ -298,11 +306,11 @@ struct OutBuf {
 };
 
 int sync_and_check(locohd_ctx* ctx) {
+    CU(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    int code = 0;
-    CU(ctx, cudaMemcpy(&code, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    const int code = *ctx->h_err;
     if (code) {
-        CU(ctx, cudaMemset(ctx->d_err, 0, sizeof(int)));
+        CU(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
         return fail(ctx, code, "%s", status_text(code));
     }
     return 0;
@@ -488,9 +496,10 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
                 ctx->launches += launch_env_sample(sv, ctx->kp, n_anchors, d_order, d_anchor_struct, d_anchor_prim,
                                                    threshold, stride, &ctx->d_fstats->sample, ctx->stream);
             }
-            if (cudaMemcpyAsync(&fs, ctx->d_fstats, sizeof fs, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            if (cudaMemcpyAsync(&ctx->h_fstats[0], ctx->d_fstats, sizeof fs, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
                 return bail(fail(ctx, LOCOHD_ERR_CUDA, "copy of the gather statistics failed"));
             if ((st = sync_and_check(ctx))) return bail(st);
+            fs = ctx->h_fstats[0];
             tr.mark("sample + sync");
         }
         // Members per environment the kernel is instantiated for: 512, and 1024 once a call has reported larger
@@ -531,10 +540,10 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
             }
             cudaError_t ce = cudaGetLastError();
             if (ce != cudaSuccess) return bail(fail(ctx, LOCOHD_ERR_CUDA, "launch failed: %s", cudaGetErrorString(ce)));
-            FusedStats fr{};
-            if (cudaMemcpyAsync(&fr, ctx->d_fstats, sizeof fr, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            if (cudaMemcpyAsync(&ctx->h_fstats[1], ctx->d_fstats, sizeof(FusedStats), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
                 return bail(fail(ctx, LOCOHD_ERR_CUDA, "copy of the gather statistics failed"));
             if ((st = sync_and_check(ctx))) return bail(st);
+            const FusedStats fr = ctx->h_fstats[1];
             tr.mark("fused kernel + sync");
             if (!fr.overflow) {
                 // remember the size for the next call of this shape unless it was a tight fit
@@ -689,6 +698,9 @@ int locohd_ctx_create(int device, locohd_ctx** out) {
     if ((ce = cudaMalloc(&ctx->d_scan, 2 * sizeof(ScanStats))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMalloc(&ctx->d_fstats, sizeof(FusedStats))) != cudaSuccess) return bail(ce);
     if ((ce = cudaMalloc(&ctx->d_score_cursor, sizeof(unsigned long long))) != cudaSuccess) return bail(ce);
+    if ((ce = cudaHostAlloc((void**)&ctx->h_err, sizeof(int), cudaHostAllocDefault)) != cudaSuccess) return bail(ce);
+    if ((ce = cudaHostAlloc((void**)&ctx->h_fstats, 2 * sizeof(FusedStats), cudaHostAllocDefault)) != cudaSuccess) return bail(ce);
+    *ctx->h_err = 0;
     {
         const char* lg = std::getenv("LOCOHD_LEGACY_GATHER");
         ctx->legacy_gather = (lg && lg[0] && lg[0] != '0') ? 1 : 0;
@@ -716,6 +728,7 @@ void locohd_ctx_destroy(locohd_ctx* ctx) {
     cudaFree(ctx->d_cat_w); cudaFree(ctx->d_cat_sw); cudaFree(ctx->d_wfs); cudaFree(ctx->d_tag_pairs);
     cudaFree(ctx->d_sqrt_tbl); cudaFree(ctx->d_rsqrt_tbl); cudaFree(ctx->d_err); cudaFree(ctx->d_scan);
     cudaFree(ctx->d_fstats); cudaFree(ctx->d_score_cursor);
+    cudaFreeHost(ctx->h_err); cudaFreeHost(ctx->h_fstats); cudaFreeHost(ctx->h_stage);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -948,6 +961,7 @@ void locohd_structs_destroy(locohd_structs* s) {
     if (!s) return;
     locohd_ctx* ctx = s->ctx;
     DeviceGuard g(ctx->device);
+    if (s->blob) { dev_free_bytes(ctx, s->blob); delete s; return; }
     dev_free(ctx, s->d_prim_off); dev_free(ctx, s->d_xyz); dev_free(ctx, s->d_cat); dev_free(ctx, s->d_tag);
     dev_free(ctx, s->d_meta); dev_free(ctx, s->d_pf); dev_free(ctx, s->d_pd); dev_free(ctx, s->d_porig);
     dev_free(ctx, s->d_sorted_pos);
@@ -1352,6 +1366,96 @@ int locohd_from_primitives(locohd_ctx* ctx, uint64_t n_a, const double* xyz_a, c
         return fail(ctx, LOCOHD_ERR_EMPTY_ENV, "threshold_distance must be positive (got %g): every environment would be empty", threshold);
     TRY_ST(check_wf_indices(ctx, wf_idx, n_pairs));
     const uint64_t n = n_a + n_b;
+    {
+        // Small calls with host inputs (the typical call of the reference API: one structure pair) travel in ONE
+        // pinned staging buffer and one host-to-device copy, and all device arrays of the call are views into one
+        // device block: a dozen pageable copies and allocations of ~10 us each otherwise dominate such a call.
+        const bool host_in = !is_device_ptr(ctx, xyz_a) && !is_device_ptr(ctx, xyz_b) && !is_device_ptr(ctx, cat_a) &&
+                             !is_device_ptr(ctx, cat_b) && !is_device_ptr(ctx, tag_a) && !is_device_ptr(ctx, tag_b) &&
+                             !is_device_ptr(ctx, anchors) && !(wf_idx && is_device_ptr(ctx, wf_idx));
+        auto up = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+        size_t o = 0;
+        const size_t o_prim = o; o = up(o + 3 * sizeof(uint64_t), 32);
+        const size_t o_job = o; o = up(o + sizeof(locohd_job), 32);
+        const size_t o_xyz = o; o = up(o + 3 * n * sizeof(double), 32);
+        const size_t o_tag = o; o = up(o + n * sizeof(uint32_t), 32);
+        const size_t o_as = o; o = up(o + 2 * n_pairs * sizeof(uint32_t), 32);
+        const size_t o_ap = o; o = up(o + 2 * n_pairs * sizeof(uint32_t), 32);
+        const size_t o_cat16 = o; o = up(o + n * sizeof(uint16_t), 32);
+        const size_t o_wf = o; o = up(o + (wf_idx ? n_pairs * sizeof(uint32_t) : 0), 32);
+        const size_t upload_bytes = o;
+        if (host_in && upload_bytes <= (8u << 20)) {
+            // device-only part of the block
+            const size_t o_cat8 = o; o = up(o + n, 32);
+            const size_t o_meta = o; o = up(o + 2 * sizeof(StructMeta), 32);
+            const size_t o_pf = o; o = up(o + n * sizeof(float4), 32);
+            const size_t o_pd = o; o = up(o + n * sizeof(PrimRec), 32);
+            const size_t o_porig = o; o = up(o + n * sizeof(uint32_t), 32);
+            const size_t o_spos = o; o = up(o + n * sizeof(uint32_t), 32);
+            const size_t o_cs = o; o = up(o + cell_entries(n, 2) * sizeof(uint32_t), 32);
+            const size_t o_cf = o; o = up(o + cell_entries(n, 2) * sizeof(uint32_t), 32);
+            const size_t total_bytes = o;
+            if (ctx->h_stage_bytes < upload_bytes) {
+                if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+                ctx->h_stage = nullptr; ctx->h_stage_bytes = 0;
+                const size_t want = std::max<size_t>(upload_bytes * 2, 1u << 20);
+                if (cudaHostAlloc((void**)&ctx->h_stage, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->h_stage = nullptr; }
+                else ctx->h_stage_bytes = want;
+            }
+            if (ctx->h_stage) {
+                unsigned char* h = ctx->h_stage;
+                const uint64_t offs[3] = {0, n_a, n};
+                std::memcpy(h + o_prim, offs, sizeof offs);
+                const locohd_job job{0, n_pairs, n_pairs};
+                std::memcpy(h + o_job, &job, sizeof job);
+                std::memcpy(h + o_xyz, xyz_a, 3 * n_a * sizeof(double));
+                std::memcpy(h + o_xyz + 3 * n_a * sizeof(double), xyz_b, 3 * n_b * sizeof(double));
+                std::memcpy(h + o_tag, tag_a, n_a * sizeof(uint32_t));
+                std::memcpy(h + o_tag + n_a * sizeof(uint32_t), tag_b, n_b * sizeof(uint32_t));
+                std::memcpy(h + o_cat16, cat_a, n_a * sizeof(uint16_t));
+                std::memcpy(h + o_cat16 + n_a * sizeof(uint16_t), cat_b, n_b * sizeof(uint16_t));
+                uint32_t* has = reinterpret_cast<uint32_t*>(h + o_as);
+                uint32_t* hap = reinterpret_cast<uint32_t*>(h + o_ap);
+                for (uint64_t i = 0; i < n_pairs; ++i) {   // environments [0, P) belong to A, [P, 2P) to B
+                    has[i] = 0; hap[i] = anchors[2 * i];
+                    has[n_pairs + i] = 1; hap[n_pairs + i] = anchors[2 * i + 1];
+                }
+                if (wf_idx) std::memcpy(h + o_wf, wf_idx, n_pairs * sizeof(uint32_t));
+                unsigned char* d = nullptr;
+                TRY_ST(dev_alloc(ctx, &d, total_bytes));
+                locohd_structs* s = new locohd_structs();
+                s->ctx = ctx; s->n_structs = 2; s->n_prims = n; s->max_prims = std::max<uint64_t>(n_a, n_b);
+                s->blob = d;
+                s->d_prim_off = reinterpret_cast<uint64_t*>(d + o_prim);
+                s->d_xyz = reinterpret_cast<double*>(d + o_xyz);
+                s->d_tag = reinterpret_cast<uint32_t*>(d + o_tag);
+                s->d_cat = d + o_cat8;
+                s->d_meta = reinterpret_cast<StructMeta*>(d + o_meta);
+                s->d_pf = reinterpret_cast<float4*>(d + o_pf);
+                s->d_pd = reinterpret_cast<PrimRec*>(d + o_pd);
+                s->d_porig = reinterpret_cast<uint32_t*>(d + o_porig);
+                s->d_sorted_pos = reinterpret_cast<uint32_t*>(d + o_spos);
+                s->d_cell_start = reinterpret_cast<uint32_t*>(d + o_cs);
+                s->d_cell_fill = reinterpret_cast<uint32_t*>(d + o_cf);
+                locohd_envset* env = nullptr;
+                auto done = [&](int st) { if (env) destroy_envset(env); locohd_structs_destroy(s); return st; };
+                if (cudaMemcpyAsync(d, h, upload_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+                    return done(fail(ctx, LOCOHD_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError())));
+                ctx->launches += launch_convert_categories(reinterpret_cast<const uint16_t*>(d + o_cat16), s->d_cat, n, ctx->kp.C, ctx->stream);
+                ctx->launches += launch_validate_xyz(s->d_xyz, 3 * n, ctx->d_err, ctx->stream);
+                int st = build_envset(ctx, s, 2 * n_pairs, reinterpret_cast<const uint32_t*>(d + o_as),
+                                      reinterpret_cast<const uint32_t*>(d + o_ap), threshold, 0, &env);
+                if (st) return done(st);
+                OutBuf<double> out;
+                if ((st = out.prepare(ctx, out_scores, n_pairs))) return done(st);
+                st = run_score(ctx, env, env, n_pairs, nullptr, reinterpret_cast<const locohd_job*>(d + o_job), nullptr, 1, n_pairs,
+                               wf_idx ? reinterpret_cast<const uint32_t*>(d + o_wf) : nullptr, out.ptr);
+                if (!st) st = out.commit();
+                const int st2 = sync_and_check(ctx);
+                return done(st ? st : st2);
+            }
+        }
+    }
     // one structure set holding A then B
     locohd_structs* s = new locohd_structs();
     s->ctx = ctx; s->n_structs = 2; s->n_prims = n;

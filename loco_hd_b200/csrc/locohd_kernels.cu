@@ -394,6 +394,20 @@ __global__ void anchor_slot_scatter_kernel(StructsView s, KParams p, uint64_t n_
     }
 }
 
+// Small calls keep the caller's anchor order (no counting sort: five launches less; the locality it buys only
+// matters when thousands of anchors share candidate rows).
+__global__ void anchor_identity_kernel(StructsView s, KParams p, uint64_t n_env, const uint32_t* __restrict__ anchor_struct,
+                                       const uint32_t* __restrict__ anchor_prim, uint32_t* __restrict__ order,
+                                       uint2* __restrict__ order_rec) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_env) return;
+    uint64_t slot = 0;
+    const bool ok = anchor_slot(s, anchor_struct, anchor_prim, e, p.err, &slot);
+    order[e] = (uint32_t)e;
+    const uint32_t sid = anchor_struct ? anchor_struct[e] : 0u;
+    order_rec[e] = ok ? make_uint2(sid, (uint32_t)(slot - s.prim_off[sid])) : make_uint2(0xFFFFFFFFu, 0u);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1a / K1b: one thread per anchor, anchors taken in cell order.
 //   Every lane walks the candidate cells of its own anchor (rows of 2*reach+1 cells are contiguous in the
@@ -2104,6 +2118,10 @@ int launch_anchor_order(const StructsView& s, const KParams& p, uint64_t n_env, 
                         const uint32_t* anchor_prim, uint64_t n_prims, uint32_t* slot_cnt, uint64_t* slot_off,
                         uint64_t* scan_scratch, ScanStats* stats, uint32_t* order, uint2* order_rec, cudaStream_t st) {
     if (!n_env) return 0;
+    if (n_env <= kIdentityOrderMax) {
+        anchor_identity_kernel<<<blocks_for(n_env, 256), 256, 0, st>>>(s, p, n_env, anchor_struct, anchor_prim, order, order_rec);
+        return 1;
+    }
     cudaMemsetAsync(slot_cnt, 0, (n_prims + 1) * sizeof(uint32_t), st);
     anchor_slot_count_kernel<<<blocks_for(n_env, 256), 256, 0, st>>>(s, p, n_env, anchor_struct, anchor_prim, slot_cnt);
     int n = 1 + launch_scan(slot_cnt, n_prims + 1, 0, slot_off, scan_scratch, stats, st);

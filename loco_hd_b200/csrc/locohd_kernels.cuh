@@ -101,6 +101,7 @@ constexpr int kFusedCap = 512;      // members per environment (default instanti
 constexpr int kFusedCapBig = 1024;  // second instantiation, used when the first reports larger environments
 constexpr int kFusedChunk = 2048;   // store entries a warp reserves with one atomicAdd
 constexpr int kScoreRun = 16;       // consecutive pairs a scoring warp claims with one atomicAdd
+constexpr uint64_t kIdentityOrderMax = 2048;   // calls of up to this many anchors keep the caller's anchor order
 
 struct FusedStats {  // written by env_fused_kernel, read back by the host
     unsigned long long cursor;     // store entries handed out (multiple of kFusedChunk)
