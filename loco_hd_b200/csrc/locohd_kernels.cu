@@ -1310,12 +1310,13 @@ constexpr int kScoreMaxWarps = 8;
 // (32 warps fit the register file); the distance-keyed ones (several weight functions) and the ones with table
 // bound checks need up to 72: 28 warps.
 constexpr int kScoreFastMaxWarps = 32;
-__host__ __device__ constexpr int score_fast_max_warps(bool key_is_w, bool check) { return (key_is_w && !check) ? 32 : 28; }
+__host__ __device__ constexpr int score_fast_max_warps(bool key_is_w, bool check, bool weighted = false) { return weighted ? 24 : ((key_is_w && !check) ? 32 : 28); }
 constexpr uint64_t kWMask = ~kCatMask;
 
 // per-lane values and counts of the generic kernel + the warp's mbarrier (16 bytes at the end)
 __host__ __device__ inline int score_state_bytes(int C) { return (((2 * C * 32 * 8 + 2 * C * 32 * 4) + 15) & ~15) + 16; }
 __host__ __device__ inline int fast_state_bytes(int CP) { return CP * 32 * 4 + 16; }   // counts + the warp's mbarrier
+constexpr int kFastWeightBytes = 128;   // 16 category weights behind the tables of the fast kernel
 
 struct PairEnvs {
     bool ok;
@@ -1575,6 +1576,18 @@ __device__ __forceinline__ double sqrt_unit(double v) {
     return fma(s0, r, s0);
 }
 
+// 1 / sqrt(x) for a positive, normal double: MUFU.RSQ64H seed (rsqrt.approx.f64, 2^-22 relative) and two Newton steps
+// (~2e-16 relative).  Straight-line code: the library rsqrt() carries a slow path behind a call, which costs the
+// weighted walk its registers.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-x * y, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+
 // Shared-memory accesses by 32-bit shared-space address (walk loop of the fast kernel: no generic -> shared
 // conversions, immediate offsets).  Tables and staged keys are read-only during the walk: plain asm, free to schedule;
 // the count words are read-modify-written: volatile with a memory clobber.
@@ -1597,8 +1610,13 @@ __device__ __forceinline__ void sts_u32_rmw(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-template <int CP, bool KEY_IS_W, bool CHECK>
-__global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK) * 32) score_fast_kernel(ScoreArgs a, KParams P, int warps_per_block,
+// WEIGHTED: category weights other than 1 (LoCoHD(category_weights=...), pmf.rs:47-63; pisces_random_pairs.py:32-41 runs
+// Hellinger-2 with such weights).  With p_r = w_r a_r / NA, NA = sum_r w_r a_r:
+//     H^2 = 1 - D / sqrt(NA NB),   D = sum_r w_r sqrt(a_r) sqrt(b_r),
+// so the incremental update only gains a factor w_c, and 1 / sqrt(NA) comes from rsqrt() instead of a table indexed by
+// an integer total.  (Weighted counts enter as count * w; upstream adds w repeatedly: <= 1e-13, documented deviation.)
+template <int CP, bool KEY_IS_W, bool CHECK, bool WEIGHTED>
+__global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK, WEIGHTED) * 32) score_fast_kernel(ScoreArgs a, KParams P, int warps_per_block,
                                                                          int per_warp_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1607,16 +1625,18 @@ __global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK) * 32) sc
     double* s_dsq = s_sqrt + table_n;                       // sqrt(k + 1) - sqrt(k)   (exact: Sterbenz)
     double* s_rsqrt = s_dsq + table_n;                      // CHECK: 1 / sqrt(k); else sqrt(k / (k + 1)), the factor
                                                             // that takes 1 / sqrt(k) to 1 / sqrt(k + 1)
+    double* s_w = s_rsqrt + table_n;                        // [16] category weights (WEIGHTED)
     for (int k = threadIdx.x; k < table_n; k += blockDim.x) {
         const double s0 = P.sqrt_tbl[k], s1 = P.sqrt_tbl[k + 1];
         s_sqrt[k] = s0;
         s_dsq[k] = s1 - s0;
         s_rsqrt[k] = CHECK ? P.rsqrt_tbl[k] : sqrt((double)k / (double)(k + 1));
     }
+    if (threadIdx.x < 16) s_w[threadIdx.x] = (WEIGHTED && (int)threadIdx.x < P.C) ? P.cat_w[threadIdx.x] : 1.0;
     __syncthreads();
     if (wib >= warps_per_block) return;
     const int C = P.C;
-    unsigned char* mine = smem_raw + (size_t)3 * table_n * 8 + (size_t)wib * per_warp_bytes;
+    unsigned char* mine = smem_raw + (size_t)3 * table_n * 8 + kFastWeightBytes + (size_t)wib * per_warp_bytes;
     uint32_t* cnt = reinterpret_cast<uint32_t*>(mine);                       // [CP][32]: A count | B count << 16
     uint64_t* mbar = reinterpret_cast<uint64_t*>(mine + CP * 32 * 4);
     uint64_t* stage = reinterpret_cast<uint64_t*>(mine + fast_state_bytes(CP));
@@ -1737,18 +1757,26 @@ __global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK) * 32) sc
         uint32_t totA = 0, totB = 0;
         int mism = 0;
         double D = 0.0, rA = 0.0, rB = 0.0;
+        double NA = 0.0, NB = 0.0;   // WEIGHTED: weighted totals
         // (re)build D, the totals and the mismatch count from the counts
         auto rebuild = [&]() {
-            totA = 0; totB = 0; mism = 0; D = 0.0;
+            totA = 0; totB = 0; mism = 0; D = 0.0; NA = 0.0; NB = 0.0;
 #pragma unroll
             for (int r = 0; r < CP; ++r) {
                 const uint32_t word = cnt[r * 32 + lane];
                 const uint32_t ka = word & 0xffffu, kb = word >> 16;
                 totA += ka; totB += kb;
                 mism += (ka != kb) ? 1 : 0;
-                D = fma(sqrt_of(ka), sqrt_of(kb), D);
+                if (WEIGHTED) {
+                    const double w = s_w[r];
+                    NA = fma(w, (double)ka, NA); NB = fma(w, (double)kb, NB);
+                    D = fma(w * sqrt_of(ka), sqrt_of(kb), D);
+                } else {
+                    D = fma(sqrt_of(ka), sqrt_of(kb), D);
+                }
             }
-            rA = rsqrt_of(totA); rB = rsqrt_of(totB);
+            if (WEIGHTED) { rA = rsqrt_pos(NA); rB = rsqrt_pos(NB); }
+            else { rA = rsqrt_of(totA); rB = rsqrt_of(totB); }
         };
         // difference form from the counts (small H^2 only)
         auto exact_h2 = [&]() -> double {
@@ -1757,7 +1785,7 @@ __global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK) * 32) sc
             for (int r = 0; r < CP; ++r) {
                 const uint32_t word = cnt[r * 32 + lane];
                 const double u = __dmul_rn(sqrt_of(word & 0xffffu), rA) - __dmul_rn(sqrt_of(word >> 16), rB);
-                acc = fma(u, u, acc);
+                acc = WEIGHTED ? fma(s_w[r] * u, u, acc) : fma(u, u, acc);
             }
             return 0.5 * acc;
         };
@@ -1803,9 +1831,20 @@ __global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK) * 32) sc
                 const uint32_t mine_k = takeA ? ka : kb, other_k = takeA ? kb : ka;
                 sts_u32_rmw(ca, word + (takeA ? 1u : 0x10000u));
                 mism += (mine_k == other_k ? 1 : 0) - (mine_k + 1u == other_k ? 1 : 0);
-                D = fma(lds_f64(dsq_base + 8u * mine_k), lds_f64(sq_base + 8u * other_k), D);
                 const uint32_t pk = takeA ? pa : pb;
-                R *= lds_f64(pk + (takeA ? dA : dB));
+                if (WEIGHTED) {
+                    const double wc = s_w[(uint32_t)raw & 0xFFu];
+                    D = fma(wc * lds_f64(dsq_base + 8u * mine_k), lds_f64(sq_base + 8u * other_k), D);
+                    NA += takeA ? wc : 0.0;
+                    NB += takeA ? 0.0 : wc;
+                    const double rnew = rsqrt_pos(takeA ? NA : NB);
+                    rA = takeA ? rnew : rA;
+                    rB = takeA ? rB : rnew;
+                    R = rA * rB;
+                } else {
+                    D = fma(lds_f64(dsq_base + 8u * mine_k), lds_f64(sq_base + 8u * other_k), D);
+                    R *= lds_f64(pk + (takeA ? dA : dB));
+                }
                 const uint64_t nxt = lds_u64(pk + 8u);
                 pa = takeA ? pk + 8u : pa;
                 pb = takeA ? pb : pk + 8u;
@@ -1816,8 +1855,10 @@ __global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK) * 32) sc
                 //  of h2's high word - fewer instructions, 1-2 % slower: the kernel is bound by the shared-memory pipe)
                 h = (mism == 0) ? 0.0 : sqrt_unit(h2);       // identical counts: exactly 0
                 if (mism != 0 && h2 < kSmallH2) {            // rare: difference form from the counts
-                    rA = rsqrt_of((pa + dA - ratio_base) >> 3);
-                    rB = rsqrt_of((pb + dB - ratio_base) >> 3);
+                    if (!WEIGHTED) {
+                        rA = rsqrt_of((pa + dA - ratio_base) >> 3);
+                        rB = rsqrt_of((pb + dB - ratio_base) >> 3);
+                    }
                     h = sqrt(exact_h2());
                 }
             }
@@ -1839,12 +1880,14 @@ __global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK) * 32) sc
             const uint32_t mine_k = takeA ? ka : kb, other_k = takeA ? kb : ka;
             cnt[c * 32 + lane] = word + (takeA ? 1u : 0x10000u);
             mism += (mine_k == other_k ? 1 : 0) - (mine_k + 1u == other_k ? 1 : 0);
-            D = fma(dsq_of(mine_k), sqrt_of(other_k), D);
+            const double wc = WEIGHTED ? s_w[c] : 1.0;
+            D = WEIGHTED ? fma(wc * dsq_of(mine_k), sqrt_of(other_k), D) : fma(dsq_of(mine_k), sqrt_of(other_k), D);
             {   // one table read and one key read per event, whichever side moved (two predicated reads of each
                 // kind cost twice the shared-memory wavefronts: ncu, profiles/r1t)
                 totA += takeA ? 1u : 0u;
                 totB += takeA ? 0u : 1u;
-                const double rnew = rsqrt_of(takeA ? totA : totB);
+                if (WEIGHTED) { NA += takeA ? wc : 0.0; NB += takeA ? 0.0 : wc; }
+                const double rnew = WEIGHTED ? rsqrt_pos(takeA ? NA : NB) : rsqrt_of(takeA ? totA : totB);
                 rA = takeA ? rnew : rA;
                 rB = takeA ? rB : rnew;
                 i += takeA ? 1u : 0u;
@@ -2342,8 +2385,11 @@ static int launch_generic(const ScoreArgs& args, const KParams& p, unsigned stag
 template <int CP, bool KEY_IS_W>
 static int launch_fast(const ScoreArgs& a, const KParams& p, bool check, int warps, int per_warp, int smem,
                        cudaStream_t st) {
-    return check ? launch_score_kernel(score_fast_kernel<CP, KEY_IS_W, true>, a, p, warps, per_warp, smem, st)
-                 : launch_score_kernel(score_fast_kernel<CP, KEY_IS_W, false>, a, p, warps, per_warp, smem, st);
+    if (!p.unit_w)
+        return check ? launch_score_kernel(score_fast_kernel<CP, KEY_IS_W, true, true>, a, p, warps, per_warp, smem, st)
+                     : launch_score_kernel(score_fast_kernel<CP, KEY_IS_W, false, true>, a, p, warps, per_warp, smem, st);
+    return check ? launch_score_kernel(score_fast_kernel<CP, KEY_IS_W, true, false>, a, p, warps, per_warp, smem, st)
+                 : launch_score_kernel(score_fast_kernel<CP, KEY_IS_W, false, false>, a, p, warps, per_warp, smem, st);
 }
 
 int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsigned max_b, double mean_a, double mean_b,
@@ -2351,7 +2397,7 @@ int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsign
     if (!args.n_pairs) return 0;
     const unsigned pad_max = ((max_a + 1) & ~1u) + ((max_b + 1) & ~1u);
     const bool key_is_w = args.a.key_is_w != 0;
-    const bool fast = p.hell2 && p.unit_w && p.C <= 16;
+    const bool fast = p.hell2 && p.C <= 16;   // Hellinger-2 with or without category weights
     if (!fast) return launch_generic(args, p, pad_max, 0, st);
 
     ScoreArgs a = args;
@@ -2374,11 +2420,11 @@ int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsign
     a.table_n = (int)table_n;
     a.stage_cap = (int)stage;
     a.only_unstaged = 0;
-    const int tables = 3 * (int)table_n * 8;
+    const int tables = 3 * (int)table_n * 8 + kFastWeightBytes;
     const int per_warp = fast_state_bytes(CP) + ((int)stage + 4) * 8;   // + the two sentinels and their padding
     const int budget = 220 * 1024;  // one CTA per SM: the tables are staged once, the rest goes to the warps' stages
     int warps = (budget - tables) / per_warp;
-    if (warps > score_fast_max_warps(key_is_w, check)) warps = score_fast_max_warps(key_is_w, check);
+    if (warps > score_fast_max_warps(key_is_w, check, !p.unit_w)) warps = score_fast_max_warps(key_is_w, check, !p.unit_w);
     if (const char* v = std::getenv("LOCOHD_SCORE_WARPS")) { const int w = std::atoi(v); if (w >= 1 && w < warps) warps = w; }   // occupancy sweeps
     if (warps < 1) warps = 1;
     const int smem = tables + per_warp * warps;

@@ -489,3 +489,21 @@ def test_trajectory_helper_from_atoms_to_scores(oracle_mod):
     assert len(stats) == 1 and np.abs(stats[0]["anchor_std"] - got.std(axis=0)).max() <= 1e-14
     assert np.abs(stats[0]["anchor_mean"] - got.mean(axis=0)).max() <= 1e-14
     assert list(batch.trajectory_scores(lchd, topo, cats, tags, atoms0, [], anchors, 10.0)) == []
+
+
+def test_category_weights_on_the_fast_path(gpu_ctx, oracle_mod):
+    """Hellinger-2 with category weights (pisces_random_pairs.py:32-41: 1 / abundance per primitive type) runs in the
+    TMA-staged kernel too (weighted D and totals); config-2 shape, 10 000 anchors, and the identical-structure case."""
+    a, b = synth.config2()
+    w = [1 / 30.61875, 1 / 1.06906, 1 / 19.46292, 1 / 5.2, 1 / 8.9, 1 / 2.7, 1 / 12.4]
+    op = set_both(gpu_ctx, oracle_mod, 7, [("kumaraswamy", (3.0, 10.0, 2.0, 5.0))], category_weights=w,
+                  tag_rule={"accept_same": False})
+    anchors = np.stack([np.arange(a.n, dtype=np.uint32)] * 2, axis=1)
+    got = gpu_ctx.from_primitives(a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, 10.0)
+    ref = oracle_mod.from_primitives(op, a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, 10.0)
+    assert_scores_close(got, ref)
+    unit = set_both(gpu_ctx, oracle_mod, 7, [("kumaraswamy", (3.0, 10.0, 2.0, 5.0))], tag_rule={"accept_same": False})
+    assert np.abs(got - gpu_ctx.from_primitives(a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, 10.0)).max() > 1e-3
+    set_both(gpu_ctx, oracle_mod, 7, [("uniform", (3.0, 10.0))], category_weights=w, tag_rule={"accept_same": False})
+    same = gpu_ctx.from_primitives(a.xyz, a.cat, a.tag, a.xyz, a.cat, a.tag, anchors[:2000], 10.0)
+    assert np.all(same == 0.0)
