@@ -1456,7 +1456,12 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
             cnt[r * 32 + lane] = ex;
         }
 
-        // ---- state: HELL2 keeps sqrt(weighted count), otherwise the weighted count itself
+        // ---- state: HELL2 keeps sqrt(weighted count); the generalised Hellinger distance (exponent e != 2) keeps
+        //      (weighted count)^(1/e), so that one event costs one root instead of 2 C; the other distances keep the
+        //      weighted count itself and scale it by 1 / norm when they are evaluated
+        const bool hell_e = !HELL2 && P.sd_kind == LOCOHD_SD_HELLINGER;
+        const double inv_e = hell_e ? 1.0 / P.sd_p0 : 0.0;
+        auto root_e = [&](double x) -> double { return x > 0.0 ? exp(inv_e * log(x)) : 0.0; };   // x^(1/e), x = w * count
         double normA = 0.0, normB = 0.0;
         uint32_t totA = 0, totB = 0;
         for (int r = 0; r < C; ++r) {
@@ -1468,11 +1473,17 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
                 const double sw = P.cat_sw[r];
                 val[r * 32 + lane] = (ka < (uint32_t)kSqrtTableSize ? __ldg(P.sqrt_tbl + ka) : sqrt((double)ka)) * sw;
                 val[(C + r) * 32 + lane] = (kb < (uint32_t)kSqrtTableSize ? __ldg(P.sqrt_tbl + kb) : sqrt((double)kb)) * sw;
+            } else if (hell_e) {
+                val[r * 32 + lane] = root_e((double)ka * w);
+                val[(C + r) * 32 + lane] = root_e((double)kb * w);
             } else {
                 val[r * 32 + lane] = (double)ka * w;
                 val[(C + r) * 32 + lane] = (double)kb * w;
             }
         }
+        // per-side scale of the values above: norm^(-1/e) for the generalised Hellinger distance, 1 / norm otherwise
+        auto side_scale = [&](double norm) -> double { return hell_e ? exp(-inv_e * log(norm)) : 1.0 / norm; };
+        double iA = HELL2 ? 0.0 : side_scale(normA), iB = HELL2 ? 0.0 : side_scale(normB);
         auto inv_sqrt_norm = [&](double norm, uint32_t tot) -> double {
             if (P.unit_w && tot < (uint32_t)kSqrtTableSize) return __ldg(P.rsqrt_tbl + tot);
             return 1.0 / sqrt(norm);
@@ -1491,10 +1502,19 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
                     acc = fma(u, u, acc);
                 }
                 return sqrt(0.5 * acc);
+            } else if (hell_e) {
+                // (1/2 sum |p_i^(1/e) - q_i^(1/e)|^e)^(1/e) with p_i^(1/e) = (w_i a_i)^(1/e) * normA^(-1/e)
+                // (statistical_distances.rs:4-10); identical compositions give exactly 0 (both sides do the same operations)
+                double dist = 0.0;
+                for (int r = 0; r < C; ++r) {
+                    const double t = fabs(__dmul_rn(val[r * 32 + lane], iA) - __dmul_rn(val[(C + r) * 32 + lane], iB));
+                    if (t > 0.0) dist += exp(P.sd_p0 * log(t));
+                }
+                return dist > 0.0 ? exp(inv_e * log(0.5 * dist)) : 0.0;
             } else {
-                auto p1 = [&](int r) { return val[r * 32 + lane] / normA; };
-                auto p2 = [&](int r) { return val[(C + r) * 32 + lane] / normB; };
-                return sd_run(P.sd_kind, P.sd_p0, P.sd_p1, C, p1, p2);
+                auto va = [&](int r) { return val[r * 32 + lane]; };
+                auto vb = [&](int r) { return val[(C + r) * 32 + lane]; };
+                return sd_scaled(P.sd_kind, P.sd_p0, P.sd_p1, C, va, vb, iA, iB);
             }
         };
 
@@ -1522,17 +1542,19 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
             const double wc = P.cat_w[c];
             if (HELL2) {
                 val[row * 32 + lane] = (k < (uint32_t)kSqrtTableSize ? __ldg(P.sqrt_tbl + k) : sqrt((double)k)) * P.cat_sw[c];
+            } else if (hell_e) {
+                val[row * 32 + lane] = root_e((double)k * wc);
             } else {
                 val[row * 32 + lane] = (double)k * wc;
             }
             if (takeA) {
                 normA += wc; totA += 1;
-                if (HELL2) rA = inv_sqrt_norm(normA, totA);
+                if (HELL2) rA = inv_sqrt_norm(normA, totA); else iA = side_scale(normA);
                 ++i;
                 if (i < i1) ra = kA[i];
             } else {
                 normB += wc; totB += 1;
-                if (HELL2) rB = inv_sqrt_norm(normB, totB);
+                if (HELL2) rB = inv_sqrt_norm(normB, totB); else iB = side_scale(normB);
                 ++j;
                 if (j < j1) rb = kB[j];
             }
