@@ -56,12 +56,16 @@ __global__ void validate_xyz_kernel(const double* __restrict__ xyz, uint64_t n3,
 // ------------------------------------------------------------------------------------------------
 // Exclusive scan of u32 values into u64 offsets (three kernels: tile sums, scan of the sums, apply).
 // ------------------------------------------------------------------------------------------------
+#ifndef LOCOHD_CELL_THREADS
+#define LOCOHD_CELL_THREADS 512
+#endif
 constexpr int kScanThreads = 256;
 constexpr int kScanPer = 8;
 constexpr int kScanTile = kScanThreads * kScanPer;
 
+template <int THREADS = kScanThreads>
 __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* total) {
-    __shared__ unsigned long long wsum[kScanThreads / 32];
+    __shared__ unsigned long long wsum[THREADS / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned long long incl = v;
     for (int o = 1; o < 32; o <<= 1) {
@@ -71,7 +75,7 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
     if (lane == 31) wsum[wid] = incl;
     __syncthreads();
     unsigned long long base = 0, tot = 0;
-    for (int w = 0; w < kScanThreads / 32; ++w) {
+    for (int w = 0; w < THREADS / 32; ++w) {
         if (w < wid) base += wsum[w];
         tot += wsum[w];
     }
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 // K0: cell list.  One CTA (256 threads) per structure; cell edge = half the radius (search +-2 cells), enlarged
 // when the structure would need more than max(2 N, 8) cells.
 // ------------------------------------------------------------------------------------------------
-constexpr int kCellThreads = 256;
+constexpr int kCellThreads = LOCOHD_CELL_THREADS;   // latency-bound passes over one structure: more threads, more loads in flight
 constexpr int kMaxCellsAxis = 1024;
 
 __device__ __forceinline__ int cell_coord(double rel, double inv_cell, int n) {
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
         const int c_lo = min(tid * per, ncell), c_hi = min(c_lo + per, ncell);
         unsigned long long sum = 0;
         for (int c = c_lo; c < c_hi; ++c) sum += cnt[c];
-        unsigned long long run = block_exclusive_scan(sum, nullptr);
+        unsigned long long run = block_exclusive_scan<kCellThreads>(sum, nullptr);
         for (int c = c_lo; c < c_hi; ++c) {
             const uint32_t v = cnt[c];
             cnt[c] = (uint32_t)run;          // from here on: the fill cursor of the cell
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
             const int c = c0 + tid;
             const unsigned long long v = (c < ncell) ? cell_start[c] : 0u;
             unsigned long long tot;
-            const unsigned long long ex = block_exclusive_scan(v, &tot);
+            const unsigned long long ex = block_exclusive_scan<kCellThreads>(v, &tot);
             const unsigned long long carry = sh_carry;
             if (c < ncell) {
                 cell_start[c] = (uint32_t)(carry + ex);
