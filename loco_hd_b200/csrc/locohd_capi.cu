@@ -30,6 +30,7 @@ struct locohd_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    uint64_t tile_launches = 0;
     bool has_params = false;
     KParams kp{};
     int n_categories = 0;
@@ -600,10 +601,44 @@ int build_envset(locohd_ctx* ctx, locohd_structs* s, uint64_t n_anchors, const u
     return 0;
 }
 
+// Groups a list of equally sized jobs into tiles of <= kTileDim x kTileDim jobs that share runs of environments
+// (greedy, in list order: a job joins the open tile while its A run and its B run fit the tile's rows and columns and
+// its cell is free).  batch.py::blocked_pairs lists an all-vs-all ensemble so that this recovers its 4 x 4 blocks.
+std::vector<ScoreTile> group_job_tiles(const std::vector<locohd_job>& jobs, const std::vector<uint64_t>& joff) {
+    std::vector<ScoreTile> tiles;
+    ScoreTile t;
+    int rows = 0, cols = 0;
+    auto open = [&]() {
+        for (int k = 0; k < kTileDim; ++k) { t.a_first[k] = kTileNone; t.b_first[k] = kTileNone; }
+        for (int k = 0; k < kTileDim * kTileDim; ++k) t.out_first[k] = kTileNone;
+        rows = cols = 0;
+    };
+    open();
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        for (;;) {
+            int r = 0, c = 0;
+            while (r < rows && t.a_first[r] != jobs[j].a_first) ++r;
+            while (c < cols && t.b_first[c] != jobs[j].b_first) ++c;
+            if (r < kTileDim && c < kTileDim && t.out_first[r * kTileDim + c] == kTileNone) {
+                if (r == rows) t.a_first[rows++] = jobs[j].a_first;
+                if (c == cols) t.b_first[cols++] = jobs[j].b_first;
+                t.out_first[r * kTileDim + c] = joff[j];
+                break;
+            }
+            tiles.push_back(t);   // does not fit: close the tile, the job opens the next one
+            open();
+        }
+    }
+    if (rows) tiles.push_back(t);
+    return tiles;
+}
+
 int run_score(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_pairs,
               const uint32_t* d_pairs, const locohd_job* d_jobs, const uint64_t* d_job_off, uint64_t n_jobs,
-              uint64_t uniform_n, const uint32_t* d_wf_idx, double* d_out) {
+              uint64_t uniform_n, const uint32_t* d_wf_idx, double* d_out, const ScoreTile* d_tiles = nullptr,
+              uint64_t n_tiles = 0) {
     ScoreArgs sa{};
+    sa.tiles = d_tiles; sa.n_tiles = n_tiles;
     sa.a = a->view(); sa.b = b->view();
     sa.n_pairs = n_pairs; sa.pairs = d_pairs; sa.jobs = d_jobs; sa.job_pair_off = d_job_off; sa.n_jobs = n_jobs;
     sa.uniform_n = uniform_n; sa.wf_idx = d_wf_idx; sa.out = d_out; sa.stage_cap = 0; sa.only_unstaged = 0; sa.table_n = 0;
@@ -616,6 +651,7 @@ int run_score(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, u
       n = launch_score(sa, ctx->kp, a->max_count, b->max_count, mean_a, mean_b, ctx->stream); }
     if (n < 0) return fail(ctx, LOCOHD_ERR_UNSUPPORTED, "shared memory budget exceeded for %d categories", ctx->kp.C);
     ctx->launches += n;
+    if (d_tiles) ctx->tile_launches += n;
     CU(ctx, cudaGetLastError());
     return 0;
 }
@@ -736,6 +772,7 @@ void locohd_ctx_destroy(locohd_ctx* ctx) {
 void* locohd_ctx_stream(locohd_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 uint64_t locohd_ctx_launch_count(const locohd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t locohd_ctx_tile_launches(const locohd_ctx* ctx) { return ctx ? ctx->tile_launches : 0; }
 
 int locohd_ctx_synchronize(locohd_ctx* ctx) {
     API_BEGIN(ctx)
@@ -1304,8 +1341,28 @@ int locohd_score_jobs_stats(locohd_ctx* ctx, const locohd_envset* a, const locoh
         (st = astd.prepare(ctx, out_anchor_stds, n_per_job)))
         return cleanup(st);
     if (anchor_stats && (st = dev_alloc(ctx, &d_stat, 2 * n_per_job))) return cleanup(st);
+    // Jobs that share runs of environments (an all-vs-all ensemble in 4 x 4 blocks) go to the tile kernel, which
+    // stages every environment once per tile instead of once per pair.  It pays when the tiles are mostly full.
+    InBuf<ScoreTile> dtiles;
+    std::vector<ScoreTile> tiles;   // alive until the call's final synchronisation
+    uint64_t n_tiles = 0;
+    if (uniform && n_per_job && n_jobs >= 4 && !wf_idx && a->key_is_w && b->key_is_w &&
+        score_tiles_applicable(ctx->kp, a->max_count, b->max_count, 1)) {
+        tiles = group_job_tiles(hj, joff);
+        // A row of a tile is one warp, four pairs wide; full tiles run 1.43 x the pair kernel's rate (profiles/r6a).
+        // The tile kernel pays when the rows are mostly filled and a team mostly has work for its four warps
+        // (one-against-many lists - trajectory frames against frame 0 - give tiles of a single row: three of four
+        // warps would idle).
+        uint64_t rows = 0;
+        for (const ScoreTile& t : tiles)
+            for (int r = 0; r < kTileDim; ++r) rows += t.a_first[r] != kTileNone ? 1 : 0;
+        if (n_jobs * 10 >= rows * kTileDim * 6 && rows >= 3 * tiles.size()) {
+            n_tiles = tiles.size();
+            if ((st = dtiles.load(ctx, tiles.data(), n_tiles))) return cleanup(st);
+        }
+    }
     st = run_score(ctx, a, b, n_pairs, nullptr, dj.ptr, djoff.ptr, n_jobs, (uniform && hj[0].n) ? hj[0].n : 0,
-                   wf.ptr, d_scores);
+                   wf.ptr, d_scores, n_tiles ? dtiles.ptr : nullptr, n_tiles);
     if (!st && (means.ptr || anchor_stats)) {
         ProfScope ps(ctx, LOCOHD_PROF_OTHER);
         if (means.ptr) ctx->launches += launch_job_means(d_scores, djoff.ptr, n_jobs, means.ptr, ctx->stream);

@@ -1930,6 +1930,278 @@ __global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK, WEIGHTED
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tile kernel: the all-vs-all ensemble (compare_ensembles.py:250-296) and every other job list in which runs of
+// environments meet several partners.  Unit of work = (tile, anchor): the <= 4 environments of env-set A and <= 4 of
+// env-set B that the tile's jobs use at this anchor are staged ONCE (<= 8 bulk copies on one mbarrier) and scored as
+// <= 16 anchor pairs by a team of 4 warps - warp r owns row r, 8 lanes per pair.  Against one pair per warp:
+//   * 0.5 instead of 2 staged environments per pair: a quarter of the L2 -> shared-memory traffic, and 8 teams
+//     (32 warps) still fit one SM although four pairs share a warp (a stage per pair leaves 9 warps, profiles/r5c);
+//   * the straight-line set-up of a pair (merge-path split, prefix scans, D from the counts, reduction: ~1 000 of the
+//     1 860 warp instructions of score_fast_kernel) is issued once for four pairs; prefix scans and the reduction
+//     take 3 shuffle steps instead of 5.
+// The arithmetic per event is that of score_fast_kernel<CP, true, false, false> (same tables, same expanded form, same
+// small-H^2 fallback); a lane's chunk is E / 8 events instead of E / 32 (the host caps E at 1024: <= 128 roundings of
+// R and D per chunk, ~3e-14 relative).  One CTA per SM (tables staged once), teams synchronise on named barriers.
+constexpr int kTileLanes = 8;                          // lanes per anchor pair
+constexpr int kTeamThreads = kTileDim * kTileDim * kTileLanes;   // 128: warp r = row r, lane >> 3 = column
+constexpr int kTileMaxTeams = 8;
+constexpr int kTileCtrlBytes = 128;
+static_assert(kTeamThreads == 128 && kTileLanes * kTileDim == 32, "a warp covers one row of the tile");
+__host__ __device__ inline int tile_team_bytes(int CP, int stage_keys) {
+    return CP * kTeamThreads * 4 + kTileCtrlBytes + stage_keys * 8;
+}
+
+struct TileCtrl {         // written by the team's loader warp between the two team barriers of an iteration
+    uint64_t mbar;
+    uint64_t tile;
+    uint32_t p;           // anchor inside the jobs of the tile
+    uint32_t state;       // 0 = score, 1 = skip (an error was raised), 2 = no units left
+    uint32_t start[2 * kTileDim];   // stage position of rows 0..3, columns 0..3
+    uint32_t M[2 * kTileDim];       // their sizes (0: absent)
+};
+static_assert(sizeof(TileCtrl) <= kTileCtrlBytes, "control block");
+
+__device__ __forceinline__ void team_barrier(int team) {
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(kTeamThreads) : "memory");
+}
+
+template <int CP>
+__global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_kernel(ScoreArgs a, KParams P, int teams,
+                                                                                      int team_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int table_n = a.table_n;
+    double* s_sqrt = reinterpret_cast<double*>(smem_raw);   // sqrt(k)
+    double* s_dsq = s_sqrt + table_n;                       // sqrt(k + 1) - sqrt(k)
+    double* s_ratio = s_dsq + table_n;                      // sqrt(k / (k + 1))
+    for (int k = threadIdx.x; k < table_n; k += blockDim.x) {
+        const double s0 = P.sqrt_tbl[k], s1 = P.sqrt_tbl[k + 1];
+        s_sqrt[k] = s0;
+        s_dsq[k] = s1 - s0;
+        s_ratio[k] = sqrt((double)k / (double)(k + 1));
+    }
+    __syncthreads();
+    const int team = wib >> 2, row = wib & 3;
+    if (team >= teams) return;
+    const int C = P.C;
+    unsigned char* mine = smem_raw + (size_t)3 * table_n * 8 + (size_t)team * team_bytes;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(mine) + row * CP * 32;            // [CP][32] per warp: A | B << 16
+    TileCtrl* ctrl = reinterpret_cast<TileCtrl*>(mine + CP * kTeamThreads * 4);
+    uint64_t* stage = reinterpret_cast<uint64_t*>(mine + CP * kTeamThreads * 4 + kTileCtrlBytes);
+    const bool loader = row == 0;
+    if (loader && lane == 0) { mbar_init(&ctrl->mbar, 1); fence_proxy_async(); }
+    unsigned mbar_parity = 0;
+    const uint32_t sq_base = __shfl_sync(kFull, smem_u32(s_sqrt), lane);
+    const uint32_t dsq_base = __shfl_sync(kFull, smem_u32(s_dsq), lane);
+    const uint32_t ratio_base = __shfl_sync(kFull, smem_u32(s_ratio), lane);
+    const uint32_t cnt_lane = __shfl_sync(kFull, smem_u32(cnt + lane), lane);
+    const int col = lane >> 3, sub = lane & (kTileLanes - 1);
+    const uint64_t n = a.uniform_n, n_units = a.n_tiles * n;
+    const WfDev& wf = P.wfs[0];
+
+    // Loader lanes 0..7 of warp 0 hold the descriptor of the NEXT unit (claimed one iteration ahead, so the dependent
+    // loads tile -> offset / size run under the scoring of the current unit).
+    uint64_t nx_unit = 0, nx_off = 0;
+    uint32_t nx_M = 0;
+    bool nx_present = false;
+    auto fetch = [&]() {
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(a.cursor, 1ull);
+        u = __shfl_sync(kFull, u, 0);
+        nx_unit = u; nx_off = 0; nx_M = 0; nx_present = false;
+        if (u < n_units && lane < 2 * kTileDim) {
+            uint64_t tile, p;
+            if (((n_units | n) >> 32) == 0) { tile = (uint32_t)u / (uint32_t)n; p = (uint32_t)u - (uint32_t)tile * (uint32_t)n; }
+            else { tile = u / n; p = u - tile * n; }
+            const ScoreTile& T = a.tiles[tile];
+            const uint64_t first = lane < kTileDim ? __ldg(T.a_first + lane) : __ldg(T.b_first + (lane - kTileDim));
+            if (first != kTileNone) {
+                const EnvView& v = lane < kTileDim ? a.a : a.b;
+                nx_off = __ldg(v.off + first + p);
+                nx_M = __ldg(v.count + first + p);
+                nx_present = true;
+            }
+        }
+    };
+    if (loader) fetch();
+
+    for (;;) {
+        team_barrier(team);   // every warp of the team is done with the stage of the previous unit
+        if (loader) {
+            const uint64_t u = nx_unit;
+            uint32_t state = 0;
+            if (u >= n_units) state = 2;
+            else {
+                if (__any_sync(kFull, nx_present && nx_M == 0)) { raise(P.err, LOCOHD_ERR_EMPTY_ENV); state = 1; }  // locohd.rs:74 panics upstream
+                // slot of an environment: its members, the sentinel, padded to an even number of keys
+                const uint32_t slot = nx_present ? ((nx_M + 2u) & ~1u) : 0u;
+                uint32_t incl = slot;
+#pragma unroll
+                for (int o = 1; o < 2 * kTileDim; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const uint32_t start = incl - slot;
+                // The even part of an environment comes as one bulk copy (16-byte granules); an odd last member is
+                // copied by hand, so the sentinel behind it is never overwritten by the copy.
+                const uint32_t bytes = (state == 0 && nx_present) ? (nx_M & ~1u) * 8u : 0u;
+                uint32_t total = bytes;
+#pragma unroll
+                for (int o = 1; o < 2 * kTileDim; o <<= 1) total += __shfl_xor_sync(kFull, total, o);
+                if (state == 0) {
+                    const EnvView& v = lane < kTileDim ? a.a : a.b;
+                    if (lane == 0) { fence_proxy_async(); mbar_expect_tx(&ctrl->mbar, total); }
+                    __syncwarp();
+                    if (lane < 2 * kTileDim && nx_present) {
+                        if (bytes) { fence_proxy_async(); bulk_g2s(stage + start, v.key + nx_off, bytes, &ctrl->mbar); }
+                        if (nx_M & 1u) stage[start + nx_M - 1] = __ldg(v.key + nx_off + nx_M - 1);
+                        stage[start + nx_M] = kSentinel;
+                    }
+                }
+                if (lane < 2 * kTileDim) { ctrl->start[lane] = start; ctrl->M[lane] = (state == 0 && nx_present) ? nx_M : 0u; }
+                if (lane == 0) {
+                    uint64_t tile;
+                    if (((n_units | n) >> 32) == 0) tile = (uint32_t)u / (uint32_t)n; else tile = u / n;
+                    ctrl->tile = tile;
+                    ctrl->p = (uint32_t)(u - tile * n);
+                }
+            }
+            if (lane == 0) ctrl->state = state;
+            if (state != 2) fetch();
+        }
+        team_barrier(team);   // descriptor, hand-copied members and sentinels are visible
+        const uint32_t state = ctrl->state;
+        if (state == 2) break;
+        if (state == 1) continue;
+        const uint64_t out_first = __ldg(a.tiles[ctrl->tile].out_first + row * kTileDim + col);
+        const uint32_t Ma = ctrl->M[row], Mb = ctrl->M[kTileDim + col];
+        const uint32_t p = ctrl->p;
+        const bool valid = out_first != kTileNone && Ma != 0 && Mb != 0;
+        const uint64_t* kA = stage + (valid ? ctrl->start[row] : 0u);
+        const uint64_t* kB = stage + (valid ? ctrl->start[kTileDim + col] : 0u);
+        mbar_wait(&ctrl->mbar, mbar_parity);
+        mbar_parity ^= 1u;
+        if (!__any_sync(kFull, valid)) continue;
+
+        const uint64_t keyA0 = kA[0], keyB0 = kB[0];
+        const uint32_t catA0 = (uint32_t)(keyA0 & kCatMask), catB0 = (uint32_t)(keyB0 & kCatMask);
+        const uint64_t key0 = max(keyA0 & kWMask, keyB0 & kWMask);
+        kA += 1; kB += 1;
+        const uint32_t na = valid ? Ma - 1 : 0u, nb = valid ? Mb - 1 : 0u;
+        const uint32_t E = na + nb;
+        const uint32_t Q = (E + kTileLanes - 1) / kTileLanes;
+        const uint32_t diag = min(E, (uint32_t)sub * Q);
+        const uint32_t i = merge_path(kA, kB, na, nb, diag), j = diag - i;
+        uint32_t i1 = __shfl_down_sync(kFull, i, 1), j1 = __shfl_down_sync(kFull, j, 1);
+        if (sub == kTileLanes - 1) { i1 = na; j1 = nb; }
+
+        // per-lane histogram of my chunk (8-bit fields: a chunk has at most 128 events), exclusive prefix over the 8
+        // lanes of the pair, anchors added; D and the mismatch count are built from the prefixes while they are in
+        // registers
+        constexpr int HW = CP / 8;
+        unsigned long long hA[HW], hB[HW];
+#pragma unroll
+        for (int w = 0; w < HW; ++w) { hA[w] = 0; hB[w] = 0; }
+        bool unknown = valid && ((catA0 >= (uint32_t)C) || (catB0 >= (uint32_t)C));
+        for (uint32_t x = i; x < i1; ++x) {
+            const uint32_t c = reinterpret_cast<const uint8_t*>(kA + x)[0];
+            unknown |= c >= (uint32_t)C;
+            const unsigned long long one = 1ull << (8u * (c & 7u));
+#pragma unroll
+            for (int w = 0; w < HW; ++w) hA[w] += (HW == 1 || (int)((c >> 3) & (HW - 1)) == w) ? one : 0ull;
+        }
+        for (uint32_t x = j; x < j1; ++x) {
+            const uint32_t c = reinterpret_cast<const uint8_t*>(kB + x)[0];
+            unknown |= c >= (uint32_t)C;
+            const unsigned long long one = 1ull << (8u * (c & 7u));
+#pragma unroll
+            for (int w = 0; w < HW; ++w) hB[w] += (HW == 1 || (int)((c >> 3) & (HW - 1)) == w) ? one : 0ull;
+        }
+        if (__any_sync(kFull, unknown)) { raise(P.err, LOCOHD_ERR_UNKNOWN_CATEGORY); continue; }  // pmf.rs:38-42
+        int mism = 0;
+        double D = 0.0;
+#pragma unroll
+        for (int r = 0; r < CP; ++r) {
+            const uint32_t v = (uint32_t)((hA[r >> 3] >> (8 * (r & 7))) & 0xFFu) |
+                               ((uint32_t)((hB[r >> 3] >> (8 * (r & 7))) & 0xFFu) << 16);
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < kTileLanes; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(kFull, incl, o);
+                if (sub >= o) incl += u;
+            }
+            uint32_t ex = incl - v;
+            if (r == (int)catA0) ex += 1u;          // anchors (locohd.rs:82-84)
+            if (r == (int)catB0) ex += 0x10000u;
+            cnt[r * 32 + lane] = ex;
+            const uint32_t ka = ex & 0xffffu, kb = ex >> 16;
+            mism += (ka != kb) ? 1 : 0;
+            D = fma(s_sqrt[ka], s_sqrt[kb], D);
+        }
+        const uint32_t totA = i + 1u, totB = j + 1u;   // members of either side before my chunk, anchors included
+        double rA = __ldg(P.rsqrt_tbl + totA), rB = __ldg(P.rsqrt_tbl + totB);
+        auto exact_h2 = [&]() -> double {   // difference form from the counts (small H^2 only)
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < CP; ++r) {
+                const uint32_t word = cnt[r * 32 + lane];
+                const double u = __dmul_rn(s_sqrt[word & 0xffffu], rA) - __dmul_rn(s_sqrt[word >> 16], rB);
+                s = fma(u, u, s);
+            }
+            return 0.5 * s;
+        };
+        uint64_t kprev = key0;
+        if (i > 0) kprev = kA[i - 1] & kWMask;
+        if (j > 0) kprev = max(kprev, kB[j - 1] & kWMask);
+        double wprev = key_value(kprev);
+        double R = __dmul_rn(rA, rB);
+        double h;
+        {
+            const double h2 = fma(-R, D, 1.0);
+            h = (mism == 0) ? 0.0 : (h2 < kSmallH2 ? sqrt(exact_h2()) : sqrt_unit(h2));
+        }
+        double acc = 0.0;
+        const uint32_t nev = (i1 - i) + (j1 - j);
+        uint32_t pa = smem_u32(kA + i), pb = smem_u32(kB + j);
+        const uint32_t dA = ratio_base + 8u * totA - pa, dB = ratio_base + 8u * totB - pb;
+        uint64_t ra = lds_u64(pa), rb = lds_u64(pb);
+        for (uint32_t it = 0; it < nev; ++it) {
+            const bool takeA = ra <= (rb | kCatMask);   // == (ra & kWMask) <= (rb & kWMask)
+            const uint64_t raw = takeA ? ra : rb;
+            const double w = key_value(raw);
+            acc = fma(w - wprev, h, acc);
+            wprev = w;
+            uint32_t ca;   // cnt_lane + category * 128
+            asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(ca) : "r"((uint32_t)raw & 0xFFu), "r"(cnt_lane));
+            const uint32_t word = lds_u32_rmw(ca);
+            const uint32_t ka = word & 0xffffu, kb = word >> 16;
+            const uint32_t mine_k = takeA ? ka : kb, other_k = takeA ? kb : ka;
+            sts_u32_rmw(ca, word + (takeA ? 1u : 0x10000u));
+            mism += (mine_k == other_k ? 1 : 0) - (mine_k + 1u == other_k ? 1 : 0);
+            const uint32_t pk = takeA ? pa : pb;
+            D = fma(lds_f64(dsq_base + 8u * mine_k), lds_f64(sq_base + 8u * other_k), D);
+            R *= lds_f64(pk + (takeA ? dA : dB));
+            const uint64_t nxt = lds_u64(pk + 8u);
+            pa = takeA ? pk + 8u : pa;
+            pb = takeA ? pb : pk + 8u;
+            ra = takeA ? nxt : ra;
+            rb = takeA ? rb : nxt;
+            const double h2 = fma(-R, D, 1.0);
+            h = (mism == 0) ? 0.0 : sqrt_unit(h2);       // identical counts: exactly 0
+            if (mism != 0 && h2 < kSmallH2) {            // rare: difference form from the counts
+                rA = __ldg(P.rsqrt_tbl + ((pa + dA - ratio_base) >> 3));
+                rB = __ldg(P.rsqrt_tbl + ((pb + dB - ratio_base) >> 3));
+                h = sqrt(exact_h2());
+            }
+        }
+        if (sub == kTileLanes - 1) acc = fma(wf.w_inf - wprev, h, acc);   // tail to infinity: the last chunk's state is final
+#pragma unroll
+        for (int o = kTileLanes / 2; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+        if (sub == 0 && valid) a.out[out_first + p] = acc;
+    }
+}
+
 __global__ void job_means_kernel(const double* __restrict__ scores, const uint64_t* __restrict__ job_pair_off,
                                  uint64_t n_jobs, double* __restrict__ means) {
     const int lane = threadIdx.x & 31;
@@ -2418,9 +2690,61 @@ static int launch_fast(const ScoreArgs& a, const KParams& p, bool check, int war
                  : launch_score_kernel(score_fast_kernel<CP, KEY_IS_W, false, false>, a, p, warps, per_warp, smem, st);
 }
 
+// Tile kernel geometry for environments of at most max_a / max_b members: teams per CTA (0: not applicable).
+static int tile_geometry(const KParams& p, unsigned max_a, unsigned max_b, int key_is_w, int* table_n_out,
+                         int* stage_keys_out, int* team_bytes_out) {
+    if (!(p.hell2 && p.unit_w && p.C <= 16 && key_is_w)) return 0;   // the configuration of score_fast_kernel<CP, true, false, false>
+    if (max_a < 1 || max_b < 1 || max_a + max_b > 1024u) return 0;   // chunks of at most 128 events per lane
+    const unsigned need = (max_a > max_b ? max_a : max_b) + 2u;
+    const unsigned table_n = (need + 63u) & ~63u;
+    const int CP = p.C <= 8 ? 8 : 16;
+    const int stage_keys = kTileDim * (int)((max_a + 2u) & ~1u) + kTileDim * (int)((max_b + 2u) & ~1u);
+    const int team_bytes = tile_team_bytes(CP, stage_keys);
+    const int budget = 227 * 1024 - 3 * (int)table_n * 8;
+    int teams = budget / team_bytes;
+    if (teams > kTileMaxTeams) teams = kTileMaxTeams;
+    if (const char* v = std::getenv("LOCOHD_TILE_TEAMS")) { const int t = std::atoi(v); if (t >= 1 && t < teams) teams = t; }   // occupancy sweeps
+    if (table_n_out) *table_n_out = (int)table_n;
+    if (stage_keys_out) *stage_keys_out = stage_keys;
+    if (team_bytes_out) *team_bytes_out = team_bytes;
+    return teams;
+}
+
+bool score_tiles_applicable(const KParams& p, unsigned max_a, unsigned max_b, int key_is_w) {
+    if (const char* v = std::getenv("LOCOHD_NO_TILES")) if (std::atoi(v)) return false;   // A/B switch
+    // below 6 teams (24 warps) one pair per warp with a stage of its own is the better kernel
+    return tile_geometry(p, max_a, max_b, key_is_w, nullptr, nullptr, nullptr) >= 6;
+}
+
+static int launch_tiles(const ScoreArgs& args, const KParams& p, unsigned max_a, unsigned max_b, cudaStream_t st) {
+    ScoreArgs a = args;
+    int table_n = 0, stage_keys = 0, team_bytes = 0;
+    const int teams = tile_geometry(p, max_a, max_b, a.a.key_is_w, &table_n, &stage_keys, &team_bytes);
+    if (teams < 1) return -1;
+    a.table_n = table_n;
+    a.stage_cap = stage_keys;
+    const int smem = 3 * table_n * 8 + teams * team_bytes;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t units = a.n_tiles * a.uniform_n;
+    const uint64_t need = (units + teams - 1) / teams;
+    const unsigned grid = (unsigned)(need < (uint64_t)sms ? need : (uint64_t)sms);   // persistent: teams claim units from the cursor
+    cudaMemsetAsync(a.cursor, 0, sizeof(unsigned long long), st);
+    if (p.C <= 8) {
+        cudaFuncSetAttribute(score_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        score_tile_kernel<8><<<grid, teams * kTeamThreads, smem, st>>>(a, p, teams, team_bytes);
+    } else {
+        cudaFuncSetAttribute(score_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        score_tile_kernel<16><<<grid, teams * kTeamThreads, smem, st>>>(a, p, teams, team_bytes);
+    }
+    return 1;
+}
+
 int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsigned max_b, double mean_a, double mean_b,
                  cudaStream_t st) {
     if (!args.n_pairs) return 0;
+    if (args.tiles) return launch_tiles(args, p, max_a, max_b, st);
     const unsigned pad_max = ((max_a + 1) & ~1u) + ((max_b + 1) & ~1u);
     const bool key_is_w = args.a.key_is_w != 0;
     const bool fast = p.hell2 && p.C <= 16;   // Hellinger-2 with or without category weights

@@ -127,7 +127,21 @@ struct EnvBuild {
     int check_first_zero;     // rows mode: the smallest distance of a row must be 0 (locohd.rs:74-77)
 };
 
+// A tile of jobs that share environment runs: up to kTileDim runs of env-set A (rows) against up to kTileDim runs of
+// env-set B (columns), every job of the tile with the same number of anchors.  An all-vs-all ensemble listed in
+// 4 x 4 blocks (batch.py::blocked_pairs) is exactly a list of such tiles.  score_tile_kernel stages the <= 8
+// environments of (tile, anchor) once and scores the <= 16 anchor pairs they form.
+constexpr int kTileDim = 4;
+constexpr uint64_t kTileNone = ~0ull;
+struct __align__(16) ScoreTile {
+    uint64_t a_first[kTileDim];                 // first environment of row r in env-set A (kTileNone: no such row)
+    uint64_t b_first[kTileDim];                 // first environment of column c in env-set B
+    uint64_t out_first[kTileDim * kTileDim];    // index of the first score of job (r, c) in `out` (kTileNone: no job)
+};
+
 struct ScoreArgs {
+    const ScoreTile* tiles;        // tile mode (score_tile_kernel): jobs grouped by the host, uniform_n anchors each
+    uint64_t n_tiles;
     EnvView a, b;
     uint64_t n_pairs;
     const uint32_t* pairs;         // explicit mode: [n_pairs][2]; nullptr -> job mode
@@ -184,6 +198,8 @@ int launch_ragged_rows_copy(const double* values, const uint8_t* cat, uint64_t n
                             const EnvBuild& b, cudaStream_t st);
 int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsigned max_b, double mean_a, double mean_b,
                  cudaStream_t st);
+// true when a job list grouped into ScoreTiles can be scored by score_tile_kernel for environments of these sizes
+bool score_tiles_applicable(const KParams& p, unsigned max_a, unsigned max_b, int key_is_w);
 int launch_job_means(const double* scores, const uint64_t* job_pair_off, uint64_t n_jobs, double* means,
                      cudaStream_t st);
 int launch_widen_xyz(const float* in, double* out, uint64_t n3, cudaStream_t st);
