@@ -1943,10 +1943,20 @@ __global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK, WEIGHTED
 // The arithmetic per event is that of score_fast_kernel<CP, true, false, false> (same tables, same expanded form, same
 // small-H^2 fallback); a lane's chunk is E / 8 events instead of E / 32 (the host caps E at 1024: <= 128 roundings of
 // R and D per chunk, ~3e-14 relative).  One CTA per SM (tables staged once), teams synchronise on named barriers.
+// ncu (profiles/r6b): 1 214 warp instructions and 375 shared-memory wavefronts per pair (1 949 / 523 for one pair per
+// warp); the shared-memory data pipe is 92 % busy and is the wall - 245 of the 375 wavefronts are the four scattered
+// 8-byte reads of the walk (next key 73, ratio table 70, the two sqrt tables 51 each; a half-warp of 14 active lanes
+// into 16 bank pairs takes ~2.7 wavefronts where 1 is ideal).
+// Measured and dropped on this kernel (profiles/r6c): R = 1 / sqrt(nA nB) by MUFU.RSQ + one Newton step instead of
+// the ratio-table read (-70 wavefronts, +7 instructions per event and a longer dependent chain: 136.6 -> 141.5 ms on
+// the 200-structure ensemble); lanes dealt to the four pairs of a row in proportion to their event counts (12 % fewer
+// walk iterations per warp, but the wavefronts follow the lane-events, not the iterations: 137.6 -> 140.6 ms);
+// 7 / 6 teams per SM run 1.3 % / 4.4 % slower than 8.
 constexpr int kTileLanes = 8;                          // lanes per anchor pair
 constexpr int kTeamThreads = kTileDim * kTileDim * kTileLanes;   // 128: warp r = row r, lane >> 3 = column
 constexpr int kTileMaxTeams = 8;
 constexpr int kTileCtrlBytes = 128;
+constexpr int kTileRun = 8;                            // consecutive units (anchors of one tile) a team claims at once
 static_assert(kTeamThreads == 128 && kTileLanes * kTileDim == 32, "a warp covers one row of the tile");
 __host__ __device__ inline int tile_team_bytes(int CP, int stage_keys) {
     return CP * kTeamThreads * 4 + kTileCtrlBytes + stage_keys * 8;
@@ -2000,16 +2010,26 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
     const uint64_t n = a.uniform_n, n_units = a.n_tiles * n;
     const WfDev& wf = P.wfs[0];
 
-    // Loader lanes 0..7 of warp 0 hold the descriptor of the NEXT unit (claimed one iteration ahead, so the dependent
-    // loads tile -> offset / size run under the scoring of the current unit).
-    uint64_t nx_unit = 0, nx_off = 0;
+    // Loader lanes 0..7 of warp 0 hold the descriptor of the NEXT unit: it is fetched one iteration ahead, right
+    // after the team was released into the current unit, so the loads (tile -> offset, size, an odd last member) run
+    // under the scoring of the current unit.  Units are claimed in runs of kTileRun consecutive anchors with one
+    // atomicAdd: the descriptors of a run share their cache lines, and the teams of all SMs still work at one
+    // moving frontier of the unit list.
+    uint64_t run_pos = 0, run_end = 0;   // loader warp, uniform
+    uint64_t nx_unit = 0, nx_off = 0, nx_last = 0;
     uint32_t nx_M = 0;
     bool nx_present = false;
     auto fetch = [&]() {
-        unsigned long long u = 0;
-        if (lane == 0) u = atomicAdd(a.cursor, 1ull);
-        u = __shfl_sync(kFull, u, 0);
-        nx_unit = u; nx_off = 0; nx_M = 0; nx_present = false;
+        if (run_pos == run_end) {
+            unsigned long long got = 0;
+            if (lane == 0) got = atomicAdd(a.cursor, (unsigned long long)a.run);
+            got = __shfl_sync(kFull, got, 0);
+            run_pos = min((uint64_t)got, n_units);
+            run_end = min((uint64_t)got + a.run, n_units);
+        }
+        const uint64_t u = run_pos;
+        if (run_pos < run_end) ++run_pos;
+        nx_unit = u; nx_off = 0; nx_M = 0; nx_last = 0; nx_present = false;
         if (u < n_units && lane < 2 * kTileDim) {
             uint64_t tile, p;
             if (((n_units | n) >> 32) == 0) { tile = (uint32_t)u / (uint32_t)n; p = (uint32_t)u - (uint32_t)tile * (uint32_t)n; }
@@ -2020,6 +2040,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
                 const EnvView& v = lane < kTileDim ? a.a : a.b;
                 nx_off = __ldg(v.off + first + p);
                 nx_M = __ldg(v.count + first + p);
+                if (nx_M & 1u) nx_last = __ldg(v.key + nx_off + nx_M - 1);
                 nx_present = true;
             }
         }
@@ -2043,8 +2064,9 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
                     if (lane >= o) incl += t;
                 }
                 const uint32_t start = incl - slot;
-                // The even part of an environment comes as one bulk copy (16-byte granules); an odd last member is
-                // copied by hand, so the sentinel behind it is never overwritten by the copy.
+                // The even part of an environment comes as one bulk copy (16-byte granules); an odd last member was
+                // fetched with the descriptor and is stored by hand, so the sentinel behind it is never overwritten
+                // by the copy.
                 const uint32_t bytes = (state == 0 && nx_present) ? (nx_M & ~1u) * 8u : 0u;
                 uint32_t total = bytes;
 #pragma unroll
@@ -2055,7 +2077,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
                     __syncwarp();
                     if (lane < 2 * kTileDim && nx_present) {
                         if (bytes) { fence_proxy_async(); bulk_g2s(stage + start, v.key + nx_off, bytes, &ctrl->mbar); }
-                        if (nx_M & 1u) stage[start + nx_M - 1] = __ldg(v.key + nx_off + nx_M - 1);
+                        if (nx_M & 1u) stage[start + nx_M - 1] = nx_last;
                         stage[start + nx_M] = kSentinel;
                     }
                 }
@@ -2068,11 +2090,11 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
                 }
             }
             if (lane == 0) ctrl->state = state;
-            if (state != 2) fetch();
         }
         team_barrier(team);   // descriptor, hand-copied members and sentinels are visible
         const uint32_t state = ctrl->state;
         if (state == 2) break;
+        if (loader) fetch();
         if (state == 1) continue;
         const uint64_t out_first = __ldg(a.tiles[ctrl->tile].out_first + row * kTileDim + col);
         const uint32_t Ma = ctrl->M[row], Mb = ctrl->M[kTileDim + col];
@@ -2731,13 +2753,13 @@ static int launch_tiles(const ScoreArgs& args, const KParams& p, unsigned max_a,
     const uint64_t need = (units + teams - 1) / teams;
     const unsigned grid = (unsigned)(need < (uint64_t)sms ? need : (uint64_t)sms);   // persistent: teams claim units from the cursor
     cudaMemsetAsync(a.cursor, 0, sizeof(unsigned long long), st);
-    if (p.C <= 8) {
-        cudaFuncSetAttribute(score_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        score_tile_kernel<8><<<grid, teams * kTeamThreads, smem, st>>>(a, p, teams, team_bytes);
-    } else {
-        cudaFuncSetAttribute(score_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        score_tile_kernel<16><<<grid, teams * kTeamThreads, smem, st>>>(a, p, teams, team_bytes);
-    }
+    const uint64_t per_team = units / ((uint64_t)grid * teams * 4);   // short launches: shorter runs even out the tail
+    a.run = (unsigned)(per_team < 1 ? 1 : (per_team > (uint64_t)kTileRun ? (uint64_t)kTileRun : per_team));
+    auto go = [&](auto kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        kernel<<<grid, teams * kTeamThreads, smem, st>>>(a, p, teams, team_bytes);
+    };
+    if (p.C <= 8) go(score_tile_kernel<8>); else go(score_tile_kernel<16>);
     return 1;
 }
 
