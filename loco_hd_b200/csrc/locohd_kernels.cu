@@ -1956,6 +1956,7 @@ constexpr int kTileLanes = 8;                          // lanes per anchor pair
 constexpr int kTeamThreads = kTileDim * kTileDim * kTileLanes;   // 128: warp r = row r, lane >> 3 = column
 constexpr int kTileMaxTeams = 8;
 constexpr int kTileCtrlBytes = 128;
+constexpr int kTileRepMax = 64;                        // at most this many table entries are replicated per bank pair
 constexpr int kTileRun = 8;                            // consecutive units (anchors of one tile) a team claims at once
 static_assert(kTeamThreads == 128 && kTileLanes * kTileDim == 32, "a warp covers one row of the tile");
 __host__ __device__ inline int tile_team_bytes(int CP, int stage_keys) {
@@ -1976,26 +1977,34 @@ __device__ __forceinline__ void team_barrier(int team) {
     asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(kTeamThreads) : "memory");
 }
 
-template <int CP>
+template <int CP, bool REP>
 __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_kernel(ScoreArgs a, KParams P, int teams,
                                                                                       int team_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int table_n = a.table_n;
-    double* s_sqrt = reinterpret_cast<double*>(smem_raw);   // sqrt(k)
-    double* s_dsq = s_sqrt + table_n;                       // sqrt(k + 1) - sqrt(k)
-    double* s_ratio = s_dsq + table_n;                      // sqrt(k / (k + 1))
-    for (int k = threadIdx.x; k < table_n; k += blockDim.x) {
-        const double s0 = P.sqrt_tbl[k], s1 = P.sqrt_tbl[k + 1];
-        s_sqrt[k] = s0;
-        s_dsq[k] = s1 - s0;
-        s_ratio[k] = sqrt((double)k / (double)(k + 1));
+    // Tables.  The two count-indexed ones (sqrt(k), sqrt(k + 1) - sqrt(k)) are "mixed" when REP: entries k < rep_n
+    // exist once per bank pair (entry k of copy c at word 16 k + c; lane l reads copy l & 15, so these reads are
+    // conflict-free whatever the counts of the 32 lanes are: 2 wavefronts per warp read instead of 3.8), the entries
+    // from rep_n on follow unreplicated.  Word index of entry k for copy c: k + min(15 k + c, 15 rep_n) - one IMAD,
+    // one min and one add, no branch.  The host picks rep_n from the shared memory the teams leave over.
+    const int rep_n = REP ? a.rep_n : 0;
+    const int mix_n = 15 * rep_n + table_n;
+    double* s_ratio = reinterpret_cast<double*>(smem_raw);   // sqrt(k / (k + 1)), indexed by a side's total
+    double* s_sqrt = s_ratio + table_n;                      // sqrt(k)
+    double* s_dsq = s_sqrt + mix_n;                          // sqrt(k + 1) - sqrt(k)   (exact: Sterbenz)
+    for (int x = threadIdx.x; x < table_n; x += blockDim.x) s_ratio[x] = sqrt((double)x / (double)(x + 1));
+    for (int x = threadIdx.x; x < mix_n; x += blockDim.x) {
+        const int e = x < 16 * rep_n ? x >> 4 : x - 15 * rep_n;
+        const double s0 = P.sqrt_tbl[e], s1 = P.sqrt_tbl[e + 1];
+        s_sqrt[x] = s0;
+        s_dsq[x] = s1 - s0;
     }
     __syncthreads();
     const int team = wib >> 2, row = wib & 3;
     if (team >= teams) return;
     const int C = P.C;
-    unsigned char* mine = smem_raw + (size_t)3 * table_n * 8 + (size_t)team * team_bytes;
+    unsigned char* mine = smem_raw + (size_t)(table_n + 2 * mix_n) * 8 + (size_t)team * team_bytes;
     uint32_t* cnt = reinterpret_cast<uint32_t*>(mine) + row * CP * 32;            // [CP][32] per warp: A | B << 16
     TileCtrl* ctrl = reinterpret_cast<TileCtrl*>(mine + CP * kTeamThreads * 4);
     uint64_t* stage = reinterpret_cast<uint64_t*>(mine + CP * kTeamThreads * 4 + kTileCtrlBytes);
@@ -2006,6 +2015,10 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
     const uint32_t dsq_base = __shfl_sync(kFull, smem_u32(s_dsq), lane);
     const uint32_t ratio_base = __shfl_sync(kFull, smem_u32(s_ratio), lane);
     const uint32_t cnt_lane = __shfl_sync(kFull, smem_u32(cnt + lane), lane);
+    const uint32_t copy8 = 8u * (lane & 15), cap8 = 120u * (uint32_t)rep_n;
+    auto tbl_off = [&](uint32_t e) -> uint32_t {   // byte offset of entry e in a count-indexed table
+        return REP ? 8u * e + min(120u * e + copy8, cap8) : 8u * e;
+    };
     const int col = lane >> 3, sub = lane & (kTileLanes - 1);
     const uint64_t n = a.uniform_n, n_units = a.n_tiles * n;
     const WfDev& wf = P.wfs[0];
@@ -2159,7 +2172,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
             cnt[r * 32 + lane] = ex;
             const uint32_t ka = ex & 0xffffu, kb = ex >> 16;
             mism += (ka != kb) ? 1 : 0;
-            D = fma(s_sqrt[ka], s_sqrt[kb], D);
+            D = fma(lds_f64(sq_base + tbl_off(ka)), lds_f64(sq_base + tbl_off(kb)), D);
         }
         const uint32_t totA = i + 1u, totB = j + 1u;   // members of either side before my chunk, anchors included
         double rA = __ldg(P.rsqrt_tbl + totA), rB = __ldg(P.rsqrt_tbl + totB);
@@ -2168,7 +2181,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
 #pragma unroll
             for (int r = 0; r < CP; ++r) {
                 const uint32_t word = cnt[r * 32 + lane];
-                const double u = __dmul_rn(s_sqrt[word & 0xffffu], rA) - __dmul_rn(s_sqrt[word >> 16], rB);
+                const double u = __dmul_rn(lds_f64(sq_base + tbl_off(word & 0xffffu)), rA) - __dmul_rn(lds_f64(sq_base + tbl_off(word >> 16)), rB);
                 s = fma(u, u, s);
             }
             return 0.5 * s;
@@ -2202,7 +2215,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
             sts_u32_rmw(ca, word + (takeA ? 1u : 0x10000u));
             mism += (mine_k == other_k ? 1 : 0) - (mine_k + 1u == other_k ? 1 : 0);
             const uint32_t pk = takeA ? pa : pb;
-            D = fma(lds_f64(dsq_base + 8u * mine_k), lds_f64(sq_base + 8u * other_k), D);
+            D = fma(lds_f64(dsq_base + tbl_off(mine_k)), lds_f64(sq_base + tbl_off(other_k)), D);
             R *= lds_f64(pk + (takeA ? dA : dB));
             const uint64_t nxt = lds_u64(pk + 8u);
             pa = takeA ? pk + 8u : pa;
@@ -2714,7 +2727,7 @@ static int launch_fast(const ScoreArgs& a, const KParams& p, bool check, int war
 
 // Tile kernel geometry for environments of at most max_a / max_b members: teams per CTA (0: not applicable).
 static int tile_geometry(const KParams& p, unsigned max_a, unsigned max_b, int key_is_w, int* table_n_out,
-                         int* stage_keys_out, int* team_bytes_out) {
+                         int* stage_keys_out, int* team_bytes_out, int* rep_n_out) {
     if (!(p.hell2 && p.unit_w && p.C <= 16 && key_is_w)) return 0;   // the configuration of score_fast_kernel<CP, true, false, false>
     if (max_a < 1 || max_b < 1 || max_a + max_b > 1024u) return 0;   // chunks of at most 128 events per lane
     const unsigned need = (max_a > max_b ? max_a : max_b) + 2u;
@@ -2726,26 +2739,34 @@ static int tile_geometry(const KParams& p, unsigned max_a, unsigned max_b, int k
     int teams = budget / team_bytes;
     if (teams > kTileMaxTeams) teams = kTileMaxTeams;
     if (const char* v = std::getenv("LOCOHD_TILE_TEAMS")) { const int t = std::atoi(v); if (t >= 1 && t < teams) teams = t; }   // occupancy sweeps
+    // what the teams leave over replicates the head of the two count-indexed tables (240 bytes per entry)
+    int rep_n = teams > 0 ? (budget - teams * team_bytes) / 240 : 0;
+    if (rep_n > kTileRepMax) rep_n = kTileRepMax;
+    if (rep_n < 16) rep_n = 0;
+    if (const char* v = std::getenv("LOCOHD_TILE_REP")) { const int r = std::atoi(v); if (r >= 0 && r < rep_n) rep_n = r; }   // A/B switch
     if (table_n_out) *table_n_out = (int)table_n;
     if (stage_keys_out) *stage_keys_out = stage_keys;
     if (team_bytes_out) *team_bytes_out = team_bytes;
+    if (rep_n_out) *rep_n_out = rep_n;
     return teams;
 }
 
 bool score_tiles_applicable(const KParams& p, unsigned max_a, unsigned max_b, int key_is_w) {
     if (const char* v = std::getenv("LOCOHD_NO_TILES")) if (std::atoi(v)) return false;   // A/B switch
     // below 6 teams (24 warps) one pair per warp with a stage of its own is the better kernel
-    return tile_geometry(p, max_a, max_b, key_is_w, nullptr, nullptr, nullptr) >= 6;
+    return tile_geometry(p, max_a, max_b, key_is_w, nullptr, nullptr, nullptr, nullptr) >= 6;
 }
 
 static int launch_tiles(const ScoreArgs& args, const KParams& p, unsigned max_a, unsigned max_b, cudaStream_t st) {
     ScoreArgs a = args;
-    int table_n = 0, stage_keys = 0, team_bytes = 0;
-    const int teams = tile_geometry(p, max_a, max_b, a.a.key_is_w, &table_n, &stage_keys, &team_bytes);
+    int table_n = 0, stage_keys = 0, team_bytes = 0, rep_n = 0;
+    const int teams = tile_geometry(p, max_a, max_b, a.a.key_is_w, &table_n, &stage_keys, &team_bytes, &rep_n);
     if (teams < 1) return -1;
     a.table_n = table_n;
     a.stage_cap = stage_keys;
-    const int smem = 3 * table_n * 8 + teams * team_bytes;
+    a.rep_n = p.C <= 8 ? rep_n : 0;
+    const bool rep = a.rep_n > 0;
+    const int smem = (table_n + 2 * (15 * a.rep_n + table_n)) * 8 + teams * team_bytes;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -2759,7 +2780,8 @@ static int launch_tiles(const ScoreArgs& args, const KParams& p, unsigned max_a,
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         kernel<<<grid, teams * kTeamThreads, smem, st>>>(a, p, teams, team_bytes);
     };
-    if (p.C <= 8) go(score_tile_kernel<8>); else go(score_tile_kernel<16>);
+    if (p.C <= 8) { if (rep) go(score_tile_kernel<8, true>); else go(score_tile_kernel<8, false>); }
+    else go(score_tile_kernel<16, false>);
     return 1;
 }
 

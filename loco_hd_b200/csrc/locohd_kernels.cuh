@@ -154,6 +154,7 @@ struct ScoreArgs {
     int stage_cap;                 // members (A + B) a warp can stage in shared memory
     int only_unstaged;             // second pass: score only the pairs the fast kernel skipped
     int table_n;                   // sqrt / rsqrt table entries staged by the fast kernel
+    int rep_n;                     // tile kernel: head entries of the count-indexed tables replicated per bank pair
     unsigned long long* cursor;    // fast kernel: next unclaimed pair (zeroed before the launch); warps claim runs of
                                    // `run` consecutive pairs, so all resident warps work at one moving frontier
     unsigned run;                  // pairs per claim: kScoreRun for large launches, fewer when the launch has fewer
