@@ -14,6 +14,9 @@
 //   K2   score_fast_kernel /    one warp per anchor pair: merge-path split of the two sorted environments over the
 //        score_kernel           32 lanes, per-lane category counts by warp prefix sums, per-lane walk that
 //                               accumulates dW * H (stat_dist_integral, locohd.rs:61-226, as a flat prefix scan)
+//   K2t  score_tile_kernel      job lists whose jobs share runs of environments (all-vs-all ensembles): a team of four
+//                               warps per (4 x 4 tile of structure pairs, anchor) stages the 8 environments once and
+//                               scores the 16 anchor pairs with 8 lanes each
 //   fallback gather (environments the fused kernel cannot take, rows of from_dmxs / from_coords):
 //   K1a  env_tile_kernel<false> one THREAD per anchor: FP32 prefilter over the candidate cells, counts the
 //                               survivors (upper bound of the environment size) -> scan -> store offsets
