@@ -630,13 +630,15 @@ def run_gpu(args, rank, local_rank, world):
     # member (3 sub, 3 mul, 2 add, 1 compare, 1 sqrt) all belong to the fused gather K1; the sampled upper-bound
     # pass does no algorithmic FP64 work.  With LOCOHD_LEGACY_GATHER=1 the multi-kernel path runs instead (9 of the
     # 10 in the exact fill K1b, the sqrt in the sort K1c).
+    score_name = ("score_tile_kernel (K2t: merge walk per 4x4 tile of structure pairs, 8 environments staged per 16 anchor pairs)"
+                  if ctx.tile_launches else "score_fast_kernel / score_kernel (K2 merge walk)")
     if "sort" in kernels:
-        alg = {"score": ("score_fast_kernel / score_kernel (K2 merge walk)", f_walk),
+        alg = {"score": (score_name, f_walk),
                "fill": ("env_tile_kernel<true> (K1b exact gather, multi-kernel path)", 0.9 * f_gather),
                "sort": ("env_sort_kernel (K1c sort + CDF + packing, multi-kernel path)", 0.1 * f_gather),
                "count": ("env_tile_kernel<false> (K1a FP32 upper-bound sizes)", 0.0)}
     else:
-        alg = {"score": ("score_fast_kernel / score_kernel (K2 merge walk)", f_walk),
+        alg = {"score": (score_name, f_walk),
                "fill": ("env_fused_kernel (K1: row pruning, exact FP64 gather, register bitonic sort, CDF, packing)",
                         f_gather),
                "count": ("env_tile_kernel<false> with stride 16 (store sizing sample)", 0.0)}
@@ -659,6 +661,16 @@ def run_gpu(args, rank, local_rank, world):
                              "achieved_tflops": ach, "frac_of_fp64_peak": ach / fp64_peak, "traffic": traffic.get(g)}
             if g in pipes:   # from the committed ncu capture of the same workload (not measured in this run)
                 per_kernel[g]["ncu"] = dict(pipes[g], source=prof_src)
+                wf = pipes[g].get("shared_wavefronts")
+                if wf and probe_info.get("sm_mhz"):
+                    # the pipe that binds the scoring kernels: one shared-memory wavefront per clock and SM; wavefronts
+                    # per launch from the committed ncu capture, launch time and SM clock measured in this run
+                    peak_wf = 148 * probe_info["sm_mhz"] * 1e6
+                    ach_wf = wf / (kernels[g]["ms_per_step"] * 1e-3)
+                    per_kernel[g]["shared_pipe_roofline"] = {
+                        "bound": "shared-memory data pipe (1 wavefront / clock / SM)", "achieved": ach_wf / 1e9,
+                        "peak": peak_wf / 1e9, "unit": "G wavefronts/s", "frac": ach_wf / peak_wf,
+                        "wavefronts_per_launch": wf, "bank_conflict_share": (pipes[g].get("shared_bank_conflicts") or 0) / wf}
     dom = max(per_kernel, key=lambda g: per_kernel[g]["launch_ms"])
     dominant, dom_flops, dom_ms = per_kernel[dom]["kernel"], per_kernel[dom]["alg_flops_per_launch"], per_kernel[dom]["launch_ms"]
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12

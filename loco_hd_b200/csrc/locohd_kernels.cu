@@ -1594,6 +1594,8 @@ __global__ void __launch_bounds__(kScoreMaxWarps * 32) score_kernel(ScoreArgs a,
 //  needs ~6 cycles per instruction (fixed-latency and shared-memory dependencies): issue slots 63 % busy instead of
 //  82 %, 12.3 ms against 11.6 ms.)
 constexpr double kSmallH2 = 1e-8;
+constexpr int kSmallH2Hi = 0x3E45798E;   // high word of 1e-8 (0x3E45798E E2308C3A): hi(h2) < this  <=>  h2 < 1e-8 up to the low
+                                         // word (1e-8 - 2^-59 relative) or h2 negative - a signed integer compare, no FP64 constant
 
 // sqrt of a double in [1e-8, ~1]: MUFU.RSQ (f32) seed + one coupled Newton step in FP64, relative error
 // 1.5 * 2^-44 = 8.5e-14.  Used for H itself (nothing amplifies the error; bar 1e-9 on the score); IEEE sqrt costs
@@ -2018,10 +2020,13 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
     const uint32_t dsq_base = __shfl_sync(kFull, smem_u32(s_dsq), lane);
     const uint32_t ratio_base = __shfl_sync(kFull, smem_u32(s_ratio), lane);
     const uint32_t cnt_lane = __shfl_sync(kFull, smem_u32(cnt + lane), lane);
+    // shared-space address of entry e of a count-indexed table: base + 8 e + min(120 e + 8 copy, 120 rep_n); the base is
+    // folded into both arguments of the min, which leaves one IMAD, one min and one shift-add per look-up
     const uint32_t copy8 = 8u * (lane & 15), cap8 = 120u * (uint32_t)rep_n;
-    auto tbl_off = [&](uint32_t e) -> uint32_t {   // byte offset of entry e in a count-indexed table
-        return REP ? 8u * e + min(120u * e + copy8, cap8) : 8u * e;
-    };
+    const uint32_t sq_copy = __shfl_sync(kFull, sq_base + copy8, lane), sq_cap = __shfl_sync(kFull, sq_base + cap8, lane);
+    const uint32_t dsq_copy = __shfl_sync(kFull, dsq_base + copy8, lane), dsq_cap = __shfl_sync(kFull, dsq_base + cap8, lane);
+    auto sq_addr = [&](uint32_t e) -> uint32_t { return REP ? 8u * e + min(120u * e + sq_copy, sq_cap) : sq_base + 8u * e; };
+    auto dsq_addr = [&](uint32_t e) -> uint32_t { return REP ? 8u * e + min(120u * e + dsq_copy, dsq_cap) : dsq_base + 8u * e; };
     const int col = lane >> 3, sub = lane & (kTileLanes - 1);
     const uint64_t n = a.uniform_n, n_units = a.n_tiles * n;
     const WfDev& wf = P.wfs[0];
@@ -2175,7 +2180,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
             cnt[r * 32 + lane] = ex;
             const uint32_t ka = ex & 0xffffu, kb = ex >> 16;
             mism += (ka != kb) ? 1 : 0;
-            D = fma(lds_f64(sq_base + tbl_off(ka)), lds_f64(sq_base + tbl_off(kb)), D);
+            D = fma(lds_f64(sq_addr(ka)), lds_f64(sq_addr(kb)), D);
         }
         const uint32_t totA = i + 1u, totB = j + 1u;   // members of either side before my chunk, anchors included
         double rA = __ldg(P.rsqrt_tbl + totA), rB = __ldg(P.rsqrt_tbl + totB);
@@ -2184,7 +2189,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
 #pragma unroll
             for (int r = 0; r < CP; ++r) {
                 const uint32_t word = cnt[r * 32 + lane];
-                const double u = __dmul_rn(lds_f64(sq_base + tbl_off(word & 0xffffu)), rA) - __dmul_rn(lds_f64(sq_base + tbl_off(word >> 16)), rB);
+                const double u = __dmul_rn(lds_f64(sq_addr(word & 0xffffu)), rA) - __dmul_rn(lds_f64(sq_addr(word >> 16)), rB);
                 s = fma(u, u, s);
             }
             return 0.5 * s;
@@ -2218,7 +2223,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
             sts_u32_rmw(ca, word + (takeA ? 1u : 0x10000u));
             mism += (mine_k == other_k ? 1 : 0) - (mine_k + 1u == other_k ? 1 : 0);
             const uint32_t pk = takeA ? pa : pb;
-            D = fma(lds_f64(dsq_base + tbl_off(mine_k)), lds_f64(sq_base + tbl_off(other_k)), D);
+            D = fma(lds_f64(dsq_addr(mine_k)), lds_f64(sq_addr(other_k)), D);
             R *= lds_f64(pk + (takeA ? dA : dB));
             const uint64_t nxt = lds_u64(pk + 8u);
             pa = takeA ? pk + 8u : pa;
@@ -2227,7 +2232,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
             rb = takeA ? rb : nxt;
             const double h2 = fma(-R, D, 1.0);
             h = (mism == 0) ? 0.0 : sqrt_unit(h2);       // identical counts: exactly 0
-            if (mism != 0 && h2 < kSmallH2) {            // rare: difference form from the counts
+            if (mism != 0 && __double2hiint(h2) < kSmallH2Hi) {   // h2 < 1e-8 (or negative): rare, difference form from the counts
                 rA = __ldg(P.rsqrt_tbl + ((pa + dA - ratio_base) >> 3));
                 rB = __ldg(P.rsqrt_tbl + ((pb + dB - ratio_base) >> 3));
                 h = sqrt(exact_h2());

@@ -99,7 +99,9 @@ for (_, n), v in per.items():
         pipes5[g] = {"warp_instructions": v["smsp__inst_executed.sum"][0],
                      "issue_slots_busy_pct": v["smsp__issue_active.avg.pct_of_peak_sustained_active"][0],
                      "shared_pipe_busy_pct": v["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"][0],
-                     "fp64_pipe_pct": v["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"][0]}
+                     "fp64_pipe_pct": v["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"][0],
+                     "shared_wavefronts": v["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"][0],
+                     "shared_bank_conflicts": v["l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"][0]}
         if g == "score":
             pairs = 2497500000.0
             out += ["", f"K2 per anchor pair: {v['smsp__inst_executed.sum'][0] / pairs:.0f} warp instructions, "
