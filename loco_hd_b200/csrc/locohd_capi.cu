@@ -633,6 +633,60 @@ std::vector<ScoreTile> group_job_tiles(const std::vector<locohd_job>& jobs, cons
     return tiles;
 }
 
+// The same for job lists in any order (plain row-major (i, j) order of an ensemble, shuffled lists): the distinct A
+// runs and B runs are ranked, a job belongs to block (rank_a / 4, rank_b / 4) and sits in cell (rank_a % 4, rank_b % 4)
+// of it; blocks are scored in (block row, block column) order, which keeps the structures of a block row in L2.  A job
+// named twice opens a second tile of its block.  O(n log n) on the host, so it is only tried when the list order
+// itself does not tile.
+std::vector<ScoreTile> group_job_tiles_sorted(const std::vector<locohd_job>& jobs, const std::vector<uint64_t>& joff) {
+    std::vector<uint64_t> av(jobs.size()), bv(jobs.size());
+    for (size_t j = 0; j < jobs.size(); ++j) { av[j] = jobs[j].a_first; bv[j] = jobs[j].b_first; }
+    std::sort(av.begin(), av.end()); av.erase(std::unique(av.begin(), av.end()), av.end());
+    std::sort(bv.begin(), bv.end()); bv.erase(std::unique(bv.begin(), bv.end()), bv.end());
+    struct Item { uint64_t block; uint32_t cell; uint32_t job; };
+    std::vector<Item> items(jobs.size());
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        const uint64_t ra = (uint64_t)(std::lower_bound(av.begin(), av.end(), jobs[j].a_first) - av.begin());
+        const uint64_t rb = (uint64_t)(std::lower_bound(bv.begin(), bv.end(), jobs[j].b_first) - bv.begin());
+        items[j] = {((ra / kTileDim) << 32) | (rb / kTileDim), (uint32_t)((ra % kTileDim) * kTileDim + rb % kTileDim), (uint32_t)j};
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.block < y.block; });
+    std::vector<ScoreTile> tiles;
+    size_t lo = 0;
+    while (lo < items.size()) {
+        size_t hi = lo;
+        while (hi < items.size() && items[hi].block == items[lo].block) ++hi;
+        size_t first_tile = tiles.size();
+        for (size_t k = lo; k < hi; ++k) {
+            const Item& it = items[k];
+            const int r = (int)(it.cell / kTileDim), c = (int)(it.cell % kTileDim);
+            size_t t = first_tile;   // first tile of this block whose cell is still free
+            while (t < tiles.size() && tiles[t].out_first[it.cell] != kTileNone) ++t;
+            if (t == tiles.size()) {
+                ScoreTile nt;
+                for (int q = 0; q < kTileDim; ++q) { nt.a_first[q] = kTileNone; nt.b_first[q] = kTileNone; }
+                for (int q = 0; q < kTileDim * kTileDim; ++q) nt.out_first[q] = kTileNone;
+                tiles.push_back(nt);
+            }
+            tiles[t].a_first[r] = jobs[it.job].a_first;
+            tiles[t].b_first[c] = jobs[it.job].b_first;
+            tiles[t].out_first[it.cell] = joff[it.job];
+        }
+        lo = hi;
+    }
+    return tiles;
+}
+
+// A row of a tile is one warp, four pairs wide; full tiles run 1.5 x the pair kernel's rate (profiles/r6a).  The tile
+// kernel pays when the rows are mostly filled and a team mostly has work for its four warps (one-against-many lists -
+// trajectory frames against frame 0 - give tiles of a single row: three of four warps would idle).
+bool tiles_pay(const std::vector<ScoreTile>& tiles, uint64_t n_jobs) {
+    uint64_t rows = 0;
+    for (const ScoreTile& t : tiles)
+        for (int r = 0; r < kTileDim; ++r) rows += t.a_first[r] != kTileNone ? 1 : 0;
+    return !tiles.empty() && n_jobs * 10 >= rows * kTileDim * 6 && rows >= 3 * tiles.size();
+}
+
 int run_score(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_pairs,
               const uint32_t* d_pairs, const locohd_job* d_jobs, const uint64_t* d_job_off, uint64_t n_jobs,
               uint64_t uniform_n, const uint32_t* d_wf_idx, double* d_out, const ScoreTile* d_tiles = nullptr,
@@ -1348,15 +1402,9 @@ int locohd_score_jobs_stats(locohd_ctx* ctx, const locohd_envset* a, const locoh
     uint64_t n_tiles = 0;
     if (uniform && n_per_job && n_jobs >= 4 && !wf_idx && a->key_is_w && b->key_is_w &&
         score_tiles_applicable(ctx->kp, a->max_count, b->max_count, 1)) {
-        tiles = group_job_tiles(hj, joff);
-        // A row of a tile is one warp, four pairs wide; full tiles run 1.43 x the pair kernel's rate (profiles/r6a).
-        // The tile kernel pays when the rows are mostly filled and a team mostly has work for its four warps
-        // (one-against-many lists - trajectory frames against frame 0 - give tiles of a single row: three of four
-        // warps would idle).
-        uint64_t rows = 0;
-        for (const ScoreTile& t : tiles)
-            for (int r = 0; r < kTileDim; ++r) rows += t.a_first[r] != kTileNone ? 1 : 0;
-        if (n_jobs * 10 >= rows * kTileDim * 6 && rows >= 3 * tiles.size()) {
+        tiles = group_job_tiles(hj, joff);                                      // the list order itself (blocked_pairs)
+        if (!tiles_pay(tiles, n_jobs)) tiles = group_job_tiles_sorted(hj, joff);   // any other order
+        if (tiles_pay(tiles, n_jobs)) {
             n_tiles = tiles.size();
             if ((st = dtiles.load(ctx, tiles.data(), n_tiles))) return cleanup(st);
         }

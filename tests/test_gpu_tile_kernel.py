@@ -93,8 +93,9 @@ def test_job_orders_the_tiles_do_not_fit_take_the_pair_kernel(gpu_ctx, oracle_mo
 
 
 def test_shuffled_job_list_and_repeated_jobs(gpu_ctx, oracle_mod, monkeypatch):
-    """The grouping is greedy in list order: a shuffled ensemble list and a list that names the same job twice are
-    still scored job by job, whatever tiles come out."""
+    """Lists whose order does not tile are regrouped on the host by the ranks of their environment runs (every cell of
+    a tile carries its own output position): plain row-major (i, j) order (compare_ensembles.py:273-296 loops that
+    way), a shuffled list and a list that names every job twice take the tile kernel too and are scored job by job."""
     rng = np.random.default_rng(5)
     base = synth.gen(23, 50, 8, 7)
     members = [synth.partner(base, 1.5, 900 + i) for i in range(8)]
@@ -104,10 +105,14 @@ def test_shuffled_job_list_and_repeated_jobs(gpu_ctx, oracle_mod, monkeypatch):
     pairs = batch.blocked_pairs(8, 4)
     want = {tuple(p): _oracle_scores(oracle_mod, op, members[p[0]], members[p[1]], anchors, anchors, 10.0)
             for p in pairs.tolist()}
-    for order in (rng.permutation(len(pairs)), np.r_[np.arange(len(pairs)), np.arange(len(pairs))]):
+    row_major = np.lexsort((pairs[:, 1], pairs[:, 0]))
+    assert np.array_equal(pairs[row_major], batch.all_pairs(8))
+    for order in (row_major, rng.permutation(len(pairs)), np.r_[np.arange(len(pairs)), np.arange(len(pairs))][::-1]):
         sel = pairs[order]
         jobs = np.array([(i * base.n, j * base.n, base.n) for i, j in sel], dtype=JOB)
+        before = gpu_ctx.tile_launches
         got = gpu_ctx.score_jobs_stats(env, env, jobs, scores=True)["scores"].reshape(len(sel), base.n)
+        assert gpu_ctx.tile_launches > before
         assert_scores_close(got.ravel(), np.concatenate([want[tuple(p)] for p in sel.tolist()]))
     env.close(); st.close()
 
