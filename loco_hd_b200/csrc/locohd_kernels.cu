@@ -232,7 +232,15 @@ __global__ void __launch_bounds__(kCellThreads) build_cells_kernel(StructsView s
         if (inv_cell == 0.0) m.reach = 0;
         const double span_x = threshold * inv_cell_x * (1.0 + 1e-9);
         m.reach_x = (inv_cell_x > 0.0 && isfinite(span_x)) ? (int)fmin(span_x, 2.0e6) + 1 : 0;
-        m.pad[0] = m.pad[1] = m.pad[2] = 0;
+        m.pad0 = 0;
+        {   // the anchor-independent form of the fused gather's thin-shell bound: the structure's largest |coordinate|
+            // stands in for the anchor's (a larger value only sends more candidates to the box test, never fewer)
+            double qmax = threshold;
+            for (int k = 0; k < 3; ++k) qmax = fmax(qmax, fmax(fabs(lo[k]), fabs(hi[k])));
+            const double r_safe = threshold - 8.9e-16 * (qmax + threshold);
+            m.r2_safe = (r_safe > 0.0 && isfinite(r_safe)) ? r_safe * r_safe * (1.0 - 1e-15)
+                                                          : (isinf(threshold) ? __dmul_rn(threshold, threshold) : 0.0);
+        }
         // FP32 prefilter: relative coordinates are rounded to f32 (error <= emax * 2^-24 each); the bound below
         // is generous (see DESIGN.md "prefilter margin").
         const double delta = 4.0 * emax * 5.9604644775390625e-8;
@@ -445,7 +453,7 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
     uint32_t jpos = 0;
     StructMeta m;
     m.nx = m.ny = m.nz = 1; m.reach = 0; m.inv_cell = 0.0; m.ox = m.oy = m.oz = 0.0; m.thr2f = 0.f;
-    m.cellf = m.prune_r = m.inv_cellxf = 0.f; m.inv_cell_x = 0.0; m.reach_x = 0;
+    m.cellf = m.prune_r = m.inv_cellxf = 0.f; m.inv_cell_x = 0.0; m.reach_x = 0; m.pad0 = 0; m.r2_safe = 0.0;
     const uint32_t* cell_start = s.cell_start;
     if (active) {
         const uint64_t sid = anchor_struct ? anchor_struct[e] : 0;
@@ -543,6 +551,7 @@ __global__ void __launch_bounds__(kTileThreads) env_tile_kernel(StructsView s, K
     }
 }
 
+__device__ __forceinline__ uint32_t smem_u32_early(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float rsqrt_approx(float x) {
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -790,18 +799,25 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? 1 :
     // Every CTA takes a contiguous block of the cell-ordered anchors and its warps draw the next anchor from a
     // shared cursor: at any time the warps of a CTA hold consecutive anchors (they do not drift apart as with a
     // fixed stride), read overlapping candidate rows (L1 hits) and finish together.
-    __shared__ unsigned long long cta_cursor;
+    // (a 32-bit offset and a plain atom.shared.add: the 64-bit shared-memory atomicAdd is a compare-and-swap loop, and
+    //  the compiler wraps an atomicAdd under `if (lane == 0)` into its warp-aggregation sequence - ~30 instructions per
+    //  environment together)
+    __shared__ unsigned int cta_cursor;
     const uint64_t per_block = (n_env + gridDim.x - 1) / gridDim.x;
+    const uint64_t t_begin = min(n_env, (uint64_t)blockIdx.x * per_block);
     const uint64_t t_end = min(n_env, (uint64_t)(blockIdx.x + 1) * per_block);
-    if (threadIdx.x == 0) cta_cursor = (uint64_t)blockIdx.x * per_block;
+    const uint32_t t_count = (uint32_t)min(t_end - t_begin, (uint64_t)0xFFFFFFFFu);   // the host keeps per_block below 2^32
+    if (threadIdx.x == 0) cta_cursor = 0u;
     __syncthreads();
+    const uint32_t cursor_addr = smem_u32_early(&cta_cursor);
 #pragma unroll 1
     for (;;) {
         __syncwarp();
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(&cta_cursor, 1ull);
-        t = __shfl_sync(kFull, t, 0);
-        if (t >= t_end) break;
+        uint32_t tk = 0;
+        if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(tk) : "r"(cursor_addr) : "memory");
+        tk = __shfl_sync(kFull, tk, 0);
+        if (tk >= t_count) break;
+        const uint64_t t = t_begin + tk;
         const uint64_t e = order[t];
         const uint2 rec = b.order_rec[t];   // (structure, cell-sorted position), written with the anchor order
         const uint64_t sid = rec.x;
@@ -885,9 +901,7 @@ __global__ void __launch_bounds__(fused_warps(CAP, DEBUG) * 32, CAP == 512 ? 1 :
         // ---- candidates: lanes over the flat concatenation of the rows; exact membership with the kd-tree crate's
         //      predicate (unfused FP64, as env_tile_kernel<true>) + tag rule; members ballot-compacted.
         //      The record of the next round is requested before the current one is tested.
-        const double qmax = fmax(fmax(fabs(q.x), fabs(q.y)), fmax(fabs(q.z), threshold));
-        const double r_safe = threshold - 8.9e-16 * (qmax + threshold);
-        const double r2_safe = (r_safe > 0.0 && isfinite(r_safe)) ? r_safe * r_safe * (1.0 - 1e-15) : (isinf(threshold) ? r2 : 0.0);
+        const double r2_safe = m.r2_safe;   // per structure (build_cells_kernel): ~40 instructions per environment less than from the anchor
         uint32_t M = 0;
         {
             int row_base = -1;   // compacted row of the last candidate of the previous round

@@ -31,8 +31,11 @@ struct __align__(16) StructMeta {
     double inv_cell_x;   // 1 / x cell edge: cells are up to 4 times finer along x (the fastest axis), which costs no
                          // extra rows and lets the gather cut every row close to the sphere
     int reach_x;         // neighbour cells along x
-    int pad[3];
+    int pad0;
+    double r2_safe;      // fused gather: squared radius below which the kd-tree crate's per-axis box test cannot reject
+                         // ((r - 8.9e-16 (max |coordinate| of the structure + r))^2 (1 - 1e-15); 0: always test)
 };
+static_assert(sizeof(StructMeta) == 96, "env_fused_kernel loads the record as six 16-byte words");
 
 // Kernel-visible parameter block of one LoCoHD instance (LoCoHD struct, locohd.rs:42-55).
 struct KParams {
