@@ -225,6 +225,13 @@ int locohd_score_jobs(locohd_ctx* ctx, const locohd_envset* a, const locohd_envs
 int locohd_score_jobs_stats(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_jobs,
                             const locohd_job* jobs, const uint32_t* wf_idx, double* out_scores, double* out_job_means,
                             double* out_anchor_means, double* out_anchor_stds);
+/* Planning query, no device needed: how locohd_score_jobs[_stats] would group this job list for the tile kernel (jobs
+ * that share runs of environments are scored tile by tile: up to 4 runs of A against up to 4 runs of B staged once per
+ * anchor).  *out_tiles = tiles the list groups into (in list order if that tiles well, else regrouped by the ranks of
+ * the runs), *out_rows = tile rows in use, *out_pays = 1 if the grouping passes the fill criteria (equal job sizes,
+ * >= 60 % of the row cells used, >= 3 rows per tile).  Whether a call then takes the tile kernel also depends on the
+ * instance (Hellinger-2, unit category weights, one weight function) and on the environment sizes. */
+int locohd_plan_job_tiles(uint64_t n_jobs, const locohd_job* jobs, uint64_t* out_tiles, uint64_t* out_rows, int* out_pays);
 /* from_anchors (locohd.rs:392-406): one pair of caller-ordered environments, walked in the reference's
  * exact three-way-merge order (the lists are NOT required to be sorted, as in the reference). */
 int locohd_score_anchor_lists(locohd_ctx* ctx, const uint16_t* seq_a, uint64_t len_a, const double* dists_a,

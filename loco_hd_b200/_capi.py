@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "locohd_envset_from_ragged_rows",
     "locohd_envset_from_coords", "locohd_envset_destroy", "locohd_envset_size", "locohd_envset_total_members",
     "locohd_envset_dump", "locohd_score_pairs", "locohd_score_jobs", "locohd_score_jobs_stats",
-    "locohd_score_anchor_lists",
+    "locohd_score_anchor_lists", "locohd_plan_job_tiles",
     "locohd_from_primitives", "locohd_wf_integral_points", "locohd_sd_run",
 ]
 
@@ -122,6 +122,7 @@ def load_library() -> C.CDLL:
         "locohd_score_jobs": (C.c_int, [vp, vp, vp, u64, vp, vp, vp, vp]),
         "locohd_score_jobs_stats": (C.c_int, [vp, vp, vp, u64, vp, vp, vp, vp, vp, vp]),
         "locohd_score_anchor_lists": (C.c_int, [vp, vp, u64, vp, u64, vp, u64, vp, u64, u32, vp]),
+        "locohd_plan_job_tiles": (C.c_int, [u64, vp, vp, vp, vp]),
         "locohd_from_primitives": (C.c_int, [vp, u64, vp, vp, vp, u64, vp, vp, vp, u64, vp, vp, dbl, vp]),
         "locohd_wf_integral_points": (C.c_int, [vp, C.POINTER(WeightFunctionC), u64, vp, vp]),
         "locohd_sd_run": (C.c_int, [vp, i32, vp, i32, u64, vp, vp, vp]),
@@ -147,6 +148,18 @@ def _arr(a, dtype):
     if a is None or isinstance(a, (int, np.integer)):
         return a
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def plan_job_tiles(jobs) -> dict:
+    """locohd_plan_job_tiles: how a job list groups into tiles of jobs that share runs of environments (host-side
+    query, no device needed).  Returns {"tiles", "rows", "pays"}."""
+    lib = load_library()
+    jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+    tiles, rows, pays = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+    st = lib.locohd_plan_job_tiles(len(jobs), _p(jobs), C.byref(tiles), C.byref(rows), C.byref(pays))
+    if st:
+        raise LocoHDError(st, "locohd_plan_job_tiles failed")
+    return {"tiles": int(tiles.value), "rows": int(rows.value), "pays": bool(pays.value)}
 
 
 def make_wf(name: str, params: Sequence[float]) -> WeightFunctionC:

@@ -1346,6 +1346,32 @@ int locohd_score_pairs(locohd_ctx* ctx, const locohd_envset* a, const locohd_env
     API_END()
 }
 
+int locohd_plan_job_tiles(uint64_t n_jobs, const locohd_job* jobs, uint64_t* out_tiles, uint64_t* out_rows, int* out_pays) {
+    if (n_jobs && !jobs) return LOCOHD_ERR_BAD_PARAM;
+    try {
+        std::vector<locohd_job> hj(jobs, jobs + n_jobs);   // host memory only: this is a host-side query
+        std::vector<uint64_t> joff(n_jobs + 1, 0);
+        bool uniform = n_jobs > 0;
+        for (uint64_t j = 0; j < n_jobs; ++j) { joff[j + 1] = joff[j] + hj[j].n; uniform = uniform && hj[j].n == hj[0].n; }
+        std::vector<ScoreTile> tiles;
+        bool pays = false;
+        if (uniform && hj[0].n && n_jobs >= 4) {
+            tiles = group_job_tiles(hj, joff);
+            if (!tiles_pay(tiles, n_jobs)) tiles = group_job_tiles_sorted(hj, joff);
+            pays = tiles_pay(tiles, n_jobs);
+        }
+        uint64_t rows = 0;
+        for (const ScoreTile& t : tiles)
+            for (int r = 0; r < kTileDim; ++r) rows += t.a_first[r] != kTileNone ? 1 : 0;
+        if (out_tiles) *out_tiles = tiles.size();
+        if (out_rows) *out_rows = rows;
+        if (out_pays) *out_pays = pays ? 1 : 0;
+        return LOCOHD_OK;
+    } catch (const std::exception&) {
+        return LOCOHD_ERR_CUDA;
+    }
+}
+
 int locohd_score_jobs(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_jobs,
                       const locohd_job* jobs, const uint32_t* wf_idx, double* out_scores, double* out_job_means) {
     return locohd_score_jobs_stats(ctx, a, b, n_jobs, jobs, wf_idx, out_scores, out_job_means, nullptr, nullptr);

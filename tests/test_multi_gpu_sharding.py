@@ -131,3 +131,39 @@ def test_blocked_pairs_and_contiguous_shares():
         runs = [batch.contiguous_share(n_jobs, r, world) for r in range(world)]
         assert [x for s in runs for x in range(n_jobs)[s]] == list(range(n_jobs))
         assert max(s.stop - s.start for s in runs) - min(s.stop - s.start for s in runs) <= 1
+
+
+def test_job_lists_group_into_tiles_on_the_host():
+    """locohd_plan_job_tiles (no device): the all-vs-all ensemble of compare_ensembles.py:250-296 groups into 4 x 4
+    tiles of structure pairs whatever the order of the list; one-against-many lists (trajectory_analyzer.py:112-120)
+    and lists of unequal jobs do not."""
+    from loco_hd_b200 import _capi
+
+    n = 5000
+
+    def jobs_of(pairs):
+        return np.array([(i * n, j * n, n) for i, j in pairs], dtype=batch.JOB_DTYPE)
+
+    S = 40                                            # 10 block rows: 45 full tiles + 10 diagonal ones
+    blocked = batch.blocked_pairs(S, 4)
+    plan = _capi.plan_job_tiles(jobs_of(blocked))
+    assert plan["pays"] and plan["tiles"] == 55 and plan["rows"] == 45 * 4 + 10 * 3
+    rng = np.random.default_rng(3)
+    for order in (batch.all_pairs(S), blocked[rng.permutation(len(blocked))]):   # row-major, shuffled
+        p2 = _capi.plan_job_tiles(jobs_of(order))
+        # (ranked separately, the A runs are structures 0 .. S-2 and the B runs 1 .. S-1: the diagonal tiles hold 10
+        #  jobs in 4 rows instead of 6 in 3)
+        assert p2["pays"] and p2["tiles"] == 55 and p2["rows"] == 45 * 4 + 9 * 4 + 3
+    twice = _capi.plan_job_tiles(jobs_of(np.concatenate([blocked, blocked])))
+    assert twice["pays"] and twice["tiles"] == 110
+    # a rank's contiguous share starts and ends inside tiles
+    share = blocked[batch.contiguous_share(len(blocked), 1, 3)]
+    assert _capi.plan_job_tiles(jobs_of(share))["pays"]
+    # frame 0 against the other frames: tiles of a single row
+    frames = _capi.plan_job_tiles(jobs_of([(0, f) for f in range(1, 65)]))
+    assert not frames["pays"] and frames["tiles"] == 16 and frames["rows"] == 16
+    # jobs of different sizes are never tiled
+    uneven = jobs_of(blocked)
+    uneven["n"][5] = n - 1
+    assert not _capi.plan_job_tiles(uneven)["pays"]
+    assert _capi.plan_job_tiles(jobs_of([]))["tiles"] == 0
