@@ -1970,7 +1970,8 @@ __global__ void __launch_bounds__(score_fast_max_warps(KEY_IS_W, CHECK, WEIGHTED
 // the ratio-table read (-70 wavefronts, +7 instructions per event and a longer dependent chain: 136.6 -> 141.5 ms on
 // the 200-structure ensemble); lanes dealt to the four pairs of a row in proportion to their event counts (12 % fewer
 // walk iterations per warp, but the wavefronts follow the lane-events, not the iterations: 137.6 -> 140.6 ms);
-// 7 / 6 teams per SM run 1.3 % / 4.4 % slower than 8.
+// 7 / 6 teams per SM run 1.3 % / 4.4 % slower than 8; cp.async.bulk.prefetch.L2 of the next unit's environments one unit
+// ahead (134.0 -> 136.2 ms, profiles/r6o).
 constexpr int kTileLanes = 8;                          // lanes per anchor pair
 constexpr int kTeamThreads = kTileDim * kTileDim * kTileLanes;   // 128: warp r = row r, lane >> 3 = column
 constexpr int kTileMaxTeams = 8;
