@@ -2042,7 +2042,12 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
     const uint32_t dsq_copy = __shfl_sync(kFull, dsq_base + copy8, lane), dsq_cap = __shfl_sync(kFull, dsq_base + cap8, lane);
     auto sq_addr = [&](uint32_t e) -> uint32_t { return REP ? 8u * e + min(120u * e + sq_copy, sq_cap) : sq_base + 8u * e; };
     auto dsq_addr = [&](uint32_t e) -> uint32_t { return REP ? 8u * e + min(120u * e + dsq_copy, dsq_cap) : dsq_base + 8u * e; };
-    const int col = lane >> 3, sub = lane & (kTileLanes - 1);
+    // warp = row of the tile, 8 lanes per column.  (Measured and dropped, profiles/r6p: warp w scoring the pairs
+    // (r, (r + w) mod 4) - a Latin square, equal event totals for the four warps, where ncu shows 19.6 % of the warp time
+    // in the team barrier waiting for the row with the largest A_r - 134.9 -> 139.5 ms: the 32 lanes of a row share
+    // one A list, lanes at the same place of their chunks read the same or neighbouring words.)
+    const int sub = lane & (kTileLanes - 1);
+    const int prow = row, pcol = lane >> 3;
     const uint64_t n = a.uniform_n, n_units = a.n_tiles * n;
     const WfDev& wf = P.wfs[0];
 
@@ -2132,12 +2137,12 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
         if (state == 2) break;
         if (loader) fetch();
         if (state == 1) continue;
-        const uint64_t out_first = __ldg(a.tiles[ctrl->tile].out_first + row * kTileDim + col);
-        const uint32_t Ma = ctrl->M[row], Mb = ctrl->M[kTileDim + col];
+        const uint64_t out_first = __ldg(a.tiles[ctrl->tile].out_first + prow * kTileDim + pcol);
+        const uint32_t Ma = ctrl->M[prow], Mb = ctrl->M[kTileDim + pcol];
         const uint32_t p = ctrl->p;
         const bool valid = out_first != kTileNone && Ma != 0 && Mb != 0;
-        const uint64_t* kA = stage + (valid ? ctrl->start[row] : 0u);
-        const uint64_t* kB = stage + (valid ? ctrl->start[kTileDim + col] : 0u);
+        const uint64_t* kA = stage + (valid ? ctrl->start[prow] : 0u);
+        const uint64_t* kB = stage + (valid ? ctrl->start[kTileDim + pcol] : 0u);
         mbar_wait(&ctrl->mbar, mbar_parity);
         mbar_parity ^= 1u;
         if (!__any_sync(kFull, valid)) continue;
