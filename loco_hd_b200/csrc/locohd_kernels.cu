@@ -2046,8 +2046,12 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
     // (r, (r + w) mod 4) - a Latin square, equal event totals for the four warps, where ncu shows 19.6 % of the warp time
     // in the team barrier waiting for the row with the largest A_r - 134.9 -> 139.5 ms: the 32 lanes of a row share
     // one A list, lanes at the same place of their chunks read the same or neighbouring words.)
-    const int sub = lane & (kTileLanes - 1);
-    const int prow = row, pcol = lane >> 3;
+    // Lane order: the column is the fast index (lane = 4 chunk + column): the four lanes that sit at the same place of
+    // their chunks of the shared A list are neighbours in one half-warp and read the same or adjacent words (keys of
+    // A, ratio-table entries).  Against lane = 8 column + chunk: 134.7 -> 133.8 ms (profiles/r6q).
+    constexpr int lstep = kTileDim;   // lane distance between consecutive chunks of a pair
+    const int sub = lane >> 2;
+    const int prow = row, pcol = lane & (kTileDim - 1);
     const uint64_t n = a.uniform_n, n_units = a.n_tiles * n;
     const WfDev& wf = P.wfs[0];
 
@@ -2156,7 +2160,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
         const uint32_t Q = (E + kTileLanes - 1) / kTileLanes;
         const uint32_t diag = min(E, (uint32_t)sub * Q);
         const uint32_t i = merge_path(kA, kB, na, nb, diag), j = diag - i;
-        uint32_t i1 = __shfl_down_sync(kFull, i, 1), j1 = __shfl_down_sync(kFull, j, 1);
+        uint32_t i1 = __shfl_down_sync(kFull, i, lstep), j1 = __shfl_down_sync(kFull, j, lstep);
         if (sub == kTileLanes - 1) { i1 = na; j1 = nb; }
 
         // per-lane histogram of my chunk (8-bit fields: a chunk has at most 128 events), exclusive prefix over the 8
@@ -2191,7 +2195,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
             uint32_t incl = v;
 #pragma unroll
             for (int o = 1; o < kTileLanes; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(kFull, incl, o);
+                const uint32_t u = __shfl_up_sync(kFull, incl, o * lstep);
                 if (sub >= o) incl += u;
             }
             uint32_t ex = incl - v;
@@ -2260,7 +2264,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
         }
         if (sub == kTileLanes - 1) acc = fma(wf.w_inf - wprev, h, acc);   // tail to infinity: the last chunk's state is final
 #pragma unroll
-        for (int o = kTileLanes / 2; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+        for (int o = kTileLanes / 2; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o * lstep);
         if (sub == 0 && valid) a.out[out_first + p] = acc;
     }
 }
