@@ -1665,7 +1665,10 @@ int locohd_wf_integral_points(locohd_ctx* ctx, const locohd_weight_function* wf,
     TRY_ST(make_wf(ctx, *wf, &w));
     WfDev* d_w = nullptr;
     TRY_ST(dev_alloc(ctx, &d_w, 1));
-    CU(ctx, cudaMemcpyAsync(d_w, &w, sizeof w, cudaMemcpyHostToDevice, ctx->stream));
+    if (cudaMemcpyAsync(d_w, &w, sizeof w, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        dev_free(ctx, d_w);
+        return fail(ctx, LOCOHD_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     InBuf<double> in;
     OutBuf<double> o;
     int st = in.load(ctx, x, n);
