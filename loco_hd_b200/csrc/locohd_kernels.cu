@@ -2807,7 +2807,9 @@ static int launch_tiles(const ScoreArgs& args, const KParams& p, unsigned max_a,
     const unsigned grid = (unsigned)(need < (uint64_t)sms ? need : (uint64_t)sms);   // persistent: teams claim units from the cursor
     cudaMemsetAsync(a.cursor, 0, sizeof(unsigned long long), st);
     const uint64_t per_team = units / ((uint64_t)grid * teams * 4);   // short launches: shorter runs even out the tail
-    a.run = (unsigned)(per_team < 1 ? 1 : (per_team > (uint64_t)kTileRun ? (uint64_t)kTileRun : per_team));
+    uint64_t max_run = kTileRun;
+    if (const char* v = std::getenv("LOCOHD_TILE_RUN")) { const int r = std::atoi(v); if (r >= 1 && r <= 4096) max_run = (uint64_t)r; }   // sweeps
+    a.run = (unsigned)(per_team < 1 ? 1 : (per_team > max_run ? max_run : per_team));
     auto go = [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         kernel<<<grid, teams * kTeamThreads, smem, st>>>(a, p, teams, team_bytes);
