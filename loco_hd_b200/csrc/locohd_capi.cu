@@ -31,6 +31,9 @@ struct locohd_ctx {
     std::string err;
     uint64_t launches = 0;
     uint64_t tile_launches = 0;
+    // grouping of the last job list into tiles (a benchmark step, the next block of frames: the same list again)
+    std::vector<locohd_job> tile_cache_jobs;
+    std::vector<ScoreTile> tile_cache_tiles;
     bool has_params = false;
     KParams kp{};
     int n_categories = 0;
@@ -1428,8 +1431,15 @@ int locohd_score_jobs_stats(locohd_ctx* ctx, const locohd_envset* a, const locoh
     uint64_t n_tiles = 0;
     if (uniform && n_per_job && n_jobs >= 4 && !wf_idx && a->key_is_w && b->key_is_w &&
         score_tiles_applicable(ctx->kp, a->max_count, b->max_count, 1)) {
-        tiles = group_job_tiles(hj, joff);                                      // the list order itself (blocked_pairs)
-        if (!tiles_pay(tiles, n_jobs)) tiles = group_job_tiles_sorted(hj, joff);   // any other order
+        if (ctx->tile_cache_jobs.size() == hj.size() &&
+            std::memcmp(ctx->tile_cache_jobs.data(), hj.data(), hj.size() * sizeof(locohd_job)) == 0) {
+            tiles = ctx->tile_cache_tiles;   // the list of the previous call: 2 ms instead of 25 for 500 000 jobs
+        } else {
+            tiles = group_job_tiles(hj, joff);                                      // the list order itself (blocked_pairs)
+            if (!tiles_pay(tiles, n_jobs)) tiles = group_job_tiles_sorted(hj, joff);   // any other order
+            ctx->tile_cache_jobs = hj;
+            ctx->tile_cache_tiles = tiles;
+        }
         if (tiles_pay(tiles, n_jobs)) {
             n_tiles = tiles.size();
             if ((st = dtiles.load(ctx, tiles.data(), n_tiles))) return cleanup(st);
