@@ -2171,19 +2171,36 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
 #pragma unroll
         for (int w = 0; w < HW; ++w) { hA[w] = 0; hB[w] = 0; }
         bool unknown = valid && ((catA0 >= (uint32_t)C) || (catB0 >= (uint32_t)C));
-        for (uint32_t x = i; x < i1; ++x) {
-            const uint32_t c = reinterpret_cast<const uint8_t*>(kA + x)[0];
-            unknown |= c >= (uint32_t)C;
-            const unsigned long long one = 1ull << (8u * (c & 7u));
+        if constexpr (HW == 1) {
+            // No test per event: the increment of a category >= 8 is shifted out of the word (shl.b64 clamps the shift
+            // amount), one in [C, 8) lands in a field that has to stay empty - both are found after the loops, from the
+            // sum of the fields (<= 128 events per chunk: no carry between them) and the fields from C on.
+            auto bump = [](unsigned long long& hh, uint32_t c) {
+                unsigned long long one;
+                asm("shl.b64 %0, %1, %2;" : "=l"(one) : "l"(1ull), "r"(8u * c));
+                hh += one;
+            };
+            for (uint32_t x = i; x < i1; ++x) bump(hA[0], reinterpret_cast<const uint8_t*>(kA + x)[0]);
+            for (uint32_t x = j; x < j1; ++x) bump(hB[0], reinterpret_cast<const uint8_t*>(kB + x)[0]);
+            const unsigned long long hs = hA[0] + hB[0];
+            const uint32_t counted = (uint32_t)((hs * 0x0101010101010101ull) >> 56);
+            unknown |= counted != (i1 - i) + (j1 - j);
+            unknown |= C < 8 && (hs >> (8 * C)) != 0ull;
+        } else {
+            for (uint32_t x = i; x < i1; ++x) {
+                const uint32_t c = reinterpret_cast<const uint8_t*>(kA + x)[0];
+                unknown |= c >= (uint32_t)C;
+                const unsigned long long one = 1ull << (8u * (c & 7u));
 #pragma unroll
-            for (int w = 0; w < HW; ++w) hA[w] += (HW == 1 || (int)((c >> 3) & (HW - 1)) == w) ? one : 0ull;
-        }
-        for (uint32_t x = j; x < j1; ++x) {
-            const uint32_t c = reinterpret_cast<const uint8_t*>(kB + x)[0];
-            unknown |= c >= (uint32_t)C;
-            const unsigned long long one = 1ull << (8u * (c & 7u));
+                for (int w = 0; w < HW; ++w) hA[w] += ((int)((c >> 3) & (HW - 1)) == w) ? one : 0ull;
+            }
+            for (uint32_t x = j; x < j1; ++x) {
+                const uint32_t c = reinterpret_cast<const uint8_t*>(kB + x)[0];
+                unknown |= c >= (uint32_t)C;
+                const unsigned long long one = 1ull << (8u * (c & 7u));
 #pragma unroll
-            for (int w = 0; w < HW; ++w) hB[w] += (HW == 1 || (int)((c >> 3) & (HW - 1)) == w) ? one : 0ull;
+                for (int w = 0; w < HW; ++w) hB[w] += ((int)((c >> 3) & (HW - 1)) == w) ? one : 0ull;
+            }
         }
         if (__any_sync(kFull, unknown)) { raise(P.err, LOCOHD_ERR_UNKNOWN_CATEGORY); continue; }  // pmf.rs:38-42
         int mism = 0;
