@@ -2250,6 +2250,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
         uint32_t pa = smem_u32(kA + i), pb = smem_u32(kB + j);
         const uint32_t dA = ratio_base + 8u * totA - pa, dB = ratio_base + 8u * totB - pb;
         uint64_t ra = lds_u64(pa), rb = lds_u64(pb);
+#pragma unroll 2
         for (uint32_t it = 0; it < nev; ++it) {
             const bool takeA = ra <= (rb | kCatMask);   // == (ra & kWMask) <= (rb & kWMask)
             const uint64_t raw = takeA ? ra : rb;
