@@ -2265,7 +2265,10 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
             const uint32_t ka = word & 0xffffu, kb = word >> 16;
             const uint32_t mine_k = takeA ? ka : kb, other_k = takeA ? kb : ka;
             sts_u32_rmw(ca, word + (takeA ? 1u : 0x10000u));
-            mism += (mine_k == other_k ? 1 : 0) - (mine_k + 1u == other_k ? 1 : 0);
+            {   // the category's counts were equal before (d == 0: one more mismatch) or are equal now (d == -1: one less)
+                const uint32_t t = mine_k - other_k + 1u;
+                if (t < 2u) mism += 2 * (int)t - 1;
+            }
             const uint32_t pk = takeA ? pa : pb;
             D = fma(lds_f64(dsq_addr(mine_k)), lds_f64(sq_addr(other_k)), D);
             R *= lds_f64(pk + (takeA ? dA : dB));
