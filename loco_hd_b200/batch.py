@@ -245,3 +245,73 @@ def trajectory_scores(lchd, topology, categories, tags, frame0_atoms, frame_bloc
         if env0 is not None:
             env0.close()
         st.close()
+
+
+def pair_anchors_by_tag(ref_cat, ref_tag, model_cat, model_tag, anchor_category: int) -> np.ndarray:
+    """Anchor pairs (reference index, model index) of one model: every reference primitive of the anchor category
+    whose tag also carries an anchor primitive in the model, in reference order - the pairing loop of
+    casp14_extend_with_locohd.py:48,66-79 (a model may lack residues; a tag that occurs twice in the model pairs
+    with its last anchor primitive, as the caller's dict comprehension does)."""
+    ref_cat, model_cat = np.asarray(ref_cat), np.asarray(model_cat)
+    ref_tag, model_tag = np.asarray(ref_tag), np.asarray(model_tag)
+    ref_anchor = np.flatnonzero(ref_cat == anchor_category)
+    model_anchor = np.flatnonzero(model_cat == anchor_category)
+    if len(ref_anchor) == 0 or len(model_anchor) == 0:
+        return np.zeros((0, 2), dtype=np.uint32)
+    mt = model_tag[model_anchor]
+    order = np.argsort(mt, kind="stable")
+    mt_sorted = mt[order]
+    pos = np.searchsorted(mt_sorted, ref_tag[ref_anchor], side="right") - 1      # last occurrence
+    hit = (pos >= 0) & (mt_sorted[np.maximum(pos, 0)] == ref_tag[ref_anchor])
+    return np.stack([ref_anchor[hit], model_anchor[order[pos[hit]]]], axis=1).astype(np.uint32)
+
+
+def models_against_reference(lchd, reference, models, anchor_category: int, threshold: float):
+    """One reference structure against many models of it, per-residue scores and the per-model mean: the loop of
+    casp14_extend_with_locohd.py:44-88 (BASELINE config 3) as one resident batch - the reference is uploaded once,
+    all environments come from two gather launches and all models are scored by one call; the per-model means are
+    reduced on the device.
+
+    lchd             a loco_hd.LoCoHD instance (public class)
+    reference        (xyz [n, 3], category ids uint16, tag ids uint32) - LoCoHD.to_arrays(list of PrimitiveAtom)
+    models           sequence of such triples; sizes and residue sets may differ from the reference's
+    anchor_category  category id of the anchor primitives (lchd.category_ids(["Cent"])[0])
+
+    Returns a list with one (anchor_pairs [p, 2] uint32, scores [p] float64, mean float) per model; a model without
+    common anchors gets empty arrays and nan."""
+    models = list(models)
+    if not models:
+        return []
+    rx, rc, rt = (np.asarray(v) for v in reference)
+    pairs = [pair_anchors_by_tag(rc, rt, m[1], m[2], anchor_category) for m in models]
+    sizes = [len(rc)] + [len(m[1]) for m in models]
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    f32 = all(np.asarray(v[0]).dtype == np.float32 for v in [reference] + models)
+    xyz = np.concatenate([np.asarray(v[0], dtype=np.float32 if f32 else np.float64).reshape(-1, 3)
+                          for v in [reference] + models])
+    cats = np.concatenate([np.asarray(v[1], dtype=np.uint16) for v in [reference] + models])
+    tags = np.concatenate([np.asarray(v[2], dtype=np.uint32) for v in [reference] + models])
+    counts = np.array([len(p) for p in pairs], dtype=np.uint64)
+    scored = np.flatnonzero(counts)
+    out = [(p, np.zeros(0), float("nan")) for p in pairs]
+    if len(scored) == 0:
+        return out
+    a_prim = np.concatenate([pairs[k][:, 0] for k in scored])
+    b_prim = np.concatenate([pairs[k][:, 1] for k in scored])
+    b_struct = np.repeat((scored + 1).astype(np.uint32), counts[scored].astype(np.int64))
+    first = np.concatenate([[0], np.cumsum(counts[scored])[:-1]]).astype(np.uint64)
+    jobs = np.stack([first, first, counts[scored]], axis=1).astype(np.uint64)
+    st = lchd.structures(offsets, xyz, cats, tags)
+    env_a = env_b = None
+    try:
+        env_a = lchd.environments(st, a_prim, threshold, anchor_struct=np.zeros(len(a_prim), dtype=np.uint32))
+        env_b = lchd.environments(st, b_prim, threshold, anchor_struct=b_struct)
+        red = lchd.score_batch(env_a, env_b, jobs, reduce=["scores", "job_mean"])
+    finally:
+        for h in (env_a, env_b, st):
+            if h is not None:
+                h.close()
+    for n, k in enumerate(scored):
+        lo = int(first[n])
+        out[k] = (pairs[k], red["scores"][lo:lo + int(counts[k])], float(red["job_mean"][n]))
+    return out

@@ -199,6 +199,50 @@ def test_public_class_resident_batch_equals_per_call_api(oracle_mod):
         obj.close()
 
 
+def test_models_against_reference_helper(oracle_mod):
+    """batch.models_against_reference (the loop of casp14_extend_with_locohd.py:44-88 as one resident batch): models that
+    lack residues or list them in another order, anchors paired by tag; per-residue scores against the per-model
+    from_arrays calls and against the oracle, the per-model mean against numpy."""
+    import loco_hd
+    from loco_hd_b200 import batch
+
+    ref = synth.gen(5, 120, 9, 8, with_centroid=True)
+    lchd = loco_hd.LoCoHD([f"T{i}" for i in range(8)], loco_hd.WeightFunction("uniform", [3.0, 10.0]),
+                          loco_hd.TagPairingRule({"accept_same": False}))
+    op = oracle_mod.Params(8, [("uniform", [3.0, 10.0])], tag_rule={"accept_same": False})
+    rng = np.random.default_rng(17)
+    models = []
+    for m in range(5):
+        full = synth.config3_model(ref, m)
+        res = np.arange(120)
+        if m == 1:
+            res = res[rng.random(120) < 0.85]                 # missing residues
+        if m == 2:
+            res = rng.permutation(res)                        # another residue order
+        if m == 3:
+            res = res[:0]                                     # nothing in common: no anchors
+        idx = (res[:, None] * 9 + np.arange(9)[None, :]).ravel()
+        tag = full.tag[idx] if m != 3 else full.tag[:18] + 1000
+        idx = idx if m != 3 else np.arange(18)
+        models.append((full.xyz[idx], full.cat[idx], tag.astype(np.uint32)))
+    cent = int(ref.centroid_cat)
+    out = batch.models_against_reference(lchd, (ref.xyz, ref.cat, ref.tag), models, cent, 10.0)
+    assert len(out) == 5
+    for m, (pairs, scores, mean) in enumerate(out):
+        mx, mc, mt = models[m]
+        if m == 3:
+            assert len(pairs) == 0 and len(scores) == 0 and np.isnan(mean)
+            continue
+        assert len(pairs) == (120 if m != 1 else len(np.unique(mt)))
+        assert np.all(ref.cat[pairs[:, 0]] == cent) and np.all(mc[pairs[:, 1]] == cent)
+        assert np.array_equal(ref.tag[pairs[:, 0]], mt[pairs[:, 1]])
+        per_call = lchd.from_arrays(ref.xyz, ref.cat, ref.tag, mx, mc, mt, pairs, 10.0)
+        assert np.abs(scores - per_call).max() <= 1e-12
+        want = oracle_mod.from_primitives(op, ref.xyz, ref.cat, ref.tag, mx, mc, mt, pairs, 10.0)
+        assert_scores_close(scores, want)
+        assert abs(mean - want.mean()) <= SCORE_TOL
+
+
 def test_from_arrays_with_tag_pair_list_rule():
     """from_arrays accepts a WithList rule when the integer tags come from intern_tags (N1)."""
     import loco_hd

@@ -121,3 +121,104 @@ def test_combine_anchor_stats_pools_exactly():
     mean, std = batch.combine_anchor_stats([len(q) for q in parts], [q.mean(axis=0) for q in parts],
                                            [q.std(axis=0) for q in parts])
     assert np.abs(mean - x.mean(axis=0)).max() < 1e-15 and np.abs(std - x.std(axis=0)).max() < 1e-15
+
+
+def test_pair_anchors_by_tag_is_the_callers_pairing_loop():
+    """batch.pair_anchors_by_tag against the dict-based pairing of casp14_extend_with_locohd.py:48,66-79, on models
+    that lack residues, carry extra ones, list them in another order and repeat a tag."""
+    rng = np.random.default_rng(11)
+    cent = 7
+    for trial in range(20):
+        n_res = int(rng.integers(1, 40))
+        k = int(rng.integers(1, 5))
+        ref_tag = np.repeat(rng.permutation(100)[:n_res], k).astype(np.uint32)
+        ref_cat = rng.integers(0, 7, n_res * k)
+        ref_cat[::k] = cent
+        keep = rng.random(n_res) < 0.8
+        m_res = np.concatenate([np.unique(ref_tag)[rng.permutation(n_res)][: int(keep.sum())], [200, 201]])
+        if trial % 3 == 0 and len(m_res) > 2:
+            m_res = np.concatenate([m_res, m_res[:1]])            # a tag that occurs twice in the model
+        model_tag = np.repeat(m_res, k).astype(np.uint32)
+        model_cat = rng.integers(0, 7, len(model_tag))
+        model_cat[::k] = cent
+        lut = {int(model_tag[i]): i for i in range(len(model_tag)) if model_cat[i] == cent}
+        want = [(i, lut[int(ref_tag[i])]) for i in range(len(ref_tag)) if ref_cat[i] == cent and int(ref_tag[i]) in lut]
+        got = batch.pair_anchors_by_tag(ref_cat, ref_tag, model_cat, model_tag, cent)
+        assert got.dtype == np.uint32 and got.shape == (len(want), 2)
+        assert got.tolist() == [list(p) for p in want]
+    assert batch.pair_anchors_by_tag([1, 2], [0, 1], [3], [0], 7).shape == (0, 2)
+    assert batch.models_against_reference(None, ([], [], []), [], 7, 10.0) == []
+
+
+class _OracleBackedLoCoHD:
+    """Stand-in for the public class with the resident-batch methods answered by the CPU oracle (TEST ONLY): lets the
+    host-side logic of batch.models_against_reference run without a device."""
+
+    def __init__(self, oracle_mod, params):
+        self.o, self.p = oracle_mod, params
+
+    class _H:
+        def __init__(self, **kw):
+            self.__dict__.update(kw)
+            self.closed = False
+
+        def close(self):
+            self.closed = True
+
+    def structures(self, offsets, xyz, cats, tags):
+        assert len(xyz) == len(cats) == len(tags) == int(offsets[-1])
+        self.last = self._H(off=np.asarray(offsets, dtype=np.int64), xyz=np.asarray(xyz, dtype=np.float64), cat=cats, tag=tags)
+        return self.last
+
+    def environments(self, st, prim, thr, anchor_struct=None):
+        return self._H(st=st, prim=np.asarray(prim), struct=np.asarray(anchor_struct), thr=thr)
+
+    def score_batch(self, ea, eb, jobs, reduce=None):
+        scores, means = [], []
+        for a0, b0, n in np.asarray(jobs, dtype=np.int64):
+            s = []
+            for i in range(n):
+                sa, sb = int(ea.struct[a0 + i]), int(eb.struct[b0 + i])
+                A = slice(ea.st.off[sa], ea.st.off[sa + 1])
+                B = slice(eb.st.off[sb], eb.st.off[sb + 1])
+                # anchors inside a structure are indices into that structure
+                s.append(self.o.from_primitives(self.p, ea.st.xyz[A], ea.st.cat[A], ea.st.tag[A], eb.st.xyz[B], eb.st.cat[B],
+                                                eb.st.tag[B], [(int(ea.prim[a0 + i]), int(eb.prim[b0 + i]))], ea.thr)[0])
+            scores += s
+            means.append(np.mean(s))
+        return {"scores": np.array(scores), "job_mean": np.array(means)}
+
+
+def test_models_against_reference_host_logic(oracle_mod):
+    """The job / anchor bookkeeping of batch.models_against_reference (casp14_extend_with_locohd.py:44-88) with the
+    device calls answered by the oracle: per-model scores equal the per-model from_primitives calls."""
+    from benchdata import synth
+
+    ref = synth.gen(5, 30, 5, 8, with_centroid=True)
+    rng = np.random.default_rng(17)
+    models = []
+    for m in range(4):
+        full = synth.config3_model(ref, m)
+        res = np.arange(30)
+        if m == 1:
+            res = res[rng.random(30) < 0.8]
+        if m == 2:
+            res = rng.permutation(res)
+        idx = (res[:, None] * 5 + np.arange(5)[None, :]).ravel()
+        if m == 3:
+            models.append((full.xyz[:10], full.cat[:10], (full.tag[:10] + 1000).astype(np.uint32)))
+        else:
+            models.append((full.xyz[idx], full.cat[idx], full.tag[idx]))
+    op = oracle_mod.Params(8, [("uniform", [3.0, 10.0])], tag_rule={"accept_same": False})
+    fake = _OracleBackedLoCoHD(oracle_mod, op)
+    out = batch.models_against_reference(fake, (ref.xyz, ref.cat, ref.tag), models, int(ref.centroid_cat), 10.0)
+    assert fake.last.closed
+    assert [len(p) for p, _, _ in out] == [30, len(np.unique(models[1][2])), 30, 0]
+    for m, (pairs, scores, mean) in enumerate(out):
+        if m == 3:
+            assert len(scores) == 0 and np.isnan(mean)
+            continue
+        mx, mc, mt = models[m]
+        assert np.array_equal(ref.tag[pairs[:, 0]], mt[pairs[:, 1]])
+        want = oracle_mod.from_primitives(op, ref.xyz, ref.cat, ref.tag, mx, mc, mt, pairs, 10.0)
+        assert np.array_equal(scores, want) and mean == pytest.approx(want.mean(), abs=1e-15)
