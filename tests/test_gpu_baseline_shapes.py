@@ -199,6 +199,33 @@ def test_public_class_resident_batch_equals_per_call_api(oracle_mod):
         obj.close()
 
 
+def test_ensemble_callers_dmx_form_equals_the_cutoff_form(gpu_ctx, oracle_mod):
+    """compare_ensembles.py:250-296 calls from_dmxs on full distance matrices with +inf at homo-residue entries; the
+    benchmark states the same computation as the cutoff form (threshold 10, hetero contacts).  Both forms on the GPU,
+    against each other and against the oracle (uniform [3, 10] is constant from the cutoff on)."""
+    base = synth.gen(9, 60, 8, 7)
+    a, b = synth.config5_member(base, 0), synth.config5_member(base, 1)
+    op = set_both(gpu_ctx, oracle_mod, 7, [("uniform", (3.0, 10.0))], tag_rule={"accept_same": False})
+    anchors = np.stack([np.arange(a.n)] * 2, axis=1).astype(np.uint32)
+    cut = gpu_ctx.from_primitives(a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, 10.0)
+    want = oracle_mod.from_primitives(op, a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, 10.0)
+    assert_scores_close(cut, want)
+
+    def dmx(c):
+        d = c.xyz[None, :, :] - c.xyz[:, None, :]
+        d = np.sqrt(np.sum(d ** 2, axis=2))
+        same = c.tag[:, None] == c.tag[None, :]
+        np.fill_diagonal(same, False)
+        d[same] = np.inf
+        return d
+
+    ea, eb = gpu_ctx.envset_from_rows(dmx(a), a.cat), gpu_ctx.envset_from_rows(dmx(b), b.cat)
+    full = gpu_ctx.score_pairs(ea, eb, anchors)
+    ea.close(); eb.close()
+    assert_scores_close(full, want)
+    assert np.abs(full - cut).max() <= 1e-12
+
+
 def test_models_against_reference_helper(oracle_mod):
     """batch.models_against_reference (the loop of casp14_extend_with_locohd.py:44-88 as one resident batch): models that
     lack residues or list them in another order, anchors paired by tag; per-residue scores against the per-model

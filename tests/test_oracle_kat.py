@@ -119,3 +119,28 @@ def test_constructor_level_errors(oracle_mod):
         oracle_mod.from_anchors(p, [0, 1], [0], [0.1, 1.0], [0.0])
     with pytest.raises(oracle_mod.OracleError):  # pmf.rs:38-42
         oracle_mod.from_anchors(p, [0, 5], [0], [0.0, 1.0], [0.0])
+
+
+def test_ensemble_callers_dmx_form_equals_the_cutoff_form(oracle_mod):
+    """compare_ensembles.py:250-296 scores an ensemble with from_dmxs on full distance matrices whose homo-residue
+    entries are set to +inf; BASELINE config 5 states the same computation as from_primitives with threshold 10 and
+    the rule {"accept_same": False}.  With uniform [3, 10] the weight function is constant from 10 on, so members at or
+    beyond the cutoff (and the banned ones at +inf) carry zero weight: the two forms give identical scores."""
+    from benchdata import synth
+
+    base = synth.gen(9, 40, 8, 7)
+    a, b = synth.config5_member(base, 0), synth.config5_member(base, 1)
+    p = oracle_mod.Params(7, [("uniform", [3.0, 10.0])], tag_rule={"accept_same": False})
+    anchors = np.stack([np.arange(a.n)] * 2, axis=1).astype(np.uint32)
+    cut = oracle_mod.from_primitives(p, a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, 10.0)
+
+    def dmx(c):
+        d = c.xyz[None, :, :] - c.xyz[:, None, :]
+        d = np.sqrt(np.sum(d ** 2, axis=2))
+        same = c.tag[:, None] == c.tag[None, :]
+        np.fill_diagonal(same, False)
+        d[same] = np.inf                                      # "Ban homo-residue contacts"
+        return d
+
+    full = oracle_mod.from_dmxs(oracle_mod.Params(7, [("uniform", [3.0, 10.0])]), a.cat, b.cat, dmx(a), dmx(b))
+    assert np.abs(full - cut).max() <= 1e-15
