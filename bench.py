@@ -255,8 +255,9 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def oracle_run_jobs(oracle, op, wl, job_ids, n_threads=0):
-    """The CPU restatement on a set of jobs; returns (anchor pairs, seconds, walk steps, env members)."""
+def oracle_run_jobs(oracle, op, wl, job_ids, n_threads=0, collect=None):
+    """The CPU restatement on a set of jobs; returns (anchor pairs, seconds, walk steps, env members); the per-anchor
+    scores of every job are appended to `collect` when given."""
     pairs, steps, members = 0, 0, 0
     t0 = time.perf_counter()
     for j in job_ids:
@@ -266,6 +267,8 @@ def oracle_run_jobs(oracle, op, wl, job_ids, n_threads=0):
         pairs += len(anchors)
         steps += int(r["steps"].sum())
         members += int(r["env_sizes"].sum())
+        if collect is not None:
+            collect.append(r["scores"])
     return pairs, time.perf_counter() - t0, steps, members
 
 
@@ -642,7 +645,7 @@ def run_gpu(args, rank, local_rank, world):
                "fill": ("env_fused_kernel (K1: row pruning, exact FP64 gather, register bitonic sort, CDF, packing)",
                         f_gather),
                "count": ("env_tile_kernel<false> with stride 16 (store sizing sample)", 0.0)}
-    traffic, pipes, prof_src = {}, {}, None
+    traffic, pipes, prof_src, traffic_note = {}, {}, None, None
     for tf in sorted((ROOT / "profiles").glob("*_traffic.json"), reverse=True):   # newest round first
         try:
             tr = json.loads(tf.read_text())
@@ -652,6 +655,7 @@ def run_gpu(args, rank, local_rank, world):
             traffic = tr.get("dram_bytes_per_launch", {})
             pipes = tr.get("pipes", {})
             prof_src = tr.get("source")
+            traffic_note = tr.get("note")
             break
     per_kernel = {}
     for g, (name, flops) in alg.items():
@@ -683,7 +687,8 @@ def run_gpu(args, rank, local_rank, world):
                         "x 2 x 1.965 GHz = 37.2)"),
         "peak_probe": {"tflops": fp64_peak, "clocks": probe_info},
         "traffic": traffic.get(dom), "alg_flops_per_launch": dom_flops, "launch_ms": dom_ms,
-        "note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch from profiles/ (ncu)",
+        "note": "traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch from profiles/ (ncu)"
+                + (f"; {traffic_note}" if traffic_note else ""),
     }
     roofline_hbm = {"bound": "hbm", "achieved": alg_bytes / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
@@ -703,19 +708,28 @@ def run_gpu(args, rank, local_rank, world):
         ids = sample_jobs(wl, args.cpu_pairs)   # ~10 s of CPU work on 16 threads
         cores = host_threads()
         oracle_run_jobs(oracle, op, wl, ids[:1], n_threads=cores)
-        p, dt, steps, members = oracle_run_jobs(oracle, op, wl, ids, n_threads=cores)
+        cpu_scores = []
+        p, dt, steps, members = oracle_run_jobs(oracle, op, wl, ids, n_threads=cores, collect=cpu_scores)
         ids1 = sample_jobs(wl, max(1, args.ref_pairs // 16))
         p1, dt1, _, _ = oracle_run_jobs(oracle, op, wl, ids1, n_threads=1)
         # the sample doubles as a parity spot check of this very run
         a, b, anchors = wl.job_arrays(0)
         ref = oracle.from_primitives(op, a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, wl.threshold)
         n0 = int(wl.jobs["n"][0])
+        # ... and every job of the timed sample against this run's GPU results (on the default workload: the first 200
+        # structure pairs = 13 tiles, all 5000 anchors of each, i.e. every anchor slice of the tile kernel's unit order)
+        if means_only:
+            sample_diff = max(abs(float(sc.mean()) - float(check_scores[j])) for j, sc in zip(ids, cpu_scores))
+        else:
+            offs = np.concatenate([[0], np.cumsum(wl.jobs["n"][:len(ids)])]).astype(np.int64)
+            sample_diff = max(float(np.abs(sc - check_scores[offs[k]:offs[k + 1]]).max()) for k, sc in enumerate(cpu_scores))
         cpu = {"value": p / dt, "unit": "anchor-pairs/s", "cores": cores, "kind": "port",
                "sample": f"first {len(ids)} structure pair(s) of the step = {p} anchor pairs, {dt:.2f} s",
                "single_thread_value": p1 / dt1,
                "walk_steps_per_pair": steps / p, "env_members_per_pair": members / p,
                ("max_abs_mean_score_diff_vs_gpu_job0" if means_only else "max_abs_score_diff_vs_gpu_job0"):
                    float(abs(ref.mean() - check_scores[0]) if means_only else np.abs(ref - check_scores[:n0]).max()),
+               ("max_abs_mean_score_diff_vs_gpu_sample" if means_only else "max_abs_score_diff_vs_gpu_sample"): sample_diff,
                "note": "C++/OpenMP restatement of the reference algorithm (Rust toolchain unavailable)"}
 
     # ---- the other BASELINE configurations, one short run each (N = 1 only), and the Python API

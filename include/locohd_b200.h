@@ -232,6 +232,14 @@ int locohd_score_jobs_stats(locohd_ctx* ctx, const locohd_envset* a, const locoh
  * >= 60 % of the row cells used, >= 3 rows per tile).  Whether a call then takes the tile kernel also depends on the
  * instance (Hellinger-2, unit category weights, one weight function) and on the environment sizes. */
 int locohd_plan_job_tiles(uint64_t n_jobs, const locohd_job* jobs, uint64_t* out_tiles, uint64_t* out_rows, int* out_pays);
+/* Planning query, no device needed: position `unit` of a tile launch of n_tiles tiles with n_anchors anchors per job
+ * -> the (tile, anchor) scored there.  The tile kernel visits all tiles for one slice of `slice` consecutive anchors
+ * before the next slice starts, so that the environments of a slice stay in L2 while the tiles pass over them
+ * (slice = 0 or >= n_anchors: tile-major order; the library picks the slice from the size of the environment store,
+ * LOCOHD_TILE_SLICE / LOCOHD_TILE_SLICE_MB in the environment override it).  LOCOHD_ERR_BAD_PARAM for a unit out of
+ * range. */
+int locohd_tile_unit(uint64_t n_tiles, uint64_t n_anchors, uint64_t slice, uint64_t unit, uint64_t* out_tile,
+                     uint64_t* out_anchor);
 /* from_anchors (locohd.rs:392-406): one pair of caller-ordered environments, walked in the reference's
  * exact three-way-merge order (the lists are NOT required to be sorted, as in the reference). */
 int locohd_score_anchor_lists(locohd_ctx* ctx, const uint16_t* seq_a, uint64_t len_a, const double* dists_a,

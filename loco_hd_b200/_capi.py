@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "locohd_envset_from_ragged_rows",
     "locohd_envset_from_coords", "locohd_envset_destroy", "locohd_envset_size", "locohd_envset_total_members",
     "locohd_envset_dump", "locohd_score_pairs", "locohd_score_jobs", "locohd_score_jobs_stats",
-    "locohd_score_anchor_lists", "locohd_plan_job_tiles",
+    "locohd_score_anchor_lists", "locohd_plan_job_tiles", "locohd_tile_unit",
     "locohd_from_primitives", "locohd_wf_integral_points", "locohd_sd_run",
 ]
 
@@ -123,6 +123,7 @@ def load_library() -> C.CDLL:
         "locohd_score_jobs_stats": (C.c_int, [vp, vp, vp, u64, vp, vp, vp, vp, vp, vp]),
         "locohd_score_anchor_lists": (C.c_int, [vp, vp, u64, vp, u64, vp, u64, vp, u64, u32, vp]),
         "locohd_plan_job_tiles": (C.c_int, [u64, vp, vp, vp, vp]),
+        "locohd_tile_unit": (C.c_int, [u64, u64, u64, u64, C.POINTER(u64), C.POINTER(u64)]),
         "locohd_from_primitives": (C.c_int, [vp, u64, vp, vp, vp, u64, vp, vp, vp, u64, vp, vp, dbl, vp]),
         "locohd_wf_integral_points": (C.c_int, [vp, C.POINTER(WeightFunctionC), u64, vp, vp]),
         "locohd_sd_run": (C.c_int, [vp, i32, vp, i32, u64, vp, vp, vp]),
@@ -160,6 +161,15 @@ def plan_job_tiles(jobs) -> dict:
     if st:
         raise LocoHDError(st, "locohd_plan_job_tiles failed")
     return {"tiles": int(tiles.value), "rows": int(rows.value), "pays": bool(pays.value)}
+
+
+def tile_unit(n_tiles: int, n_anchors: int, slice_: int, unit: int):
+    """(tile, anchor) at position `unit` of a tile launch (locohd_tile_unit; host-side, no device)."""
+    t, p = C.c_uint64(), C.c_uint64()
+    st = load_library().locohd_tile_unit(n_tiles, n_anchors, slice_, unit, C.byref(t), C.byref(p))
+    if st:
+        raise LocoHDError(st, "locohd_tile_unit")
+    return int(t.value), int(p.value)
 
 
 def make_wf(name: str, params: Sequence[float]) -> WeightFunctionC:

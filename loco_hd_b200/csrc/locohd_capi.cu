@@ -1375,6 +1375,20 @@ int locohd_plan_job_tiles(uint64_t n_jobs, const locohd_job* jobs, uint64_t* out
     }
 }
 
+int locohd_tile_unit(uint64_t n_tiles, uint64_t n_anchors, uint64_t slice, uint64_t unit, uint64_t* out_tile,
+                     uint64_t* out_anchor) {
+    if (!out_tile || !out_anchor || n_anchors == 0 || n_tiles > (~0ull) / n_anchors || unit >= n_tiles * n_anchors)
+        return LOCOHD_ERR_BAD_PARAM;
+    const TileOrder o = make_tile_order(n_tiles, n_anchors, slice);
+    tile_unit<uint64_t>(o, unit, out_tile, out_anchor);
+    if (((n_tiles * n_anchors) >> 32) == 0) {   // the kernel's 32-bit path must agree
+        uint32_t t32 = 0, p32 = 0;
+        tile_unit<uint32_t>(o, (uint32_t)unit, &t32, &p32);
+        if (t32 != *out_tile || p32 != *out_anchor) return LOCOHD_ERR_CUDA;
+    }
+    return LOCOHD_OK;
+}
+
 int locohd_score_jobs(locohd_ctx* ctx, const locohd_envset* a, const locohd_envset* b, uint64_t n_jobs,
                       const locohd_job* jobs, const uint32_t* wf_idx, double* out_scores, double* out_job_means) {
     return locohd_score_jobs_stats(ctx, a, b, n_jobs, jobs, wf_idx, out_scores, out_job_means, nullptr, nullptr);

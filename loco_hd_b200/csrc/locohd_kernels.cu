@@ -1985,9 +1985,10 @@ __host__ __device__ inline int tile_team_bytes(int CP, int stage_keys) {
 
 struct TileCtrl {         // written by the team's loader warp between the two team barriers of an iteration
     uint64_t mbar;
-    uint64_t tile;
-    uint32_t p;           // anchor inside the jobs of the tile
+    uint32_t tile[2];     // tile and anchor (inside the jobs of the tile) of the current unit and of the next one:
+    uint32_t p[2];        // written by fetch() one iteration ahead, slot = iteration & 1
     uint32_t state;       // 0 = score, 1 = skip (an error was raised), 2 = no units left
+    uint32_t pad;
     uint32_t start[2 * kTileDim];   // stage position of rows 0..3, columns 0..3
     uint32_t M[2 * kTileDim];       // their sizes (0: absent)
 };
@@ -2030,7 +2031,7 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
     uint64_t* stage = reinterpret_cast<uint64_t*>(mine + CP * kTeamThreads * 4 + kTileCtrlBytes);
     const bool loader = row == 0;
     if (loader && lane == 0) { mbar_init(&ctrl->mbar, 1); fence_proxy_async(); }
-    unsigned mbar_parity = 0;
+    unsigned flags = 0;   // bit 0: parity of the team's mbarrier, bit 1: control-block slot of the NEXT fetch
     const uint32_t sq_base = __shfl_sync(kFull, smem_u32(s_sqrt), lane);
     const uint32_t dsq_base = __shfl_sync(kFull, smem_u32(s_dsq), lane);
     const uint32_t ratio_base = __shfl_sync(kFull, smem_u32(s_ratio), lane);
@@ -2077,8 +2078,11 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
         nx_unit = u; nx_off = 0; nx_M = 0; nx_last = 0; nx_present = false;
         if (u < n_units && lane < 2 * kTileDim) {
             uint64_t tile, p;
-            if (((n_units | n) >> 32) == 0) { tile = (uint32_t)u / (uint32_t)n; p = (uint32_t)u - (uint32_t)tile * (uint32_t)n; }
-            else { tile = u / n; p = u - tile * n; }
+            // unit -> (tile, anchor) in the sliced order (TileOrder, locohd_kernels.cuh); the team reads them from the
+            // control block's slot of the unit's iteration (two slots: this fetch runs while the current unit is scored)
+            if (((n_units | n) >> 32) == 0) { uint32_t t32, p32; tile_unit<uint32_t>(a.order, (uint32_t)u, &t32, &p32); tile = t32; p = p32; }
+            else tile_unit<uint64_t>(a.order, u, &tile, &p);
+            if (lane == 0) { ctrl->tile[(flags >> 1) & 1u] = (uint32_t)tile; ctrl->p[(flags >> 1) & 1u] = (uint32_t)p; }
             const ScoreTile& T = a.tiles[tile];
             const uint64_t first = lane < kTileDim ? __ldg(T.a_first + lane) : __ldg(T.b_first + (lane - kTileDim));
             if (first != kTileNone) {
@@ -2093,6 +2097,8 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
     if (loader) fetch();
 
     for (;;) {
+        const uint32_t slot = (flags >> 1) & 1u;   // where fetch() left this unit's tile and anchor
+        flags ^= 2u;
         team_barrier(team);   // every warp of the team is done with the stage of the previous unit
         if (loader) {
             const uint64_t u = nx_unit;
@@ -2127,12 +2133,6 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
                     }
                 }
                 if (lane < 2 * kTileDim) { ctrl->start[lane] = start; ctrl->M[lane] = (state == 0 && nx_present) ? nx_M : 0u; }
-                if (lane == 0) {
-                    uint64_t tile;
-                    if (((n_units | n) >> 32) == 0) tile = (uint32_t)u / (uint32_t)n; else tile = u / n;
-                    ctrl->tile = tile;
-                    ctrl->p = (uint32_t)(u - tile * n);
-                }
             }
             if (lane == 0) ctrl->state = state;
         }
@@ -2141,14 +2141,14 @@ __global__ void __launch_bounds__(kTileMaxTeams * kTeamThreads, 1) score_tile_ke
         if (state == 2) break;
         if (loader) fetch();
         if (state == 1) continue;
-        const uint64_t out_first = __ldg(a.tiles[ctrl->tile].out_first + prow * kTileDim + pcol);
+        const uint64_t out_first = __ldg(a.tiles[ctrl->tile[slot]].out_first + prow * kTileDim + pcol);
         const uint32_t Ma = ctrl->M[prow], Mb = ctrl->M[kTileDim + pcol];
-        const uint32_t p = ctrl->p;
+        const uint32_t p = ctrl->p[slot];
         const bool valid = out_first != kTileNone && Ma != 0 && Mb != 0;
         const uint64_t* kA = stage + (valid ? ctrl->start[prow] : 0u);
         const uint64_t* kB = stage + (valid ? ctrl->start[kTileDim + pcol] : 0u);
-        mbar_wait(&ctrl->mbar, mbar_parity);
-        mbar_parity ^= 1u;
+        mbar_wait(&ctrl->mbar, flags & 1u);
+        flags ^= 1u;
         if (!__any_sync(kFull, valid)) continue;
 
         const uint64_t keyA0 = kA[0], keyB0 = kB[0];
@@ -2812,7 +2812,27 @@ bool score_tiles_applicable(const KParams& p, unsigned max_a, unsigned max_b, in
     return tile_geometry(p, max_a, max_b, key_is_w, nullptr, nullptr, nullptr, nullptr) >= 6;
 }
 
-static int launch_tiles(const ScoreArgs& args, const KParams& p, unsigned max_a, unsigned max_b, cudaStream_t st) {
+// Anchors per slice of the unit order (TileOrder): as many as keep the environments of one slice of every structure
+// inside a budget of L2 (126 MB on a B200, in two halves; 32 MB leaves room for the scores written and for the tile
+// descriptors), a multiple of the run length so that a claimed run stays inside one tile.  0 = tile-major order
+// (the whole store fits the budget, or LOCOHD_TILE_SLICE=0).  LOCOHD_TILE_SLICE=<anchors> / LOCOHD_TILE_SLICE_MB=<MB>: sweeps.
+static uint64_t tile_slice(const ScoreArgs& a, double mean_a, double mean_b) {
+    const uint64_t n = a.uniform_n;
+    if (const char* v = std::getenv("LOCOHD_TILE_SLICE")) { const long long s = std::atoll(v); return s <= 0 || (uint64_t)s >= n ? 0 : (uint64_t)s; }
+    double budget = 32.0 * 1048576.0;
+    if (const char* v = std::getenv("LOCOHD_TILE_SLICE_MB")) { const double mb = std::atof(v); if (mb > 0.0) budget = mb * 1048576.0; }
+    const bool same = a.a.key == a.b.key && a.a.off == a.b.off;
+    const double store = 8.0 * ((double)a.a.n_env * (mean_a + 1.0) + (same ? 0.0 : (double)a.b.n_env * (mean_b + 1.0)));
+    if (n == 0 || store <= budget) return 0;
+    const double per_anchor = store / (double)n;           // bytes of environments per anchor index, all structures
+    uint64_t s = (uint64_t)(budget / per_anchor);
+    s = s / kTileRun * kTileRun;
+    if (s < (uint64_t)kTileRun) s = kTileRun;
+    return s >= n ? 0 : s;
+}
+
+static int launch_tiles(const ScoreArgs& args, const KParams& p, unsigned max_a, unsigned max_b, double mean_a, double mean_b,
+                        cudaStream_t st) {
     ScoreArgs a = args;
     int table_n = 0, stage_keys = 0, team_bytes = 0, rep_n = 0;
     const int teams = tile_geometry(p, max_a, max_b, a.a.key_is_w, &table_n, &stage_keys, &team_bytes, &rep_n);
@@ -2833,6 +2853,7 @@ static int launch_tiles(const ScoreArgs& args, const KParams& p, unsigned max_a,
     uint64_t max_run = kTileRun;
     if (const char* v = std::getenv("LOCOHD_TILE_RUN")) { const int r = std::atoi(v); if (r >= 1 && r <= 4096) max_run = (uint64_t)r; }   // sweeps
     a.run = (unsigned)(per_team < 1 ? 1 : (per_team > max_run ? max_run : per_team));
+    a.order = make_tile_order(a.n_tiles, a.uniform_n, tile_slice(a, mean_a, mean_b));
     auto go = [&](auto kernel) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         kernel<<<grid, teams * kTeamThreads, smem, st>>>(a, p, teams, team_bytes);
@@ -2845,7 +2866,7 @@ static int launch_tiles(const ScoreArgs& args, const KParams& p, unsigned max_a,
 int launch_score(const ScoreArgs& args, const KParams& p, unsigned max_a, unsigned max_b, double mean_a, double mean_b,
                  cudaStream_t st) {
     if (!args.n_pairs) return 0;
-    if (args.tiles) return launch_tiles(args, p, max_a, max_b, st);
+    if (args.tiles) return launch_tiles(args, p, max_a, max_b, mean_a, mean_b, st);
     const unsigned pad_max = ((max_a + 1) & ~1u) + ((max_b + 1) & ~1u);
     const bool key_is_w = args.a.key_is_w != 0;
     const bool fast = p.hell2 && p.C <= 16;   // Hellinger-2 with or without category weights

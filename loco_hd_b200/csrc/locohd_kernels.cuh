@@ -142,6 +142,45 @@ struct __align__(16) ScoreTile {
     uint64_t out_first[kTileDim * kTileDim];    // index of the first score of job (r, c) in `out` (kTileNone: no job)
 };
 
+// Order of the units (tile, anchor) of a tile launch.  Tile-major order (all anchors of a tile, then the next tile)
+// re-reads an environment from DRAM for almost every tile it takes part in: the 8 structures of a tile hold 60 MB of
+// environments on the 1000-structure ensemble, so only the row structures survive in L2 from one tile to the next
+// (ncu: 459 B of DRAM reads per anchor pair, 29 x the algorithmic bytes of the step).  Sliced order: the anchors are
+// cut into slices of `slice` consecutive anchors and ALL tiles are visited for one slice before the next slice
+// starts; the environments of one slice of every structure (slice x 1.5 MB there) stay in L2 while the ~31 000
+// tiles pass over them, and every environment comes from DRAM once per launch.
+struct TileOrder {
+    uint64_t slice;       // anchors per slice (= n: one slice, tile-major order)
+    uint64_t per_slice;   // units of a full slice = n_tiles * slice
+    uint64_t full;        // units in full slices
+    uint64_t base_last;   // first anchor of the short last slice
+    uint64_t last;        // its anchors (0: n is a multiple of slice)
+};
+__host__ __device__ inline TileOrder make_tile_order(uint64_t n_tiles, uint64_t n, uint64_t slice) {
+    TileOrder o;
+    if (slice == 0 || slice > n) slice = n;
+    o.slice = slice;
+    o.per_slice = n_tiles * slice;
+    o.full = slice ? (n / slice) * o.per_slice : 0;
+    o.base_last = slice ? (n / slice) * slice : 0;
+    o.last = n - o.base_last;
+    return o;
+}
+template <class T>
+__host__ __device__ inline void tile_unit(const TileOrder& o, T u, T* tile, T* p) {
+    if (u < (T)o.full) {
+        const T s = u / (T)o.per_slice, r = u - s * (T)o.per_slice;
+        const T t = r / (T)o.slice;
+        *tile = t;
+        *p = s * (T)o.slice + (r - t * (T)o.slice);
+    } else {
+        const T r = u - (T)o.full;
+        const T t = r / (T)o.last;
+        *tile = t;
+        *p = (T)o.base_last + (r - t * (T)o.last);
+    }
+}
+
 struct ScoreArgs {
     const ScoreTile* tiles;        // tile mode (score_tile_kernel): jobs grouped by the host, uniform_n anchors each
     uint64_t n_tiles;
@@ -158,6 +197,7 @@ struct ScoreArgs {
     int only_unstaged;             // second pass: score only the pairs the fast kernel skipped
     int table_n;                   // sqrt / rsqrt table entries staged by the fast kernel
     int rep_n;                     // tile kernel: head entries of the count-indexed tables replicated per bank pair
+    TileOrder order;               // tile kernel: unit -> (tile, anchor), slice by slice (read from the parameter bank)
     unsigned long long* cursor;    // fast kernel: next unclaimed pair (zeroed before the launch); warps claim runs of
                                    // `run` consecutive pairs, so all resident warps work at one moving frontier
     unsigned run;                  // pairs per claim: kScoreRun for large launches, fewer when the launch has fewer

@@ -67,3 +67,25 @@ def test_product_never_imports_the_oracle():
         # the host layer carries no PyTorch (north_star): torch is bench / test plumbing only
         if path.suffix == ".py":
             assert not re.search(r"^\s*(from|import)\s+torch\b", text, re.M), f"{path} imports torch"
+
+
+def test_tile_unit_order_is_a_bijection():
+    """locohd_tile_unit (host-side query of the tile kernel's unit order; the same inline function the kernel uses, in
+    its 64-bit and 32-bit forms): every (tile, anchor) exactly once, slice by slice, for slices that divide the anchor
+    count, that leave a short last slice, that exceed it, and for the tile-major order (slice 0)."""
+    from loco_hd_b200 import _capi
+
+    for n_tiles, n, s in [(5, 37, 8), (5, 40, 8), (3, 10, 0), (3, 10, 16), (4, 203, 24), (1, 9, 8), (6, 16, 16), (2, 1, 8)]:
+        seen = [_capi.tile_unit(n_tiles, n, s, u) for u in range(n_tiles * n)]
+        assert len(set(seen)) == n_tiles * n and all(0 <= t < n_tiles and 0 <= p < n for t, p in seen)
+        if 0 < s < n:
+            # slice-major: the slice index never decreases, and within a slice the tile index never decreases
+            key = [(p // s, t) for t, p in seen]
+            assert key == sorted(key)
+            assert [p for t, p in seen[:s]] == list(range(s))   # a run of consecutive units = consecutive anchors of a tile
+        else:
+            assert seen == [(u // n, u % n) for u in range(n_tiles * n)]
+    assert _capi.tile_unit(31219, 5000, 16, 31219 * 16 + 5) == (0, 21)
+    assert _capi.tile_unit(2 ** 20, 5000, 16, 2 ** 20 * 16 * 7 + 16 * 3 + 2) == (3, 7 * 16 + 2)   # > 2^32 units: 64-bit form only
+    with pytest.raises(_capi.LocoHDError):
+        _capi.tile_unit(3, 10, 8, 30)

@@ -166,3 +166,38 @@ def test_tile_kernel_reports_unknown_categories(gpu_ctx, oracle_mod):
         gpu_ctx.score_jobs_stats(env, env, jobs, scores=True)
     assert ei.value.status == 3 and gpu_ctx.tile_launches > before
     env.close(); st.close()
+
+
+def test_sliced_unit_order_scores_the_same_units(gpu_ctx, oracle_mod, monkeypatch):
+    """The tile kernel visits all tiles for one slice of anchors before the next slice (environments of a slice stay in
+    L2; on the 1000-structure ensemble the library picks the slice from the store size).  Forced here on a small
+    ensemble: slices of 8, 24 and 200 anchors over 203 anchors (a short last slice of 3 / 11 anchors, runs that cross
+    tile boundaries), against the tile-major order bit for bit - the same units, only in another order - and the
+    oracle."""
+    base = synth.gen(31, 29, 7, 7)
+    assert base.n == 203
+    members = [synth.partner(base, 1.5, 900 + i) for i in range(12)]   # 12: the 66 structure pairs fill their tiles well enough
+    anchors = np.arange(base.n, dtype=np.uint32)
+    op = set_both(gpu_ctx, oracle_mod, 7, [("uniform", (3.0, 10.0))], tag_rule={"accept_same": False})
+    st, env = _resident(gpu_ctx, members, anchors, 10.0)
+    pairs = batch.blocked_pairs(len(members), 4)
+    jobs = np.array([(i * base.n, j * base.n, base.n) for i, j in pairs], dtype=JOB)
+    monkeypatch.setenv("LOCOHD_TILE_SLICE", "0")
+    before = gpu_ctx.tile_launches
+    plain = gpu_ctx.score_jobs_stats(env, env, jobs, scores=True, job_means=True)
+    assert gpu_ctx.tile_launches > before
+    want = np.stack([_oracle_scores(oracle_mod, op, members[i], members[j], anchors, anchors, 10.0) for i, j in pairs])
+    assert_scores_close(plain["scores"], want.ravel())
+    for s in ("8", "24", "200", "203", "1000"):
+        monkeypatch.setenv("LOCOHD_TILE_SLICE", s)
+        before = gpu_ctx.tile_launches
+        sliced = gpu_ctx.score_jobs_stats(env, env, jobs, scores=True, job_means=True)
+        assert gpu_ctx.tile_launches > before
+        assert np.array_equal(sliced["scores"], plain["scores"]), f"slice {s}"
+        assert np.array_equal(sliced["job_means"], plain["job_means"])
+    monkeypatch.delenv("LOCOHD_TILE_SLICE")
+    monkeypatch.setenv("LOCOHD_TILE_SLICE_MB", "0.25")       # the automatic choice, with a budget this store exceeds
+    auto = gpu_ctx.score_jobs_stats(env, env, jobs, scores=True)
+    assert np.array_equal(auto["scores"], plain["scores"])
+    monkeypatch.delenv("LOCOHD_TILE_SLICE_MB")
+    env.close(); st.close()
