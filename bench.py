@@ -272,6 +272,21 @@ def oracle_run_jobs(oracle, op, wl, job_ids, n_threads=0, collect=None):
     return pairs, time.perf_counter() - t0, steps, members
 
 
+def sample_parity(wl, ids, cpu_scores, gpu_results, means_only):
+    """max |CPU - GPU| over the jobs `ids` (the first len(ids) jobs of the step, as sample_jobs returns them):
+    cpu_scores[k] = the oracle's per-anchor scores of job ids[k]; gpu_results = the job means of the step (means_only)
+    or its per-anchor scores, job after job.  nan if the GPU results do not cover the sample."""
+    try:
+        if means_only:
+            return max(abs(float(sc.mean()) - float(gpu_results[j])) for j, sc in zip(ids, cpu_scores))
+        offs = np.concatenate([[0], np.cumsum(wl.jobs["n"][:len(ids)])]).astype(np.int64)
+        if offs[-1] > len(gpu_results):
+            return float("nan")
+        return max(float(np.abs(sc - gpu_results[offs[k]:offs[k + 1]]).max()) for k, sc in enumerate(cpu_scores))
+    except (IndexError, ValueError):
+        return float("nan")
+
+
 def sample_jobs(wl, target_pairs):
     ids, tot = [], 0
     for j in range(len(wl.jobs)):
@@ -718,11 +733,7 @@ def run_gpu(args, rank, local_rank, world):
         n0 = int(wl.jobs["n"][0])
         # ... and every job of the timed sample against this run's GPU results (on the default workload: the first 200
         # structure pairs = 13 tiles, all 5000 anchors of each, i.e. every anchor slice of the tile kernel's unit order)
-        if means_only:
-            sample_diff = max(abs(float(sc.mean()) - float(check_scores[j])) for j, sc in zip(ids, cpu_scores))
-        else:
-            offs = np.concatenate([[0], np.cumsum(wl.jobs["n"][:len(ids)])]).astype(np.int64)
-            sample_diff = max(float(np.abs(sc - check_scores[offs[k]:offs[k + 1]]).max()) for k, sc in enumerate(cpu_scores))
+        sample_diff = sample_parity(wl, ids, cpu_scores, check_scores, means_only)
         cpu = {"value": p / dt, "unit": "anchor-pairs/s", "cores": cores, "kind": "port",
                "sample": f"first {len(ids)} structure pair(s) of the step = {p} anchor pairs, {dt:.2f} s",
                "single_thread_value": p1 / dt1,

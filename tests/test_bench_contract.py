@@ -51,3 +51,41 @@ def test_reference_arm_other_ranks_stay_silent():
     res = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert res.returncode == 0, res.stderr[-2000:]
     assert res.stdout.strip() == ""
+
+
+def test_sample_parity_helper():
+    """bench.sample_parity (the GPU arm's check of every sampled job against the oracle) on a small ensemble, with the
+    oracle's own results standing in for the GPU's: 0 for identical results, the injected error otherwise, nan (not an
+    exception) when the results do not cover the sample."""
+    import importlib.util
+
+    import numpy as np
+
+    import oracle
+
+    spec = importlib.util.spec_from_file_location("_bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    oracle.build()
+    base = bench.synth.gen(9, 12, 8, 7)
+    # a small stand-in workload with the structure of the default one: every pair of 4 members, every primitive an anchor
+    clouds = [bench.synth.partner(base, 1.5, 3000 + i) for i in range(4)]
+    groups = [(s, np.arange(base.n)) for s in range(4)]
+    jobs = [(i, j) for i in range(4) for j in range(i + 1, 4)]
+    wl = bench.Workload("cfg5", "test", 7, ("uniform", (3.0, 10.0)), clouds, groups, jobs, scaling="strong", means_only=True)
+    op = bench.oracle_params(oracle, wl)
+    ids = bench.sample_jobs(wl, 3 * base.n)
+    assert ids == [0, 1, 2]
+    got = []
+    p, dt, steps, members = bench.oracle_run_jobs(oracle, op, wl, ids, n_threads=1, collect=got)
+    assert p == 3 * base.n and len(got) == 3 and all(len(g) == base.n for g in got)
+    means = np.array([g.mean() for g in got] + [0.0, 0.0, 0.0])
+    assert bench.sample_parity(wl, ids, got, means, True) == 0.0
+    means[2] += 1e-3
+    assert abs(bench.sample_parity(wl, ids, got, means, True) - 1e-3) < 1e-12
+    flat = np.concatenate(got)
+    assert bench.sample_parity(wl, ids, got, flat, False) == 0.0
+    flat[base.n + 5] += 2e-3
+    assert abs(bench.sample_parity(wl, ids, got, flat, False) - 2e-3) < 1e-12
+    assert np.isnan(bench.sample_parity(wl, ids, got, flat[: base.n], False))
+    assert np.isnan(bench.sample_parity(wl, ids, got, means[:1], True))
