@@ -127,3 +127,75 @@ def test_cuda_batch_path_against_exact_values(gpu_ctx):
         assert err <= GPU_TOL, f"case {c['id']}: batch path off the exact value by {err}"
         for h in (ea, eb, sa, sb):
             h.close()
+
+
+# ------------------------------------------------------------------------------------------ BASELINE configs[4] shape
+CFG5_FIX = Path(__file__).resolve().parent / "golden" / "highprec_cfg5.npz"
+
+
+def _cfg5():
+    import hashlib
+
+    from benchdata import synth
+
+    z = np.load(CFG5_FIX)
+    meta = json.loads(str(z["meta"]))
+    base = synth.config5_base()
+    need = sorted({i for pr in meta["pairs"] for i in pr})
+    members = {i: synth.config5_member(base, i) for i in need}
+    h = hashlib.sha256()
+    for i in need:
+        c = members[i]
+        h.update(np.ascontiguousarray(c.xyz).tobytes()); h.update(c.cat.tobytes()); h.update(c.tag.tobytes())
+    assert h.hexdigest() == meta["sha256"], "the seeded generator no longer reproduces the structures of the fixture"
+    return z, meta, base, members
+
+
+def test_oracle_against_exact_values_at_the_ensemble_shape(oracle_mod):
+    """Two full members of the 1000-structure ensemble (5000 primitives, ~380 merged events per anchor pair), the
+    configuration the headline number is measured on: oracle within 1e-14 of the 60-digit values."""
+    z, meta, base, members = _cfg5()
+    assert max(max(e) for e in meta["events"].values()) >= 500
+    p = oracle_mod.Params(7, [("uniform", [3.0, 10.0])], tag_rule={"accept_same": False})
+    an = np.stack([z["anchors"]] * 2, axis=1).astype(np.uint32)
+    for i, j in meta["pairs"]:
+        a, b = members[i], members[j]
+        got = oracle_mod.from_primitives(p, a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, an, 10.0)
+        assert np.abs(got - z[f"truth_{i}_{j}"]).max() <= 1e-14
+
+
+@pytest.mark.gpu
+def test_cuda_kernels_against_exact_values_at_the_ensemble_shape(gpu_ctx):
+    """The same exact values against (a) the one-call entry point (fused gather + one pair per warp) and (b) the tile
+    kernel: members 0..11 resident, all 66 structure pairs x 5000 anchors in blocked order - a 91 MB environment store,
+    so the units run in the sliced order - of which the fixture's 3 pairs x 32 anchors are compared."""
+    from benchdata import synth
+    from loco_hd_b200 import batch
+
+    z, meta, base, members = _cfg5()
+    anchors = z["anchors"]
+    an = np.stack([anchors] * 2, axis=1).astype(np.uint32)
+    gpu_ctx.set_params(7, (("uniform", (3.0, 10.0)),), None, ("Hellinger", (2.0,)), {"accept_same": False})
+    for i, j in meta["pairs"]:
+        a, b = members[i], members[j]
+        got = gpu_ctx.from_primitives(a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, an, 10.0)
+        assert np.abs(got - z[f"truth_{i}_{j}"]).max() <= GPU_TOL
+    clouds = [members.get(i) or synth.config5_member(base, i) for i in range(12)]
+    offs = np.cumsum([0] + [c.n for c in clouds]).astype(np.uint64)
+    st = gpu_ctx.structs_create(offs, np.concatenate([c.xyz for c in clouds]), np.concatenate([c.cat for c in clouds]),
+                                np.concatenate([c.tag for c in clouds]))
+    every = np.arange(base.n, dtype=np.uint32)
+    env = gpu_ctx.envset_build(st, np.tile(every, len(clouds)), 10.0,
+                               anchor_struct=np.repeat(np.arange(len(clouds), dtype=np.uint32), base.n))
+    pairs = batch.blocked_pairs(len(clouds), 4)
+    jobs = np.array([(i * base.n, j * base.n, base.n) for i, j in pairs],
+                    dtype=[("a_first", "<u8"), ("b_first", "<u8"), ("n", "<u8")])
+    before = gpu_ctx.tile_launches
+    res = gpu_ctx.score_jobs_stats(env, env, jobs, scores=True, job_means=True)
+    assert gpu_ctx.tile_launches > before, "the blocked job list of 12 members must take the tile kernel"
+    scores = res["scores"].reshape(len(pairs), base.n)
+    index = {tuple(p): k for k, p in enumerate(pairs.tolist())}
+    for i, j in meta["pairs"]:
+        assert np.abs(scores[index[(i, j)], anchors] - z[f"truth_{i}_{j}"]).max() <= GPU_TOL
+    assert np.abs(res["job_means"] - scores.mean(axis=1)).max() <= 1e-13
+    env.close(); st.close()
