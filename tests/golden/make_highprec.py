@@ -64,6 +64,12 @@ def sdist(name, q, a, b):
     if name == "Kullback-Leibler":
         return sum(x * mp.log((x + q[0]) / (y + q[0])) for x, y in zip(p1, p2))
     alpha, eps = q
+    if alpha == 1:        # statistical_distances.rs:36-38: the Kullback-Leibler limit
+        return sum(x * mp.log((x + eps) / (y + eps)) for x, y in zip(p1, p2))
+    if alpha == mp.inf:   # :42-51: log of the largest probability ratio
+        return mp.log(max((x + eps) / (y + eps) for x, y in zip(p1, p2)))
+    if alpha == 0:        # :55-64: minus log of the mass q puts where p is positive
+        return -mp.log(sum(y for x, y in zip(p1, p2) if x > 0))
     return mp.log(sum(x * ((x + eps) / (y + eps)) ** (alpha - 1) for x, y in zip(p1, p2))) / (alpha - 1)
 
 
@@ -97,8 +103,7 @@ def score(A, B, anchor, r, wf, sd, weights, accept_same):
     total, wprev = mp.mpf(0), cdf(*wf, mp.mpf(0))
     for d2, side, c in ev:
         wv = cdf(*wf, mp.sqrt(d2))
-        if wv != wprev:
-            total += (wv - wprev) * sdist(*sd, a, b)
+        total += (wv - wprev) * sdist(*sd, a, b)   # also when the weight is 0: 0 * inf = nan, as in the reference (locohd.rs:127-129)
         wprev = wv
         (a if side == 0 else b)[c] += w[c]
     return total + (cdf(*wf, mp.inf) - wprev) * sdist(*sd, a, b), len(ev)
@@ -115,8 +120,7 @@ def score_lists(sa, sb, da, db, wf, sd, weights):
     total, wprev = mp.mpf(0), cdf(*wf, mp.mpf(0))
     for d, side, c in ev:
         wv = cdf(*wf, d)
-        if wv != wprev:
-            total += (wv - wprev) * sdist(*sd, a, b)
+        total += (wv - wprev) * sdist(*sd, a, b)
         wprev = wv
         (a if side == 0 else b)[c] += w[c]
     return total + (cdf(*wf, mp.inf) - wprev) * sdist(*sd, a, b)
@@ -160,8 +164,11 @@ SDS = [("Hellinger", [2.0]), ("Hellinger", [3.5]), ("Kolmogorov-Smirnov", []), (
 def main():
     cases, arrays = [], {}
     k = 0
-    for wi, wf in enumerate(WFS):
-        for si, sd in enumerate(SDS):
+    # cases 36...: the special branches of the Renyi divergence (alpha = 1, +inf, 0); CPU checks only
+    special = [(WFS[0], ("Renyi", [1.0, 0.02])), (WFS[3], ("Renyi", [1.0, 0.02])), (WFS[0], ("Renyi", [float("inf"), 0.02])),
+               (WFS[2], ("Renyi", [float("inf"), 0.02])), (WFS[0], ("Renyi", [0.0, 0.0])), (WFS[1], ("Renyi", [0.0, 0.0]))]
+    for wf, sd in [(wf, sd) for wf in WFS for sd in SDS] + special:
+        for _ in (0,):
             # Hellinger-2 (the TMA-staged / tile kernels' arithmetic) gets the dense, protein-like cases
             rng = np.random.default_rng(7000 + k)
             C = int(rng.integers(3, 9))
