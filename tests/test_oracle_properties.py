@@ -16,7 +16,7 @@ def _cloud(rng, n, C, n_tags):
     return xyz, rng.integers(0, C, n).astype(np.uint16), rng.integers(0, n_tags, n).astype(np.uint32)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True, database=None)   # the same examples on every box
 @given(seed=st.integers(0, 2 ** 31), n=st.integers(2, 70), C=st.integers(1, 9), wf=st.integers(0, 3),
        sd=st.sampled_from([("Hellinger", [2.0]), ("Hellinger", [3.0]), ("Kolmogorov-Smirnov", [])]),
        rule=st.sampled_from([None, {"accept_same": False}, {"accept_same": True}]), thr=st.sampled_from([4.0, 7.5, 30.0]))
