@@ -272,6 +272,24 @@ def oracle_run_jobs(oracle, op, wl, job_ids, n_threads=0, collect=None):
     return pairs, time.perf_counter() - t0, steps, members
 
 
+def other_workload(name, args, ctx, local_rank, fp64_peak):
+    """One short run of another BASELINE configuration (N = 1 only): the `other_workloads` entry of the line."""
+    xa = argparse.Namespace(**vars(args))
+    if name == "cfg5":
+        xa.ensemble = 96
+    w2 = make_workload(name, 0, 1, xa)
+    steps = max(3, min(args.steps, 5))
+    r = measure(w2, ctx, local_rank, Solo(), steps, 3, args, clocks=False)
+    tot = max(sum(v[0] for v in r["prof"].values()), 1e-9)
+    return {"workload": w2.desc, "value": r["value"], "unit": "anchor-pairs/s",
+            "ms_per_step": r["step_ms"], "anchor_pairs_per_step": w2.n_pairs,
+            "e2e": r["e2e"], "gpu_launches": r["launches"],
+            "kernel_ms_per_step": {g: ms / steps for g, (ms, n) in r["prof"].items() if n},
+            "kernel_share": {g: ms / tot for g, (ms, n) in r["prof"].items() if n},
+            "roofline_step_frac_fp64": (r["f_walk"] + r["f_gather"]) / (r["step_ms"] * 1e-3) / 1e12 / fp64_peak,
+            "env_size_mean": float(r["sizes"].mean())}
+
+
 def sample_parity(wl, ids, cpu_scores, gpu_results, means_only):
     """max |CPU - GPU| over the jobs `ids` (the first len(ids) jobs of the step, as sample_jobs returns them):
     cpu_scores[k] = the oracle's per-anchor scores of job ids[k]; gpu_results = the job means of the step (means_only)
@@ -716,32 +734,35 @@ def run_gpu(args, rank, local_rank, world):
     cpu = None
     check_scores = m["check_scores"]
     if world == 1 and not args.no_cpu_baseline:
-        import oracle
+        try:
+            import oracle
 
-        oracle.build()
-        op = oracle_params(oracle, wl)
-        ids = sample_jobs(wl, args.cpu_pairs)   # ~10 s of CPU work on 16 threads
-        cores = host_threads()
-        oracle_run_jobs(oracle, op, wl, ids[:1], n_threads=cores)
-        cpu_scores = []
-        p, dt, steps, members = oracle_run_jobs(oracle, op, wl, ids, n_threads=cores, collect=cpu_scores)
-        ids1 = sample_jobs(wl, max(1, args.ref_pairs // 16))
-        p1, dt1, _, _ = oracle_run_jobs(oracle, op, wl, ids1, n_threads=1)
-        # the sample doubles as a parity spot check of this very run
-        a, b, anchors = wl.job_arrays(0)
-        ref = oracle.from_primitives(op, a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, wl.threshold)
-        n0 = int(wl.jobs["n"][0])
-        # ... and every job of the timed sample against this run's GPU results (on the default workload: the first 200
-        # structure pairs = 13 tiles, all 5000 anchors of each, i.e. every anchor slice of the tile kernel's unit order)
-        sample_diff = sample_parity(wl, ids, cpu_scores, check_scores, means_only)
-        cpu = {"value": p / dt, "unit": "anchor-pairs/s", "cores": cores, "kind": "port",
-               "sample": f"first {len(ids)} structure pair(s) of the step = {p} anchor pairs, {dt:.2f} s",
-               "single_thread_value": p1 / dt1,
-               "walk_steps_per_pair": steps / p, "env_members_per_pair": members / p,
-               ("max_abs_mean_score_diff_vs_gpu_job0" if means_only else "max_abs_score_diff_vs_gpu_job0"):
-                   float(abs(ref.mean() - check_scores[0]) if means_only else np.abs(ref - check_scores[:n0]).max()),
-               ("max_abs_mean_score_diff_vs_gpu_sample" if means_only else "max_abs_score_diff_vs_gpu_sample"): sample_diff,
-               "note": "C++/OpenMP restatement of the reference algorithm (Rust toolchain unavailable)"}
+            oracle.build()
+            op = oracle_params(oracle, wl)
+            ids = sample_jobs(wl, args.cpu_pairs)   # ~10 s of CPU work on 16 threads
+            cores = host_threads()
+            oracle_run_jobs(oracle, op, wl, ids[:1], n_threads=cores)
+            cpu_scores = []
+            p, dt, steps, members = oracle_run_jobs(oracle, op, wl, ids, n_threads=cores, collect=cpu_scores)
+            ids1 = sample_jobs(wl, max(1, args.ref_pairs // 16))
+            p1, dt1, _, _ = oracle_run_jobs(oracle, op, wl, ids1, n_threads=1)
+            # the sample doubles as a parity spot check of this very run
+            a, b, anchors = wl.job_arrays(0)
+            ref = oracle.from_primitives(op, a.xyz, a.cat, a.tag, b.xyz, b.cat, b.tag, anchors, wl.threshold)
+            n0 = int(wl.jobs["n"][0])
+            # ... and every job of the timed sample against this run's GPU results (on the default workload: the first 200
+            # structure pairs = 13 tiles, all 5000 anchors of each, i.e. every anchor slice of the tile kernel's unit order)
+            sample_diff = sample_parity(wl, ids, cpu_scores, check_scores, means_only)
+            cpu = {"value": p / dt, "unit": "anchor-pairs/s", "cores": cores, "kind": "port",
+                   "sample": f"first {len(ids)} structure pair(s) of the step = {p} anchor pairs, {dt:.2f} s",
+                   "single_thread_value": p1 / dt1,
+                   "walk_steps_per_pair": steps / p, "env_members_per_pair": members / p,
+                   ("max_abs_mean_score_diff_vs_gpu_job0" if means_only else "max_abs_score_diff_vs_gpu_job0"):
+                       float(abs(ref.mean() - check_scores[0]) if means_only else np.abs(ref - check_scores[:n0]).max()),
+                   ("max_abs_mean_score_diff_vs_gpu_sample" if means_only else "max_abs_score_diff_vs_gpu_sample"): sample_diff,
+                   "note": "C++/OpenMP restatement of the reference algorithm (Rust toolchain unavailable)"}
+        except Exception as exc:   # an optional section must not cost the headline line
+            cpu = {"error": repr(exc), "kind": "port"}
 
     # ---- the other BASELINE configurations, one short run each (N = 1 only), and the Python API
     others, py_api = None, None
@@ -750,21 +771,14 @@ def run_gpu(args, rank, local_rank, world):
         for name in ("cfg2", "cfg3", "cfg4", "cfg5"):
             if name == wl.name:
                 continue
-            xa = argparse.Namespace(**vars(args))
-            if name == "cfg5":
-                xa.ensemble = 96
-            w2 = make_workload(name, 0, 1, xa)
-            r = measure(w2, ctx, local_rank, Solo(), max(3, min(args.steps, 5)), 3, args, clocks=False)
-            tot = max(sum(v[0] for v in r["prof"].values()), 1e-9)
-            others[name] = {"workload": w2.desc, "value": r["value"], "unit": "anchor-pairs/s",
-                            "ms_per_step": r["step_ms"], "anchor_pairs_per_step": w2.n_pairs,
-                            "e2e": r["e2e"], "gpu_launches": r["launches"],
-                            "kernel_ms_per_step": {g: ms / max(3, min(args.steps, 5)) for g, (ms, n) in r["prof"].items() if n},
-                            "kernel_share": {g: ms / tot for g, (ms, n) in r["prof"].items() if n},
-                            "roofline_step_frac_fp64": (r["f_walk"] + r["f_gather"]) / (r["step_ms"] * 1e-3) / 1e12 / fp64_peak,
-                            "env_size_mean": float(r["sizes"].mean())}
-            del r, w2
-        py_api = python_api_latency(local_rank)
+            try:
+                others[name] = other_workload(name, args, ctx, local_rank, fp64_peak)
+            except Exception as exc:   # an optional section must not cost the headline line
+                others[name] = {"error": repr(exc)}
+        try:
+            py_api = python_api_latency(local_rank)
+        except Exception as exc:
+            py_api = {"error": repr(exc)}
 
     line = {
         "metric": "anchor_pairs_per_second", "value": m["value"], "unit": "anchor-pairs/s", "n_gpus": world,
