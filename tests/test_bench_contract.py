@@ -89,3 +89,30 @@ def test_sample_parity_helper():
     assert abs(bench.sample_parity(wl, ids, got, flat, False) - 2e-3) < 1e-12
     assert np.isnan(bench.sample_parity(wl, ids, got, flat[: base.n], False))
     assert np.isnan(bench.sample_parity(wl, ids, got, means[:1], True))
+
+
+def test_other_workload_entry_is_built_from_a_measurement(monkeypatch):
+    """bench.other_workload (the `other_workloads` entries of the GPU arm's line) with the device measurement replaced
+    by a canned result: the entry carries the keys the line documents."""
+    import argparse
+    import importlib.util
+
+    import numpy as np
+
+    spec = importlib.util.spec_from_file_location("_bench_mod2", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    seen = {}
+
+    def fake_measure(wl, ctx, local_rank, ranks, steps, warmup, args, clocks=True):
+        seen.update(name=wl.name, steps=steps, warmup=warmup, clocks=clocks, solo=type(ranks).__name__)
+        return {"value": 1.0e8, "step_ms": 2.0, "e2e": {"value": 9.0e7}, "launches": 12, "f_walk": 1.0e9, "f_gather": 1.0e8,
+                "prof": {"score": (6.0, 3), "fill": (3.0, 3), "unused": (0.0, 0)}, "sizes": np.array([100, 200])}
+
+    monkeypatch.setattr(bench, "measure", fake_measure)
+    args = argparse.Namespace(steps=20, warmup=5, pairs=1, models=2, frames=2, ensemble=1000)
+    out = bench.other_workload("cfg3", args, None, 0, 30.0)
+    assert seen == {"name": "cfg3", "steps": 5, "warmup": 3, "clocks": False, "solo": "Solo"}
+    assert out["value"] == 1.0e8 and out["anchor_pairs_per_step"] == 2 * 300 and out["gpu_launches"] == 12
+    assert out["kernel_ms_per_step"] == {"score": 1.2, "fill": 0.6} and abs(sum(out["kernel_share"].values()) - 1.0) < 1e-12
+    assert out["env_size_mean"] == 150.0 and out["roofline_step_frac_fp64"] > 0
